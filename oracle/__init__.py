@@ -1,0 +1,36 @@
+"""
+oracle/ -- CPU restatement of gordo's per-machine autoencoder anomaly path.
+
+THIS PACKAGE IS TEST INFRASTRUCTURE, NOT PRODUCT.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import it, and there only as the checker / the CPU arm that is timed beside the
+GPU.  Nothing under ``gordo_b200/`` imports it; the product fails loudly when the CUDA
+library is missing.
+
+What is restated (file:line are relative to the reference checkout, equinor/gordo @ 99a4819d):
+
+* ``factories.py``  -- gordo/machine/model/factories/utils.py:7-41 (hourglass_calc_dims),
+  feedforward_autoencoder.py:15-251, lstm_autoencoder.py:15-263 (topologies only).
+* ``dense.py``      -- the [3P] Keras 3.3.3 Dense forward / MSE / L1 activity regulariser /
+  Adam / ``Model.fit`` batching that gordo/machine/model/models.py:243-300 delegates to.
+* ``lstm.py``       -- the [3P] Keras LSTM cell + BPTT, gordo/machine/model/models.py:557-660
+  (primer step, ordered batches, 10 000-window predict) and :713-793 (windowing).
+* ``scaler.py``     -- [3P] sklearn MinMaxScaler (examples/config.yaml:75-82, diff.py:25).
+* ``anomaly.py``    -- gordo/machine/model/anomaly/diff.py:166-458 (fit, cross_validate,
+  thresholds, anomaly columns) and gordo/machine/model/utils.py:49-165 (frame layout).
+
+PARITY PIN STATUS
+-----------------
+pinned     : hourglass dims (reference golden vectors, tests/gordo/machine/model/
+             test_factories_utils.py:8-24 + docstrings), windowing (test_model.py:239-311),
+             anomaly columns / thresholds / frame layout: checked against the REAL
+             reference ``diff.py`` + ``model/utils.py`` imported here with TensorFlow stubbed
+             (tests/golden/make_golden.py wrote tests/golden/*.npz), MinMaxScaler /
+             TimeSeriesSplit against scikit-learn run here.
+UNPINNED   : Dense / LSTM forward values, loss history, Adam trajectories: TensorFlow, Keras
+             and scikeras cannot be installed in the build container (no network) and the
+             reference's tests hold no golden weight / output for any Keras model.  For
+             those the oracle restates the published Keras 3.3.3 algorithms; "parity
+             unpinned" -- see DESIGN.md.  The hand-written backward passes are cross-checked
+             against torch autograd on CPU (tests/test_oracle_grad.py).
+"""

@@ -1,0 +1,161 @@
+"""
+The oracle against the reference's own golden vectors and against outputs of the REAL
+reference code (tests/golden/make_golden.py).  CPU only.
+"""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import factories, lstm
+from oracle.scaler import MinMaxScaler, time_series_split
+from oracle.anomaly import DiffDetector, anomaly_frame, rolling_min_max
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+META = json.load(open(os.path.join(G, "golden_meta.json")))
+NPZ = np.load(os.path.join(G, "detector_golden.npz"))
+
+
+# reference golden vectors: tests/gordo/machine/model/test_factories_utils.py:8-24
+@pytest.mark.parametrize("args,expected", [
+    ((0.2, 4, 5), (4, 3, 2, 1)), ((0.5, 3, 10), (8, 7, 5)), ((0.5, 3, 3), (3, 2, 2)),
+    ((0.3, 3, 10), (8, 5, 3)), ((1, 3, 10), (10, 10, 10)), ((0, 3, 100000), (66667, 33334, 1))])
+def test_hourglass_reference_vectors(args, expected):
+    assert factories.hourglass_calc_dims(*args) == expected
+
+
+def test_hourglass_against_real_reference_grid():
+    for key, dims in META["hourglass"].items():
+        cf, el, n = key.split("|")
+        assert list(factories.hourglass_calc_dims(float(cf), int(el), int(n))) == dims, key
+
+
+def test_hourglass_docstring_topologies():
+    # feedforward_autoencoder.py:225-238
+    assert factories.feedforward_hourglass(10)["widths"] == [10, 8, 7, 5, 5, 7, 8, 10]
+    assert factories.feedforward_hourglass(5)["widths"] == [5, 4, 4, 3, 3, 4, 4, 5]
+    assert factories.feedforward_hourglass(10, compression_factor=0.2)["widths"] == [10, 7, 5, 2, 2, 5, 7, 10]
+    assert factories.feedforward_hourglass(10, encoding_layers=1)["widths"] == [10, 5, 5, 10]
+    # l1 activity regulariser on encoder layers i >= 1 only (:78-81)
+    assert factories.feedforward_hourglass(10)["l1"] == [0.0, 10e-5, 10e-5, 0.0, 0.0, 0.0, 0.0]
+    with pytest.raises(ValueError):
+        factories.hourglass_calc_dims(1.5, 3, 10)
+    with pytest.raises(ValueError):
+        factories.hourglass_calc_dims(0.5, 0, 10)
+    with pytest.raises(ValueError):
+        factories.feedforward_model(4, encoding_dim=(3, 2), encoding_func=("tanh",))
+
+
+def test_minmax_scaler_against_sklearn():
+    sc = MinMaxScaler().fit(NPZ["mm_in"])
+    np.testing.assert_allclose(sc.scale_, NPZ["mm_scale"], rtol=1e-13)
+    np.testing.assert_allclose(sc.min_, NPZ["mm_min"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(sc.transform(NPZ["mm_in"]), NPZ["mm_out"], rtol=1e-12, atol=1e-14)
+
+
+def test_time_series_split_against_sklearn():
+    for key, folds in META["time_series_split"].items():
+        n, k = map(int, key.split("|"))
+        got = [[int(tr[0]), int(tr[-1]), int(te[0]), int(te[-1])] for tr, te in time_series_split(n, k)]
+        assert got == folds, key
+
+
+# reference golden vectors: tests/gordo/machine/model/test_model.py:239-311
+def test_windowing_reference_vectors():
+    X = np.array([[0, 1], [2, 3], [4, 5], [6, 7], [8, 9]]); y = X.copy()
+    b = lstm.timeseries_batches(X, y, 2, 3, 0)
+    assert b[0][0].tolist() == [[[0, 1], [2, 3], [4, 5]], [[2, 3], [4, 5], [6, 7]]]
+    assert b[0][1].tolist() == [[4, 5], [6, 7]]
+    assert b[1][0].tolist() == [[[4, 5], [6, 7], [8, 9]]] and b[1][1].tolist() == [[8, 9]]
+    b = lstm.timeseries_batches(X, y, 2, 2, 1)
+    assert b[0][0].tolist() == [[[0, 1], [2, 3]], [[2, 3], [4, 5]]] and b[0][1].tolist() == [[4, 5], [6, 7]]
+    assert b[1][0].tolist() == [[[4, 5], [6, 7]]] and b[1][1].tolist() == [[8, 9]]
+    b = lstm.timeseries_batches(X, y, 2, 2, 2)
+    assert b[0][0].tolist() == [[[0, 1], [2, 3]], [[2, 3], [4, 5]]] and b[0][1].tolist() == [[6, 7], [8, 9]]
+    assert len(b) == 1                                   # "No more elements left"
+    with pytest.raises(ValueError):
+        lstm.window_index(1, 2, -1)
+    # docstring models.py:753-768: len(gen) == 9 for 100 rows, lookback 20, batch 10
+    assert len(lstm.timeseries_batches(np.zeros((100, 2)), np.zeros((100, 2)), 10, 20, 0)) == 9
+    # output length: tests/gordo/machine/model/test_model.py:324-338, builder offsets
+    # tests/gordo/builder/test_builder.py:99-115 (LSTM-AE L=10 -> 9, Forecast L=13 -> 13)
+    assert lstm.window_count(4, 3, 0) == 2
+    assert 100 - lstm.window_count(100, 10, 0) == 9 and 100 - lstm.window_count(100, 13, 1) == 13
+
+
+class _OffsetLinear:
+    """numpy twin of make_golden.OffsetLinear (OLS with intercept, drops leading rows)."""
+
+    def __init__(self, offset):
+        self.offset = offset
+
+    def fit(self, X, y):
+        A = np.hstack([np.asarray(X, float), np.ones((len(X), 1))])
+        self.coef, *_ = np.linalg.lstsq(A, np.asarray(y, float), rcond=None)
+        return self
+
+    def predict(self, X):
+        A = np.hstack([np.asarray(X, float), np.ones((len(X), 1))])
+        return (A @ self.coef)[self.offset:]
+
+
+@pytest.mark.parametrize("ci", range(len(META["cases"])))
+def test_detector_against_real_reference(ci):
+    case = META["cases"][ci]
+    pre = f"c{ci}_"
+    X, y = NPZ[pre + "X"], NPZ[pre + "y"]
+    det = DiffDetector(lambda tag: _OffsetLinear(case["offset"]), window=case["window"],
+                       smoothing_method=case["method"])
+    det.cross_validate(X, y)
+    det.fit(X, y)
+    res = det.anomaly(X, y)
+    tol = dict(rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(det.feature_thresholds_, NPZ[pre + "feature_thresholds"], **tol)
+    np.testing.assert_allclose(det.aggregate_threshold_, NPZ[pre + "aggregate_threshold"], **tol)
+    np.testing.assert_allclose(np.stack([det.feature_thresholds_per_fold_[f"fold-{i}"] for i in range(3)]),
+                               NPZ[pre + "feature_thresholds_per_fold"], **tol)
+    np.testing.assert_allclose([det.aggregate_thresholds_per_fold_[f"fold-{i}"] for i in range(3)],
+                               NPZ[pre + "aggregate_thresholds_per_fold"], **tol)
+    if case["window"] is not None:
+        np.testing.assert_allclose(det.smooth_feature_thresholds_, NPZ[pre + "smooth_feature_thresholds"], **tol)
+        np.testing.assert_allclose(det.smooth_aggregate_threshold_, NPZ[pre + "smooth_aggregate_threshold"], **tol)
+    assert case["n_rows"] == len(res["model-output"]) == case["n"] - case["offset"]
+    for grp in case["groups"]:
+        want = NPZ[pre + "col_" + grp]
+        got = np.asarray(res[grp], float)
+        if want.ndim == 2 and want.shape[1] == 1 and got.ndim == 1:
+            want = want[:, 0]
+        np.testing.assert_allclose(got, want, equal_nan=True, **tol)
+    # frame layout (model/utils.py:49-165 + the joins of diff.py)
+    tags = [f"tag-{j}" for j in range(case["t"])]
+    index = (pd.date_range("2019-01-01", periods=case["n"], freq="10min")
+             if case["index"] == "dates" else pd.RangeIndex(case["n"]))
+    frame = anomaly_frame(res, tags, index=index, frequency=pd.Timedelta(minutes=10))
+    assert [list(map(str, c)) for c in frame.columns] == case["columns"]
+    assert [None if s is None else str(s) for s in frame["start"].iloc[:3, 0].tolist()] == case["start"] \
+        if frame["start"].ndim == 2 else True
+    if case["index"] == "dates":
+        assert frame[("end", "")].iloc[:3].tolist() == case["end"]
+        assert frame[("start", "")].iloc[:3].tolist() == case["start"]
+
+
+def test_require_thresholds_error():
+    assert META["require_thresholds_raises"] is True
+    r = np.random.default_rng(5); X = r.random((50, 2))
+    det = DiffDetector(lambda tag: _OffsetLinear(0)).fit(X, X)
+    with pytest.raises(AttributeError):
+        det.anomaly(X, X)
+    DiffDetector(lambda tag: _OffsetLinear(0), require_thresholds=False).fit(X, X).anomaly(X, X)
+
+
+def test_rolling_min_max_matches_pandas():
+    r = np.random.default_rng(0)
+    for n in (3, 6, 7, 100):
+        x = r.random((n, 3))
+        want = pd.DataFrame(x).rolling(6).min().max().to_numpy()
+        np.testing.assert_allclose(rolling_min_max(x, 6), want, equal_nan=True)
+        w1 = pd.Series(x[:, 0]).rolling(6).min().max()
+        got = rolling_min_max(x[:, 0], 6)
+        assert (np.isnan(w1) and np.isnan(got)) or np.isclose(w1, got)
