@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""
+bench.py -- anomaly windows/sec of the fleet scoring hot path on N B200s (contract: see the task).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--machines M]
+
+Workload at N=1 (BASELINE.json configs[1], "c2"): 128 Machines x 50 tags x 100 000 timesteps,
+feed-forward hourglass autoencoder (50-42-33-25-25-33-42-50, tanh), bf16 tensor-core inference
+fused with DiffBasedAnomalyDetector scoring (all `.anomaly()` columns incl. confidences).
+A "step" = one pass of the fused scorer over every row of every Machine.  N>1: Machines are
+partitioned across ranks (128 per rank, weak scaling), no data-path collective.
+
+`value`  : windows/s with inputs resident in HBM (CUDA events around K launches).
+`e2e`    : same metric through FFFleet.anomaly_host(): pinned HOST buffers in, pinned HOST
+           columns out, H2D + kernel + D2H inside the timed region (chunked over 2 streams).
+`--impl reference`: the CPU arm = the oracle port of the reference path (Keras cannot be
+           installed offline), one Machine per host process on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_TAGS = 50
+N_ROWS = 100_000
+M_PER_GPU = 128
+SEED0 = 20260921          # Machine m uses default_rng(20260921 + m)
+METRIC = "anomaly_windows_per_sec"
+UNIT = "windows/s"
+
+
+def hourglass_widths(T, encoding_layers=3, cf=0.5):
+    import math
+    smallest = max(min(math.ceil(cf * T), T), 1)
+    slope = (T - smallest) / encoding_layers
+    dims = [round(T - i * slope) for i in range(1, encoding_layers + 1)]
+    return [T] + dims + dims[::-1] + [T]
+
+
+def machine_data(m, n_rows=N_ROWS, T=T_TAGS):
+    rng = np.random.default_rng(SEED0 + m)
+    return rng, rng.random((n_rows, T), dtype=np.float32)
+
+
+def machine_params(rng, widths):
+    parts = []
+    for a, b in zip(widths[:-1], widths[1:]):
+        lim = np.sqrt(6.0 / (a + b))
+        parts += [rng.uniform(-lim, lim, size=(a, b)).astype(np.float32).ravel(), np.zeros(b, np.float32)]
+    return np.concatenate(parts)
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_one_machine(m):
+    """The reference path for ONE Machine as the reference runs it: MinMax transform,
+    Keras-style predict in batches of 32, float64 pandas-equivalent scoring."""
+    from oracle import dense, factories
+    from oracle.scaler import MinMaxScaler
+    spec = factories.feedforward_hourglass(T_TAGS)
+    rng, X = machine_data(m)
+    params = dense.ff_unflatten(machine_params(rng, spec["widths"]), spec["widths"])
+    sx = MinMaxScaler().fit(X); sy = MinMaxScaler().fit(X)
+    ft = rng.uniform(0.1, 0.5, T_TAGS); at = rng.uniform(0.01, 0.1)
+    t0 = time.perf_counter()
+    yhat = dense.ff_predict(spec, params, sx.transform(X).astype(np.float32), batch_size=32)
+    d_s = np.abs(sy.transform(yhat) - sy.transform(X))
+    tot_s = np.square(d_s).mean(axis=1)
+    d_u = np.abs(yhat.astype(np.float64) - X)
+    tot_u = np.square(d_u).mean(axis=1)
+    conf = d_u / ft; tconf = tot_s / at
+    dt = time.perf_counter() - t0
+    return dt, float(tot_s.sum() + tot_u.sum() + conf[0, 0] + tconf[0])
+
+
+def cpu_arm(n_machines, n_procs):
+    """Time the oracle on n_machines Machines over n_procs processes -> (windows/s, seconds)."""
+    ms = list(range(n_machines))
+    t0 = time.perf_counter()
+    if n_procs <= 1:
+        for m in ms:
+            _cpu_one_machine(m)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(n_procs) as pool:
+            pool.map(_cpu_one_machine, ms, chunksize=1)
+    dt = time.perf_counter() - t0
+    return n_machines * N_ROWS / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = len(os.sched_getaffinity(0))
+    _cpu_one_machine(0)                                # calibrate: seconds per Machine on one core
+    t1 = time.perf_counter(); _cpu_one_machine(1); per_machine = time.perf_counter() - t1
+    # each step = a bounded sample sized for ~10 s: one Machine per process, all host cores
+    per_step = max(cores, int(min(M_PER_GPU * args.gpus, cores * max(1, round(10.0 / max(per_machine, 1e-3))))))
+    for _ in range(min(args.warmup, 1)):
+        cpu_arm(cores, cores)
+    vals, tot_t = [], 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_arm(per_step, cores)
+        vals.append(v); tot_t += dt
+    value = per_step * N_ROWS * args.steps / tot_t
+    sample = (f"{per_step} of {M_PER_GPU * args.gpus} Machines per step ({T_TAGS} tags x {N_ROWS} rows each), "
+              f"oracle port, one Machine per process, batch_size=32 predict")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": f"c2: {M_PER_GPU} Machines/GPU x {T_TAGS} tags x {N_ROWS} timesteps, feedforward_hourglass "
+                        f"AE 50-42-33-25-25-33-42-50 tanh, fused predict + DiffBasedAnomalyDetector.anomaly columns "
+                        f"(with thresholds/confidences)",
+            "machines": M_PER_GPU * n_gpus, "tags": T_TAGS, "rows_per_machine": N_ROWS,
+            "partition": f"machines round-robin over {n_gpus} GPU(s), no collective",
+            "io_dtype": "f32", "l2_policy": "inputs+outputs (>= 13 GB per pass) far exceed the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gordo_b200.fleet import FFFleet, FFTopology, Schedule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    M = args.machines or M_PER_GPU
+    widths = hourglass_widths(T_TAGS)
+    acts = ["tanh"] * (len(widths) - 2) + ["linear"]
+    l1 = [0.0] + [1e-4] * 2 + [0.0] * 4
+    topo = FFTopology(widths, acts, l1)
+    fleet = FFFleet(topo, M, dev)
+    sched = Schedule([N_ROWS] * M)
+    R = M * N_ROWS
+
+    # ---- synthetic inputs in pinned host memory (this rank's Machines: global ids rank, rank+world, ...)
+    x_host = torch.empty((R, T_TAGS), dtype=torch.float32, pin_memory=True)
+    xh = x_host.numpy()
+    params = np.empty((M, topo.n_params), np.float32)
+    ft = np.empty((M, T_TAGS), np.float32); at = np.empty((M,), np.float32)
+    for i in range(M):
+        rng, X = machine_data(rank + i * world)
+        xh[i * N_ROWS:(i + 1) * N_ROWS] = X
+        params[i] = machine_params(rng, widths)
+        ft[i] = rng.uniform(0.1, 0.5, T_TAGS); at[i] = rng.uniform(0.01, 0.1)
+    fleet.set_params(torch.from_numpy(params))
+    x_dev = x_host.to(dev, non_blocking=True)
+    lo = torch.arange(M, device=dev, dtype=torch.int64) * N_ROWS
+    fleet.in_scale, fleet.in_min = FFFleet.minmax_fit(x_dev, lo, lo + N_ROWS)
+    fleet.err_scale = fleet.in_scale.clone()
+    fleet.feat_thr = torch.from_numpy(ft).to(dev); fleet.agg_thr = torch.from_numpy(at).to(dev)
+    out = fleet.score(sched, x_dev, precision=args.precision)          # allocates the result columns once
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K launches between two events on the launching stream
+    for _ in range(args.warmup):
+        fleet.score(sched, x_dev, precision=args.precision, out=out)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fleet.score(sched, x_dev, precision=args.precision, out=out)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # the other precision, for the record (not the headline)
+    other = "f32" if args.precision == "bf16" else "bf16"
+    fleet.score(sched, x_dev, precision=other, out=out); torch.cuda.synchronize()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record(); fleet.score(sched, x_dev, precision=other, out=out); o1.record(); torch.cuda.synchronize()
+    ms_other = o0.elapsed_time(o1)
+    fleet.score(sched, x_dev, precision=args.precision, out=out)
+
+    # ---- end to end through the host-buffer API (H2D + kernel + D2H every step)
+    pipe = fleet.host_pipeline(sched, n_chunks=8, precision=args.precision)
+    e2e_steps = max(1, min(args.steps, 3))
+    pipe.run(x_host)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        host_out = pipe.run(x_host)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1) / e2e_steps
+    clocks = sampler.stop()
+    checksum = float(host_out["total-anomaly-scaled"][:1000].double().sum())
+
+    ms_step = ms_total / args.steps
+    times = torch.tensor([ms_step, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e = float(times[0]), float(times[1])
+    windows = R * world
+    value = windows / (ms_step * 1e-3)
+    e2e_value = windows / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_per_window = 4 * T_TAGS + 4 * (3 * T_TAGS + 2) + 4 * (T_TAGS + 1)
+        achieved = R * bytes_per_window / (ms_total / args.steps * 1e-3) / 1e9       # this rank's kernel
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ff_score_tc_bytes_per_launch")
+        except Exception:
+            pass
+        cpu_v, cpu_dt = cpu_arm(args.cpu_machines, 1) if args.cpu_machines > 0 else (None, 0.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes * world,
+                    "d2h_bytes_per_step": pipe.d2h_bytes * world, "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "api": "FFFleet.host_pipeline().run(pinned host X) -> pinned host columns"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "kernel": "ff_score_tc_kernel" if args.precision == "bf16" else "ff_score_f32_kernel",
+                         "algorithmic_bytes_per_window": bytes_per_window},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{args.cpu_machines} Machine(s) of the same workload, {cpu_dt:.1f} s, oracle "
+                                       f"port run as the reference runs it (one Machine at a time, predict batch 32)"},
+            "clocks": clocks,
+            "other_precision": {"precision": other, "ms_per_step": ms_other, "value": R / (ms_other * 1e-3)},
+            "checksum": checksum,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--machines", type=int, default=0, help="Machines per GPU (default 128)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-machines", type=int, default=4, help="Machines in the cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,101 @@
+// Internal helpers shared by the sm_100a kernels of libgordo_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/gordo_b200.h"
+
+#define GB_OK 0
+#define GB_ERR_ARG -1
+#define GB_ERR_CUDA -2
+#define GB_ERR_UNSUPPORTED -3
+
+void gb_set_error(const char* fmt, ...);
+
+#define GB_CUDA_CHECK(expr)                                                         \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            gb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr,               \
+                         cudaGetErrorString(_e));                                   \
+            return GB_ERR_CUDA;                                                     \
+        }                                                                           \
+    } while (0)
+
+#define GB_REQUIRE(cond, ...)                                                       \
+    do {                                                                            \
+        if (!(cond)) { gb_set_error(__VA_ARGS__); return GB_ERR_ARG; }              \
+    } while (0)
+
+struct gb200_fleet {
+    int32_t n_machines;
+    int64_t rows_total;
+    int32_t tiles_total;        // 128-row tiles over all machines
+    int64_t* d_row_lo;          // [M] first row of each Machine
+    int64_t* d_row_hi;          // [M] one past the last row
+    int32_t* d_tile_off;        // [M+1] prefix of ceil(rows/128)
+    int64_t* h_row_lo;          // host copies
+    int64_t* h_row_hi;
+    int32_t* h_tile_off;
+    int sm_count;
+};
+
+// ---------------------------------------------------------------- activations (precise fp32)
+__device__ __forceinline__ float gb_act(int code, float z) {
+    switch (code) {
+        case GB200_ACT_TANH:     return tanhf(z);
+        case GB200_ACT_RELU:     return fmaxf(z, 0.0f);
+        case GB200_ACT_SIGMOID:  return 1.0f / (1.0f + expf(-z));
+        case GB200_ACT_ELU:      return z > 0.0f ? z : expm1f(z);
+        case GB200_ACT_SOFTPLUS: return z > 0.0f ? z + log1pf(expf(-z)) : log1pf(expf(z));
+        default:                 return z;
+    }
+}
+// d act / dz given pre-activation z and output h
+__device__ __forceinline__ float gb_act_grad(int code, float z, float h) {
+    switch (code) {
+        case GB200_ACT_TANH:     return 1.0f - h * h;
+        case GB200_ACT_RELU:     return z > 0.0f ? 1.0f : 0.0f;
+        case GB200_ACT_SIGMOID:  return h * (1.0f - h);
+        case GB200_ACT_ELU:      return z > 0.0f ? 1.0f : h + 1.0f;
+        case GB200_ACT_SOFTPLUS: return 1.0f / (1.0f + expf(-z));
+        default:                 return 1.0f;
+    }
+}
+
+static inline int gb_round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ __forceinline__ int gb_round_up_dev(int x, int m) { return (x + m - 1) / m * m; }
+
+// launchers implemented in the individual .cu files
+int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, const float* params,
+                           const float* in_scale, const float* in_min, const float* err_scale,
+                           const float* feat_thr, const float* agg_thr, const float* x, const float* y,
+                           float* model_out, float* tag_scaled, float* tag_unscaled,
+                           float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
+                           cudaStream_t stream);
+int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const void* packed,
+                          const float* in_scale, const float* in_min, const float* err_scale,
+                          const float* feat_thr, const float* agg_thr, const float* x, const float* y,
+                          float* model_out, float* tag_scaled, float* tag_unscaled,
+                          float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
+                          cudaStream_t stream);
+int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch);
+int gb_launch_ff_pack_bf16(const gb200_ff_arch* arch, int n_machines, const float* params, void* packed,
+                           cudaStream_t stream);
+int gb_launch_minmax_fit(int n_jobs, const int64_t* lo, const int64_t* hi, const float* x, int n_tags,
+                         float* scale, float* min_, cudaStream_t stream);
+int gb_launch_rolling_min_max(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v,
+                              int n_cols, int window, float* out, cudaStream_t stream);
+int gb_launch_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int n_jobs,
+                     const int64_t* lo, const int64_t* hi, const int32_t* scale_slot,
+                     const float* in_scale, const float* in_min, const float* x, const float* y,
+                     const int64_t* perm_off, const int32_t* perm_pool, int epochs, int batch_size,
+                     int l1_mean, float* params, float* adam_mv, int64_t* adam_t, float* hist_loss,
+                     float* hist_acc, cudaStream_t stream);
+int gb_launch_score_outputs(int n_machines, const int64_t* out_row_off, const int64_t* y_row_off,
+                            int n_tags, const float* model_out, const float* y, const float* err_scale,
+                            const float* feat_thr, const float* agg_thr, float* tag_scaled,
+                            float* tag_unscaled, float* total_scaled, float* total_unscaled,
+                            float* conf, float* total_conf, cudaStream_t stream);

@@ -1,0 +1,207 @@
+// ff_score_f32: fp32 fused  MinMax-scale -> Dense stack -> DiffBasedAnomalyDetector columns.
+//
+// The exact-arithmetic path (GB200_PREC_F32): plain fp32 FMAs in the reference's operation order
+// (x*scale+min, z = h.W + b, act, |yhat - y| ...), any topology up to GB200_MAX_LAYERS layers.
+// Work unit = (Machine, 128-row tile); one thread owns one row; the Machine's weights are staged
+// once per CTA in shared memory (padded to 8-float rows for 128-bit broadcast loads) when they
+// fit, otherwise streamed through L1/L2.  Replaces models.py:289-300 + diff.py:336-444.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;
+
+struct ScoreArgs {
+    gb200_ff_arch arch;
+    const int64_t* row_lo; const int64_t* row_hi;
+    const int32_t* tile_off;
+    int n_machines;
+    int tiles_total;
+    int64_t n_params;
+    const float* params;
+    const float* in_scale; const float* in_min; const float* err_scale;
+    const float* feat_thr; const float* agg_thr;
+    const float* x; const float* y;
+    float* model_out; float* tag_scaled; float* tag_unscaled;
+    float* total_scaled; float* total_unscaled; float* conf; float* total_conf;
+    int max_w;            // max layer width
+    int smem_w_floats;    // padded weight image size (0 = weights stay in global)
+};
+
+__device__ __forceinline__ int find_machine(const int32_t* tile_off, int n, int tile) {
+    int lo = 0, hi = n;                       // largest m with tile_off[m] <= tile
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool SMEM_W>
+__global__ void __launch_bounds__(TILE)
+ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* act0 = smem;                               // [max_w][TILE]
+    float* act1 = act0 + (size_t)a.max_w * TILE;      // [max_w][TILE]
+    float* wsm  = act1 + (size_t)a.max_w * TILE;      // padded weights (SMEM_W)
+    __shared__ int s_m;
+
+    const int tid = threadIdx.x;
+    const int L = a.arch.n_layers;
+    const int T_in = a.arch.widths[0], T_out = a.arch.widths[L];
+    int cur_m = -1;
+
+    // contiguous tile range per CTA: a CTA re-stages weights only when it crosses a Machine boundary
+    const int per_cta = (a.tiles_total + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per_cta;
+    const int t_end = min(t_begin + per_cta, a.tiles_total);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        if (tid == 0) s_m = find_machine(a.tile_off, a.n_machines, tile);
+        __syncthreads();
+        const int m = s_m;
+        const float* P = a.params + (size_t)m * a.n_params;
+        if (SMEM_W && m != cur_m) {
+            // stage this Machine's weights: layer l -> W padded [in][ldw] then bias [ldw]
+            int so = 0; int64_t go = 0;
+            for (int l = 0; l < L; ++l) {
+                const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
+                const int ldw = (wout + 7) & ~7;
+                for (int i = tid; i < win * ldw; i += TILE) {
+                    int k = i / ldw, n = i - k * ldw;
+                    wsm[so + i] = n < wout ? P[go + (int64_t)k * wout + n] : 0.0f;
+                }
+                so += win * ldw; go += (int64_t)win * wout;
+                for (int i = tid; i < ldw; i += TILE) wsm[so + i] = i < wout ? P[go + i] : 0.0f;
+                so += ldw; go += wout;
+            }
+            cur_m = m;
+        }
+        const int64_t row = a.row_lo[m] + (int64_t)(tile - a.tile_off[m]) * TILE + tid;
+        const bool valid = row < a.row_hi[m];
+
+        // ---- input: MinMaxScaler.transform in fp32
+        {
+            const float* sc = a.in_scale ? a.in_scale + (size_t)m * T_in : nullptr;
+            const float* mn = a.in_min ? a.in_min + (size_t)m * T_in : nullptr;
+            const float* xr = a.x + row * T_in;
+            for (int k = 0; k < T_in; ++k) {
+                float v = valid ? xr[k] : 0.0f;
+                if (sc) v = fmaf(v, sc[k], mn[k]);
+                act0[k * TILE + tid] = v;
+            }
+        }
+        __syncthreads();            // weights staged (and s_m consumed)
+
+        float* hin = act0; float* hout = act1;
+        int so = 0; int64_t go = 0;
+        for (int l = 0; l < L; ++l) {
+            const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
+            const int code = a.arch.acts[l];
+            const int ldw = (wout + 7) & ~7;
+            const float* W; const float* B;
+            if (SMEM_W) { W = wsm + so; B = W + win * ldw; so += win * ldw + ldw; }
+            else        { W = P + go;   B = W + (int64_t)win * wout; go += (int64_t)win * wout + wout; }
+            for (int n0 = 0; n0 < wout; n0 += 8) {
+                float acc[8];
+                if (SMEM_W) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(B + n0);
+                    const float4 b1 = *reinterpret_cast<const float4*>(B + n0 + 4);
+                    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+                    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+                    #pragma unroll 4
+                    for (int k = 0; k < win; ++k) {
+                        const float h = hin[k * TILE + tid];
+                        const float4 w0 = *reinterpret_cast<const float4*>(W + k * ldw + n0);
+                        const float4 w1 = *reinterpret_cast<const float4*>(W + k * ldw + n0 + 4);
+                        acc[0] = fmaf(h, w0.x, acc[0]); acc[1] = fmaf(h, w0.y, acc[1]);
+                        acc[2] = fmaf(h, w0.z, acc[2]); acc[3] = fmaf(h, w0.w, acc[3]);
+                        acc[4] = fmaf(h, w1.x, acc[4]); acc[5] = fmaf(h, w1.y, acc[5]);
+                        acc[6] = fmaf(h, w1.z, acc[6]); acc[7] = fmaf(h, w1.w, acc[7]);
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = (n0 + j < wout) ? __ldg(B + n0 + j) : 0.0f;
+                    for (int k = 0; k < win; ++k) {
+                        const float h = hin[k * TILE + tid];
+                        const float* wr = W + (int64_t)k * wout + n0;
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (n0 + j < wout) acc[j] = fmaf(h, __ldg(wr + j), acc[j]);
+                    }
+                }
+                #pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n0 + j < wout) hout[(n0 + j) * TILE + tid] = gb_act(code, acc[j]);
+            }
+            float* t = hin; hin = hout; hout = t;     // each thread reads only its own column
+        }
+
+        // ---- epilogue: DiffBasedAnomalyDetector columns (diff.py:350-444)
+        if (valid) {
+            const float* yr = (a.y ? a.y : a.x) + row * T_out;
+            const float* es = a.err_scale ? a.err_scale + (size_t)m * T_out : nullptr;
+            const float* ft = a.feat_thr ? a.feat_thr + (size_t)m * T_out : nullptr;
+            float ss = 0.0f, su = 0.0f;
+            for (int j = 0; j < T_out; ++j) {
+                const float yh = hin[j * TILE + tid];
+                const float d = fabsf(yh - yr[j]);
+                const float s = es ? d * fabsf(es[j]) : d;
+                su = fmaf(d, d, su); ss = fmaf(s, s, ss);
+                const int64_t o = row * T_out + j;
+                if (a.model_out) a.model_out[o] = yh;
+                if (a.tag_unscaled) a.tag_unscaled[o] = d;
+                if (a.tag_scaled) a.tag_scaled[o] = s;
+                if (a.conf && ft) a.conf[o] = d / ft[j];
+            }
+            const float ts = ss / (float)T_out, tu = su / (float)T_out;
+            if (a.total_scaled) a.total_scaled[row] = ts;
+            if (a.total_unscaled) a.total_unscaled[row] = tu;
+            if (a.total_conf && a.agg_thr) a.total_conf[row] = ts / a.agg_thr[m];
+        }
+        __syncthreads();            // act buffers / s_m reused by the next tile
+    }
+}
+
+}  // namespace
+
+int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, const float* params,
+                           const float* in_scale, const float* in_min, const float* err_scale,
+                           const float* feat_thr, const float* agg_thr, const float* x, const float* y,
+                           float* model_out, float* tag_scaled, float* tag_unscaled,
+                           float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
+                           cudaStream_t stream) {
+    ScoreArgs a{};
+    a.arch = *arch;
+    a.row_lo = f->d_row_lo; a.row_hi = f->d_row_hi; a.tile_off = f->d_tile_off;
+    a.n_machines = f->n_machines; a.tiles_total = f->tiles_total;
+    a.n_params = gb200_ff_param_count(arch);
+    a.params = params; a.in_scale = in_scale; a.in_min = in_min; a.err_scale = err_scale;
+    a.feat_thr = feat_thr; a.agg_thr = agg_thr; a.x = x; a.y = y;
+    a.model_out = model_out; a.tag_scaled = tag_scaled; a.tag_unscaled = tag_unscaled;
+    a.total_scaled = total_scaled; a.total_unscaled = total_unscaled;
+    a.conf = conf; a.total_conf = total_conf;
+    int max_w = 0, wfloats = 0;
+    for (int l = 0; l <= arch->n_layers; ++l) max_w = arch->widths[l] > max_w ? arch->widths[l] : max_w;
+    for (int l = 0; l < arch->n_layers; ++l) {
+        int ldw = gb_round_up(arch->widths[l + 1], 8);
+        wfloats += arch->widths[l] * ldw + ldw;
+    }
+    a.max_w = max_w;
+    if (f->tiles_total == 0) return GB_OK;
+    const size_t act_bytes = (size_t)2 * max_w * TILE * sizeof(float);
+    const size_t smem_cap = 227 * 1024 - 64;
+    GB_REQUIRE(act_bytes <= smem_cap, "ff_score_f32: layer width %d too large for the fp32 kernel", max_w);
+    const bool smem_w = act_bytes + (size_t)wfloats * sizeof(float) <= smem_cap;
+    a.smem_w_floats = smem_w ? wfloats : 0;
+    const size_t smem = act_bytes + (smem_w ? (size_t)wfloats * sizeof(float) : 0);
+    auto kern = smem_w ? ff_score_f32_kernel<true> : ff_score_f32_kernel<false>;
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    GB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = f->sm_count * per_sm;
+    if (grid > f->tiles_total) grid = f->tiles_total;
+    kern<<<grid, TILE, smem, stream>>>(a);
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
+}

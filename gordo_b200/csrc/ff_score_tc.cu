@@ -1,0 +1,520 @@
+// ff_score_tc: the Blackwell-native scorer (GB200_PREC_BF16_TC).
+//
+//   MinMax-scale -> 2E+1 chained Dense layers on tcgen05 tensor cores -> anomaly columns,
+// one 128-row tile of one Machine at a time per warpgroup, everything between the HBM read of the
+// tile and the HBM write of the result columns stays on chip.
+//
+// Structure (one persistent CTA per SM, NWG warpgroups = NWG independent "tile engines"):
+//   * the Machine's operand image (bf16 weights pre-packed in the tcgen05 canonical K-major
+//     no-swizzle layout + fp32 biases) is brought in once per CTA per Machine with ONE 1-D bulk
+//     async copy (cp.async.bulk -> UBLKCP, mbarrier complete_tx);
+//   * each warpgroup: bulk-copies its [128 x T] fp32 tile (a tile of consecutive rows of a
+//     row-major matrix is one contiguous run in HBM), builds the bf16 A operand in shared memory
+//     (thread = row = TMEM lane), then for every layer one elected thread issues Kp/16
+//     tcgen05.mma (M=128, N=Np, K=16, fp32 accumulate in TMEM) + tcgen05.commit; all 128
+//     threads pull the accumulator back with tcgen05.ld (32x32b.x16), add bias, apply the
+//     activation and write the next layer's A operand;
+//   * final epilogue: |yhat - y| is written IN PLACE over the y tile, the row totals are reduced in
+//     registers, and the tile goes back to HBM as full-row contiguous runs (tag-anomaly-unscaled,
+//     and, scaled per column on the way out, tag-anomaly-scaled and anomaly-confidence); yhat then
+//     overwrites the tile and is copied out the same way.
+// Algorithmic HBM traffic per row: 4*T_in read + 4*(3*T_out + 2) written (+4*(T_out+1) with
+// thresholds); weights are amortised over ~780 tiles per Machine.
+//
+// Replaces models.py:289-300 + diff.py:336-444.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int WG_THREADS = 128;
+constexpr int MAX_WG = 4;
+
+// ---------------------------------------------------------------- packed operand image
+struct PackLayout {
+    int n_layers;
+    int Kp[GB200_MAX_LAYERS], Np[GB200_MAX_LAYERS];
+    int w_off[GB200_MAX_LAYERS];     // byte offset of layer l's B operand
+    int b_off[GB200_MAX_LAYERS];     // byte offset of layer l's bias (fp32 [Np])
+    int total_bytes;                 // multiple of 16
+    int max_Kp, max_Np;
+};
+
+PackLayout make_layout(const gb200_ff_arch* a) {
+    PackLayout p{};
+    p.n_layers = a->n_layers;
+    int off = 0;
+    for (int l = 0; l < a->n_layers; ++l) {
+        p.Kp[l] = gb_round_up(a->widths[l], 16);
+        p.Np[l] = gb_round_up(a->widths[l + 1], 16);
+        p.w_off[l] = off; off += p.Kp[l] * p.Np[l] * 2;
+        if (p.Kp[l] > p.max_Kp) p.max_Kp = p.Kp[l];
+        if (p.Np[l] > p.max_Np) p.max_Np = p.Np[l];
+    }
+    for (int l = 0; l < a->n_layers; ++l) { p.b_off[l] = off; off += p.Np[l] * 4; }
+    p.total_bytes = gb_round_up(off, 16);
+    return p;
+}
+
+__global__ void pack_bf16_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_params,
+                                 const float* __restrict__ params, uint8_t* __restrict__ packed) {
+    const int m = blockIdx.x;
+    const float* P = params + (size_t)m * n_params;
+    uint8_t* out = packed + (size_t)m * lay.total_bytes;
+    int64_t go = 0;
+    for (int l = 0; l < arch.n_layers; ++l) {
+        const int win = arch.widths[l], wout = arch.widths[l + 1];
+        const int Kp = lay.Kp[l], Np = lay.Np[l];
+        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(out + lay.w_off[l]);
+        // canonical K-major, no swizzle: element (n, k) at
+        //   (k/8) * (Np/8)*64 + (n/8)*64 + (n%8)*8 + (k%8)      [bf16 elements]
+        for (int i = threadIdx.x; i < Kp * Np; i += blockDim.x) {
+            const int k = i / Np, n = i - k * Np;
+            const float w = (k < win && n < wout) ? P[go + (int64_t)k * wout + n] : 0.0f;
+            B[(k >> 3) * (Np >> 3) * 64 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
+        }
+        go += (int64_t)win * wout;
+        float* bias = reinterpret_cast<float*>(out + lay.b_off[l]);
+        for (int i = threadIdx.x; i < Np; i += blockDim.x) bias[i] = i < wout ? P[go + i] : 0.0f;
+        go += wout;
+    }
+}
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        // a barrier that never completes is a bug (lost TMA / MMA completion): fail loudly
+        // instead of hanging the device (each failed try_wait already sleeps in hardware)
+        if (!done && ++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: canonical K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (K-adjacent core matrices) | SBO>>4 [32,46) (8-row groups)
+// | version=1 [46,48) | layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1,
+// B=bf16 [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_fast(int code, float z) {
+    switch (code) {
+        case GB200_ACT_TANH: { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z)); return r; }
+        case GB200_ACT_RELU: return fmaxf(z, 0.0f);
+        case GB200_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-z));
+        case GB200_ACT_ELU: return z > 0.0f ? z : __expf(z) - 1.0f;
+        case GB200_ACT_SOFTPLUS: return z > 15.0f ? z : __logf(1.0f + __expf(z));
+        default: return z;
+    }
+}
+
+struct TcArgs {
+    gb200_ff_arch arch;
+    PackLayout lay;
+    const int64_t* row_lo; const int64_t* row_hi; const int32_t* tile_off;
+    int n_machines, tiles_total;
+    const uint8_t* packed;
+    const float* in_scale; const float* in_min; const float* err_scale;
+    const float* feat_thr; const float* agg_thr;
+    const float* x; const float* y;
+    float* model_out; float* tag_scaled; float* tag_unscaled;
+    float* total_scaled; float* total_unscaled; float* conf; float* total_conf;
+    int nwg;                 // warpgroups per CTA
+    int tmem_cols_wg;        // accumulator columns per warpgroup
+    int tmem_cols_total;     // power of two >= 32
+    int xtile_bytes;         // 128*T_in*4 rounded to 16
+    int ytile_bytes;         // 0 when y aliases x
+    int abuf_bytes;          // 128*max_Kp*2
+    int vec_floats;          // per-Machine vectors: in_scale,in_min [T_in], |es|, ft [T_out]
+};
+
+__device__ __forceinline__ int find_machine(const int32_t* tile_off, int n, int tile) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tile_off[mid] <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// Copy one warp's rows (cnt floats, contiguous in smem and in HBM) out, optionally transforming
+// by a per-column factor.  MODE 0: copy, 1: * vec[col], 2: / vec[col].
+template <int MODE>
+__device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const float* __restrict__ src, int cnt,
+                                              int T, const float* __restrict__ vec, int lane, bool vec16) {
+    if (vec16) {
+        int col = (lane * 4) % T;
+        const int step = 128 % T;
+        for (int o = lane * 4; o < cnt; o += 128) {
+            float4 v = *reinterpret_cast<const float4*>(src + o);
+            if (MODE != 0) {
+                int c0 = col, c1 = c0 + 1 == T ? 0 : c0 + 1, c2 = c1 + 1 == T ? 0 : c1 + 1, c3 = c2 + 1 == T ? 0 : c2 + 1;
+                if (T < 4) { c0 = o % T; c1 = (o + 1) % T; c2 = (o + 2) % T; c3 = (o + 3) % T; }
+                if (MODE == 1) { v.x *= vec[c0]; v.y *= vec[c1]; v.z *= vec[c2]; v.w *= vec[c3]; }
+                else { v.x = v.x / vec[c0]; v.y = v.y / vec[c1]; v.z = v.z / vec[c2]; v.w = v.w / vec[c3]; }
+                col += step; if (col >= T) col -= T;
+            }
+            *reinterpret_cast<float4*>(dst + o) = v;
+        }
+    } else {
+        for (int o = lane; o < cnt; o += 32) {
+            float v = src[o];
+            if (MODE == 1) v *= vec[o % T];
+            if (MODE == 2) v = v / vec[o % T];
+            dst[o] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MAX_WG * WG_THREADS, 1)
+ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t w_bar;
+    __shared__ __align__(8) uint64_t x_bar[MAX_WG];
+    __shared__ __align__(8) uint64_t mma_bar[MAX_WG];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_seg_m, s_seg_end;
+
+    const int tid = threadIdx.x;
+    const int wg = tid / WG_THREADS;
+    const int wtid = tid - wg * WG_THREADS;          // row within the tile == TMEM lane
+    const int warp_in_wg = wtid >> 5, lane = tid & 31;
+    const int L = a.arch.n_layers;
+    const int T_in = a.arch.widths[0], T_out = a.arch.widths[L];
+    const bool y_sep = a.ytile_bytes != 0;
+
+    // ---- shared memory carve-up
+    uint8_t* w_img = smem;                                                    // operand image
+    float* vecs = reinterpret_cast<float*>(smem + a.lay.total_bytes);         // per-Machine vectors
+    float* v_scale = vecs; float* v_min = vecs + T_in; float* v_es = vecs + 2 * T_in; float* v_ft = v_es + T_out;
+    uint8_t* wg_base = smem + a.lay.total_bytes + gb_round_up_dev(a.vec_floats * 4, 128)
+                     + (size_t)wg * (a.xtile_bytes + a.ytile_bytes + a.abuf_bytes);
+    float* xbuf = reinterpret_cast<float*>(wg_base);
+    float* ybuf = y_sep ? reinterpret_cast<float*>(wg_base + a.xtile_bytes) : xbuf;
+    uint8_t* abuf = wg_base + a.xtile_bytes + a.ytile_bytes;
+
+    if (tid == 0) {
+        mbar_init(&w_bar, 1);
+        for (int g = 0; g < a.nwg; ++g) { mbar_init(&x_bar[g], 1); mbar_init(&mma_bar[g], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) tmem_alloc(&s_tmem_base, a.tmem_cols_total);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = s_tmem_base + (uint32_t)(wg * a.tmem_cols_wg);          // column offset
+    const uint32_t tmem_lane = tmem_acc + ((uint32_t)(warp_in_wg * 32) << 16);        // this warp's lanes
+
+    const int per_cta = (a.tiles_total + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * per_cta;
+    const int t_end = min(t_begin + per_cta, a.tiles_total);
+    uint32_t w_phase = 0, x_phase = 0, mma_phase = 0;
+
+    int seg_begin = t_begin;
+    while (seg_begin < t_end) {
+        // ---- segment = run of this CTA's tiles that belong to one Machine
+        if (tid == 0) {
+            const int m = find_machine(a.tile_off, a.n_machines, seg_begin);
+            s_seg_m = m; s_seg_end = min(t_end, a.tile_off[m + 1]);
+            mbar_expect_tx(&w_bar, (uint32_t)a.lay.total_bytes);
+            bulk_g2s(w_img, a.packed + (size_t)m * a.lay.total_bytes, (uint32_t)a.lay.total_bytes, &w_bar);
+        }
+        __syncthreads();
+        const int m = s_seg_m, seg_end = s_seg_end;
+        for (int i = tid; i < T_in; i += blockDim.x) {
+            v_scale[i] = a.in_scale ? a.in_scale[(size_t)m * T_in + i] : 1.0f;
+            v_min[i] = a.in_min ? a.in_min[(size_t)m * T_in + i] : 0.0f;
+        }
+        for (int i = tid; i < T_out; i += blockDim.x) {
+            v_es[i] = a.err_scale ? fabsf(a.err_scale[(size_t)m * T_out + i]) : 1.0f;
+            v_ft[i] = a.feat_thr ? a.feat_thr[(size_t)m * T_out + i] : 1.0f;
+        }
+        mbar_wait(&w_bar, w_phase); w_phase ^= 1;
+        __syncthreads();
+        const int64_t m_row0 = a.row_lo[m], m_row1 = a.row_hi[m];
+        const float agg = a.agg_thr ? a.agg_thr[m] : 1.0f;
+
+        if (wg < a.nwg) {
+            for (int tile = seg_begin + wg; tile < seg_end; tile += a.nwg) {
+                const int64_t row0 = m_row0 + (int64_t)(tile - a.tile_off[m]) * TILE;
+                const int nrows = (int)min((int64_t)TILE, m_row1 - row0);
+                const bool valid = wtid < nrows;
+                // ---- tile load: one contiguous run of nrows*T floats
+                const float* xsrc = a.x + row0 * T_in;
+                const float* ysrc = y_sep ? a.y + row0 * T_out : xsrc;
+                const uint32_t xbytes = (uint32_t)nrows * T_in * 4, ybytes = (uint32_t)nrows * T_out * 4;
+                const bool x16 = ((reinterpret_cast<uintptr_t>(xsrc) | xbytes) & 15) == 0;
+                const bool y16 = !y_sep || ((reinterpret_cast<uintptr_t>(ysrc) | ybytes) & 15) == 0;
+                if (x16 && y16) {
+                    if (wtid == 0) {
+                        mbar_expect_tx(&x_bar[wg], xbytes + (y_sep ? ybytes : 0));
+                        bulk_g2s(xbuf, xsrc, xbytes, &x_bar[wg]);
+                        if (y_sep) bulk_g2s(ybuf, ysrc, ybytes, &x_bar[wg]);
+                    }
+                    mbar_wait(&x_bar[wg], x_phase); x_phase ^= 1;
+                } else {
+                    for (int i = wtid; i < nrows * T_in; i += WG_THREADS) xbuf[i] = xsrc[i];
+                    if (y_sep) for (int i = wtid; i < nrows * T_out; i += WG_THREADS) ybuf[i] = ysrc[i];
+                    named_bar_sync(1 + wg, WG_THREADS);
+                }
+                // ---- A operand of layer 0: bf16(x*scale+min), canonical K-major core matrices
+                {
+                    const int Kp = a.lay.Kp[0];
+                    const float* xr = xbuf + wtid * T_in;
+                    uint8_t* arow = abuf + (wtid >> 3) * 128 + (wtid & 7) * 16;
+                    for (int c = 0; c < Kp / 8; ++c) {
+                        float v[8];
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = c * 8 + j;
+                            v[j] = (valid && k < T_in) ? fmaf(xr[k], v_scale[k], v_min[k]) : 0.0f;
+                        }
+                        uint4 pk;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(arow + c * 2048) = pk;
+                    }
+                }
+                // ---- the Dense stack
+                for (int l = 0; l < L; ++l) {
+                    const int Kp = a.lay.Kp[l], Np = a.lay.Np[l];
+                    fence_proxy_async();            // generic-proxy A stores -> visible to the tensor core
+                    tc_fence_before();
+                    named_bar_sync(1 + wg, WG_THREADS);
+                    if (wtid == 0) {
+                        tc_fence_after();
+                        const uint32_t idesc = make_idesc(TILE, Np);
+                        const uint32_t a_addr = smem_u32(abuf), b_addr = smem_u32(w_img + a.lay.w_off[l]);
+                        const uint32_t b_lbo = (uint32_t)(Np / 8) * 128;
+                        for (int ks = 0; ks < Kp / 16; ++ks) {
+                            const uint64_t da = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
+                            const uint64_t db = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
+                            umma_bf16(tmem_acc, da, db, idesc, ks > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&mma_bar[wg]);
+                    }
+                    mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
+                    tc_fence_after();
+                    if (l == L - 1) break;
+                    // hidden-layer epilogue: bias + activation -> next A operand
+                    const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[l]);
+                    const int code = a.arch.acts[l];
+                    uint8_t* arow = abuf + (wtid >> 3) * 128 + (wtid & 7) * 16;
+                    for (int c = 0; c < Np / 16; ++c) {
+                        float v[16];
+                        tmem_ld16(tmem_lane + c * 16, v);
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = act_fast(code, v[j] + bias[c * 16 + j]);
+                        #pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[h * 8 + 0], v[h * 8 + 1]);
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[h * 8 + 2], v[h * 8 + 3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[h * 8 + 4], v[h * 8 + 5]);
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[h * 8 + 6], v[h * 8 + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                            *reinterpret_cast<uint4*>(arow + (c * 2 + h) * 2048) = pk;
+                        }
+                    }
+                }
+                // ---- final epilogue
+                const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[L - 1]);
+                const int code = a.arch.acts[L - 1];
+                const int NpL = a.lay.Np[L - 1];
+                float* yrow = ybuf + wtid * T_out;
+                // pass 1: d = |yhat - y| in place over y; row totals in registers
+                float su = 0.0f, ss = 0.0f;
+                for (int c = 0; c < NpL / 16; ++c) {
+                    float v[16];
+                    tmem_ld16(tmem_lane + c * 16, v);
+                    if (valid) {
+                        #pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = c * 16 + j;
+                            if (n < T_out) {
+                                const float yh = act_fast(code, v[j] + bias[n]);
+                                const float d = fabsf(yh - yrow[n]);
+                                const float s = d * v_es[n];
+                                su = fmaf(d, d, su); ss = fmaf(s, s, ss);
+                                yrow[n] = d;
+                            }
+                        }
+                    }
+                }
+                if (valid) {
+                    const int64_t row = row0 + wtid;
+                    const float ts = ss / (float)T_out;
+                    if (a.total_scaled) a.total_scaled[row] = ts;
+                    if (a.total_unscaled) a.total_unscaled[row] = su / (float)T_out;
+                    if (a.total_conf && a.agg_thr) a.total_conf[row] = ts / agg;
+                }
+                __syncwarp();
+                {
+                    const int wrows = max(0, min(32, nrows - warp_in_wg * 32));
+                    const int cnt = wrows * T_out;
+                    const int64_t goff = (row0 + warp_in_wg * 32) * T_out;
+                    const float* src = ybuf + warp_in_wg * 32 * T_out;
+                    const bool v16 = (((goff * 4) | (int64_t)(cnt * 4)) & 15) == 0 && ((warp_in_wg * 32 * T_out * 4) & 15) == 0
+                                     && ((reinterpret_cast<uintptr_t>(a.model_out) | reinterpret_cast<uintptr_t>(a.tag_scaled) |
+                                          reinterpret_cast<uintptr_t>(a.tag_unscaled) | reinterpret_cast<uintptr_t>(a.conf)) & 15) == 0;
+                    if (cnt > 0) {
+                        if (a.tag_unscaled) warp_copy_out<0>(a.tag_unscaled + goff, src, cnt, T_out, nullptr, lane, v16);
+                        if (a.tag_scaled) warp_copy_out<1>(a.tag_scaled + goff, src, cnt, T_out, v_es, lane, v16);
+                        if (a.conf && a.feat_thr) warp_copy_out<2>(a.conf + goff, src, cnt, T_out, v_ft, lane, v16);
+                    }
+                    __syncwarp();
+                    // pass 2: yhat overwrites the tile, then goes out the same way
+                    if (a.model_out) {
+                        for (int c = 0; c < NpL / 16; ++c) {
+                            float v[16];
+                            tmem_ld16(tmem_lane + c * 16, v);
+                            if (valid) {
+                                #pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int n = c * 16 + j;
+                                    if (n < T_out) yrow[n] = act_fast(code, v[j] + bias[n]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (cnt > 0) warp_copy_out<0>(a.model_out + goff, src, cnt, T_out, nullptr, lane, v16);
+                    }
+                }
+                // the tile buffers are about to be overwritten through the async proxy
+                fence_proxy_async();
+                tc_fence_before();
+                named_bar_sync(1 + wg, WG_THREADS);
+            }
+        }
+        __syncthreads();            // all warpgroups done with this Machine's operand image
+        seg_begin = seg_end;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(s_tmem_base, a.tmem_cols_total);
+}
+
+}  // namespace
+
+int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch) {
+    PackLayout lay = make_layout(arch);
+    // eligible when the image + one warpgroup's buffers fit the 227 KB shared-memory window and
+    // a layer fits one UMMA (N <= 256) and one accumulator slice (<= 512 TMEM columns)
+    if (lay.max_Np > 256 || lay.max_Kp > 256) return 0;
+    const int T_in = arch->widths[0], T_out = arch->widths[arch->n_layers];
+    const int64_t per_wg = gb_round_up(TILE * T_in * 4, 16) + gb_round_up(TILE * T_out * 4, 16) + TILE * lay.max_Kp * 2;
+    if (lay.total_bytes + 4096 + per_wg > 227 * 1024 - 2048) return 0;
+    return lay.total_bytes;
+}
+
+int gb_launch_ff_pack_bf16(const gb200_ff_arch* arch, int n_machines, const float* params, void* packed,
+                           cudaStream_t stream) {
+    if (n_machines <= 0) return GB_OK;
+    PackLayout lay = make_layout(arch);
+    pack_bf16_kernel<<<n_machines, 256, 0, stream>>>(*arch, lay, gb200_ff_param_count(arch), params, (uint8_t*)packed);
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
+}
+
+int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const void* packed,
+                          const float* in_scale, const float* in_min, const float* err_scale,
+                          const float* feat_thr, const float* agg_thr, const float* x, const float* y,
+                          float* model_out, float* tag_scaled, float* tag_unscaled,
+                          float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
+                          cudaStream_t stream) {
+    if (f->tiles_total == 0) return GB_OK;
+    TcArgs a{};
+    a.arch = *arch; a.lay = make_layout(arch);
+    a.row_lo = f->d_row_lo; a.row_hi = f->d_row_hi; a.tile_off = f->d_tile_off;
+    a.n_machines = f->n_machines; a.tiles_total = f->tiles_total;
+    a.packed = (const uint8_t*)packed;
+    a.in_scale = in_scale; a.in_min = in_min; a.err_scale = err_scale; a.feat_thr = feat_thr; a.agg_thr = agg_thr;
+    a.x = x; a.y = (y == x) ? nullptr : y;
+    a.model_out = model_out; a.tag_scaled = tag_scaled; a.tag_unscaled = tag_unscaled;
+    a.total_scaled = total_scaled; a.total_unscaled = total_unscaled; a.conf = conf; a.total_conf = total_conf;
+    const int T_in = arch->widths[0], T_out = arch->widths[arch->n_layers];
+    a.xtile_bytes = gb_round_up(TILE * T_in * 4, 128);
+    a.ytile_bytes = a.y ? gb_round_up(TILE * T_out * 4, 128) : 0;
+    a.abuf_bytes = TILE * a.lay.max_Kp * 2;
+    a.vec_floats = 2 * T_in + 2 * T_out;
+    int cols = 32; while (cols < a.lay.max_Np) cols <<= 1;
+    a.tmem_cols_wg = cols;
+    const size_t cap = 227 * 1024 - 1024;
+    const size_t fixed = (size_t)a.lay.total_bytes + gb_round_up(a.vec_floats * 4, 128);
+    const size_t per_wg = (size_t)a.xtile_bytes + a.ytile_bytes + a.abuf_bytes;
+    int nwg = MAX_WG;
+    while (nwg > 1 && (fixed + nwg * per_wg > cap || nwg * cols > 512)) --nwg;
+    GB_REQUIRE(fixed + nwg * per_wg <= cap, "ff_score_tc: topology does not fit in shared memory");
+    a.nwg = nwg;
+    int tot = 32; while (tot < nwg * cols) tot <<= 1;
+    a.tmem_cols_total = tot;
+    const size_t smem = fixed + nwg * per_wg;
+    GB_CUDA_CHECK(cudaFuncSetAttribute(ff_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = f->sm_count;
+    const int min_tiles_per_cta = nwg;            // keep every warpgroup of a CTA busy
+    const int max_grid = (f->tiles_total + min_tiles_per_cta - 1) / min_tiles_per_cta;
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+    ff_score_tc_kernel<<<grid, nwg * WG_THREADS, smem, stream>>>(a);
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
+}

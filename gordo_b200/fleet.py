@@ -1,0 +1,278 @@
+"""
+Fleet host layer: M independent Machines of one topology, their tensors held in PyTorch on one
+B200, every arithmetic step a call into libgordo_b200.so (include/gordo_b200.h).
+
+This is the batched twin of what the reference does one Machine at a time:
+``for machine in machines: ModelBuilder(machine).build()`` (gordo/builder/local_build.py:69-70)
+-> ``DiffBasedAnomalyDetector.cross_validate / fit / anomaly`` (gordo/machine/model/anomaly/diff.py).
+PyTorch is used for device memory, streams and RNG only.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("gordo_b200 needs contiguous CUDA tensors")
+
+
+@dataclass
+class FFTopology:
+    """Feed-forward stack as the factories of factories/feedforward_autoencoder.py build it."""
+    widths: List[int]
+    acts: List[str]
+    l1: List[float] = field(default_factory=list)
+    adam: Dict[str, float] = field(default_factory=lambda: dict(lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7))
+
+    def __post_init__(self):
+        if not self.l1:
+            self.l1 = [0.0] * (len(self.widths) - 1)
+        self.arch = N.make_ff_arch(self.widths, self.acts, self.l1)
+
+    @property
+    def n_params(self) -> int:
+        return sum(self.widths[i] * self.widths[i + 1] + self.widths[i + 1] for i in range(len(self.widths) - 1))
+
+    @property
+    def n_in(self) -> int:
+        return self.widths[0]
+
+    @property
+    def n_out(self) -> int:
+        return self.widths[-1]
+
+    def key(self):
+        return (tuple(self.widths), tuple(self.acts), tuple(self.l1))
+
+    def glorot_init(self, n_machines: int, generator: torch.Generator, device) -> torch.Tensor:
+        """[M, P] float32: glorot-uniform kernels, zero biases ([3P] Keras Dense defaults)."""
+        out = torch.zeros((n_machines, self.n_params), dtype=torch.float32, device=device)
+        o = 0
+        for i in range(len(self.widths) - 1):
+            a, b = self.widths[i], self.widths[i + 1]
+            lim = float(np.sqrt(6.0 / (a + b)))
+            w = (torch.rand((n_machines, a * b), generator=generator, device=device, dtype=torch.float32) * 2 - 1) * lim
+            out[:, o:o + a * b] = w
+            o += a * b + b
+        return out
+
+
+class Schedule:
+    """Row layout of a fleet (gb200_fleet handle): Machine m owns rows [row_off[m], row_off[m+1])."""
+
+    def __init__(self, row_counts: Optional[Sequence[int]] = None, *, rows_lo=None, rows_hi=None,
+                 rows_total: Optional[int] = None):
+        self._h = C.c_void_p()
+        i64p = C.POINTER(C.c_int64)
+        if row_counts is not None:
+            rc = np.asarray(row_counts, dtype=np.int64)
+            self.row_off = np.concatenate([[0], np.cumsum(rc)]).astype(np.int64)
+            self.rows_lo, self.rows_hi = self.row_off[:-1].copy(), self.row_off[1:].copy()
+            self.n_machines = len(rc)
+            self.rows_total = int(self.row_off[-1])
+            N.check(N.lib().gb200_fleet_create(C.byref(self._h), self.n_machines,
+                                               self.row_off.ctypes.data_as(i64p)), "gb200_fleet_create")
+        else:
+            # explicit sub-ranges of a [rows_total, T] matrix (virtual Machines, e.g. CV test folds)
+            self.rows_lo = np.ascontiguousarray(rows_lo, dtype=np.int64)
+            self.rows_hi = np.ascontiguousarray(rows_hi, dtype=np.int64)
+            self.n_machines = len(self.rows_lo)
+            self.rows_total = int(rows_total if rows_total is not None else self.rows_hi.max())
+            N.check(N.lib().gb200_fleet_create_ranges(C.byref(self._h), self.n_machines,
+                                                      self.rows_lo.ctypes.data_as(i64p),
+                                                      self.rows_hi.ctypes.data_as(i64p)), "gb200_fleet_create_ranges")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().gb200_fleet_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+SCORE_COLUMNS = ("model-output", "tag-anomaly-scaled", "tag-anomaly-unscaled",
+                 "total-anomaly-scaled", "total-anomaly-unscaled",
+                 "anomaly-confidence", "total-anomaly-confidence")
+
+
+class FFFleet:
+    """
+    M feed-forward autoencoder Machines of one topology on one GPU.
+
+    State (all CUDA float32): ``params`` [M,P]; input scaler ``in_scale``/``in_min`` [M,T_in]
+    (the Pipeline's MinMaxScaler); error scaler ``err_scale`` [M,T_out] (the detector's
+    MinMaxScaler, diff.py:173); thresholds ``feat_thr`` [M,T_out], ``agg_thr`` [M] once
+    cross-validated (diff.py:256-264).
+    """
+
+    def __init__(self, topo: FFTopology, n_machines: int, device="cuda:0"):
+        N.lib()
+        self.topo = topo
+        self.M = n_machines
+        self.device = torch.device(device)
+        self.params: Optional[torch.Tensor] = None
+        self.in_scale = self.in_min = self.err_scale = None
+        self.feat_thr = self.agg_thr = None
+        self._packed = None
+        self._packed_version = -1
+        self._version = 0
+
+    # ------------------------------------------------------------------ parameters
+    def set_params(self, params: torch.Tensor):
+        params = params.to(self.device, torch.float32).contiguous()
+        if params.shape != (self.M, self.topo.n_params):
+            raise ValueError(f"params must be [{self.M}, {self.topo.n_params}], got {tuple(params.shape)}")
+        self.params = params
+        self._version += 1
+
+    def init_params(self, seed: int = 0):
+        g = torch.Generator(device=self.device); g.manual_seed(int(seed))
+        self.set_params(self.topo.glorot_init(self.M, g, self.device))
+
+    def tc_eligible(self) -> bool:
+        return N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch)) > 0
+
+    def packed(self) -> torch.Tensor:
+        """bf16 tcgen05 operand image of the current weights (re-packed when they change)."""
+        if self._packed is None or self._packed_version != self._version:
+            nbytes = N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch))
+            if nbytes <= 0:
+                raise ValueError("topology is not eligible for the tensor-core path")
+            if self._packed is None:
+                self._packed = torch.empty((self.M, nbytes), dtype=torch.uint8, device=self.device)
+            N.check(N.lib().gb200_ff_pack_bf16(C.byref(self.topo.arch), self.M, N.ptr(self.params),
+                                               N.ptr(self._packed), _stream_ptr()), "gb200_ff_pack_bf16")
+            self._packed_version = self._version
+        return self._packed
+
+    # ------------------------------------------------------------------ scalers / thresholds
+    @staticmethod
+    def minmax_fit(x: torch.Tensor, rows_lo: torch.Tensor, rows_hi: torch.Tensor):
+        """sklearn MinMaxScaler.fit over row ranges -> (scale [J,T], min_ [J,T])."""
+        _require_cuda(x, rows_lo, rows_hi)
+        J, T = rows_lo.numel(), x.shape[1]
+        scale = torch.empty((J, T), dtype=torch.float32, device=x.device)
+        mn = torch.empty_like(scale)
+        N.check(N.lib().gb200_minmax_fit(J, N.ptr(rows_lo), N.ptr(rows_hi), N.ptr(x), T, N.ptr(scale),
+                                         N.ptr(mn), _stream_ptr()), "gb200_minmax_fit")
+        return scale, mn
+
+    @staticmethod
+    def rolling_min_max(v: torch.Tensor, rows_lo: torch.Tensor, rows_hi: torch.Tensor, window: int = 6):
+        """pandas rolling(window).min().max() per column over row ranges -> [J, C]."""
+        v2 = v if v.dim() == 2 else v.unsqueeze(1)
+        _require_cuda(v2, rows_lo, rows_hi)
+        J, Cc = rows_lo.numel(), v2.shape[1]
+        out = torch.empty((J, Cc), dtype=torch.float32, device=v.device)
+        N.check(N.lib().gb200_rolling_min_max(J, N.ptr(rows_lo), N.ptr(rows_hi), N.ptr(v2), Cc, int(window),
+                                              N.ptr(out), _stream_ptr()), "gb200_rolling_min_max")
+        return out
+
+    # ------------------------------------------------------------------ inference + scoring
+    def score(self, sched: Schedule, x: torch.Tensor, y: Optional[torch.Tensor] = None, *,
+              precision: str = "bf16", columns: Sequence[str] = SCORE_COLUMNS,
+              out: Optional[Dict[str, torch.Tensor]] = None, subset: Optional[slice] = None):
+        """
+        Fused predict + DiffBasedAnomalyDetector.anomaly columns for every row of every Machine
+        (models.py:289-300 + diff.py:336-444).  x: [rows_total, T_in] float32 CUDA; y defaults
+        to x.  Returns {column: tensor}; threshold-based columns only when thresholds are set.
+        """
+        if self.params is None:
+            raise RuntimeError("fleet has no parameters (call set_params / init_params / fit)")
+        if sched.n_machines != self.M:
+            raise ValueError("schedule and fleet disagree on the number of Machines")
+        _require_cuda(x, y)
+        if x.dtype != torch.float32 or x.shape != (sched.rows_total, self.topo.n_in):
+            raise ValueError(f"x must be float32 [{sched.rows_total}, {self.topo.n_in}]")
+        R, To = sched.rows_total, self.topo.n_out
+        want = set(columns)
+        if self.feat_thr is None:
+            want.discard("anomaly-confidence")
+        if self.agg_thr is None:
+            want.discard("total-anomaly-confidence")
+        res = dict(out) if out else {}
+
+        def buf(name, shape):
+            if name not in want:
+                return None
+            if name not in res:
+                res[name] = torch.empty(shape, dtype=torch.float32, device=x.device)
+            return res[name]
+
+        mo = buf("model-output", (R, To)); ts = buf("tag-anomaly-scaled", (R, To))
+        tu = buf("tag-anomaly-unscaled", (R, To)); tts = buf("total-anomaly-scaled", (R,))
+        ttu = buf("total-anomaly-unscaled", (R,)); cf = buf("anomaly-confidence", (R, To))
+        tcf = buf("total-anomaly-confidence", (R,))
+        if precision == "bf16":
+            prec, packed = N.PREC_BF16_TC, self.packed()
+        elif precision == "f32":
+            prec, packed = N.PREC_F32, None
+        else:
+            raise ValueError("precision must be 'bf16' or 'f32'")
+        N.check(N.lib().gb200_ff_score(
+            sched.handle, C.byref(self.topo.arch), prec, N.ptr(self.params), N.ptr(packed),
+            N.ptr(self.in_scale), N.ptr(self.in_min), N.ptr(self.err_scale),
+            N.ptr(self.feat_thr), N.ptr(self.agg_thr), N.ptr(x), N.ptr(y),
+            N.ptr(mo), N.ptr(ts), N.ptr(tu), N.ptr(tts), N.ptr(ttu), N.ptr(cf), N.ptr(tcf),
+            _stream_ptr()), "gb200_ff_score")
+        return res
+
+    def predict(self, sched: Schedule, x: torch.Tensor, precision: str = "f32") -> torch.Tensor:
+        return self.score(sched, x, precision=precision, columns=("model-output",))["model-output"]
+
+    def host_pipeline(self, sched: Schedule, n_chunks: int = 8, precision: str = "bf16", columns=SCORE_COLUMNS):
+        """Pinned-host-in / pinned-host-out scoring over two streams (see host_pipeline.HostPipeline)."""
+        from .host_pipeline import HostPipeline
+        return HostPipeline(self, sched, n_chunks, precision, columns)
+
+    # ------------------------------------------------------------------ training
+    def fit_jobs(self, x: torch.Tensor, y: Optional[torch.Tensor], rows_lo: torch.Tensor, rows_hi: torch.Tensor,
+                 params: torch.Tensor, *, in_scale=None, in_min=None, scale_slot=None,
+                 epochs=1, batch_size=32, perm_pool=None, perm_off=None, l1_mean=False,
+                 adam_mv=None, adam_t=None, want_history=True):
+        """
+        Keras ``Model.fit`` for J independent jobs in one launch (models.py:243-287).  ``params``
+        [J,P] is updated in place.  Returns (hist_loss [J,epochs], hist_acc [J,epochs], adam_mv, adam_t).
+        """
+        _require_cuda(x, y, rows_lo, rows_hi, params, in_scale, in_min, scale_slot, perm_pool, perm_off, adam_mv, adam_t)
+        J, P = params.shape
+        if P != self.topo.n_params:
+            raise ValueError("params width does not match the topology")
+        if adam_mv is None:
+            adam_mv = torch.zeros((J, 2 * P), dtype=torch.float32, device=x.device)
+        if adam_t is None:
+            adam_t = torch.zeros((J,), dtype=torch.int64, device=x.device)
+        hl = torch.empty((J, epochs), dtype=torch.float32, device=x.device) if want_history else None
+        ha = torch.empty((J, epochs), dtype=torch.float32, device=x.device) if want_history else None
+        adam = N.Adam(**{k: float(v) for k, v in self.topo.adam.items()})
+        N.check(N.lib().gb200_ff_fit(
+            C.byref(self.topo.arch), C.byref(adam), J, N.ptr(rows_lo), N.ptr(rows_hi), N.ptr(scale_slot),
+            N.ptr(in_scale), N.ptr(in_min), N.ptr(x), N.ptr(y), N.ptr(perm_off), N.ptr(perm_pool),
+            int(epochs), int(batch_size), int(bool(l1_mean)), N.ptr(params), N.ptr(adam_mv), N.ptr(adam_t),
+            N.ptr(hl), N.ptr(ha), _stream_ptr()), "gb200_ff_fit")
+        return hl, ha, adam_mv, adam_t
+
+
+def time_series_split_bounds(n: int, n_splits: int = 3):
+    """sklearn TimeSeriesSplit(n_splits) as (train_end == test_start, test_end) pairs."""
+    n_folds = n_splits + 1
+    if n_folds > n:
+        raise ValueError(f"Cannot have number of folds={n_folds} greater than the number of samples={n}.")
+    test_size = n // n_folds
+    return [(s, s + test_size) for s in range(n - n_splits * test_size, n, test_size)]

@@ -1,0 +1,204 @@
+/*
+ * gordo_b200.h -- C-ABI of libgordo_b200.so: the B200 (sm_100a) implementation of gordo's
+ * per-machine autoencoder anomaly path for a FLEET of independent Machines.
+ *
+ * The reference (equinor/gordo @ 99a4819d) has no FFI: the path is Python calling Keras / sklearn
+ * / pandas one Machine at a time.  Each entry point below cites the reference interface whose
+ * arithmetic it replaces; gordo_b200/ (Python) mirrors the reference's estimator surface on top.
+ *
+ * Conventions
+ *   - plain C types only; every data pointer is a CALLER-OWNED DEVICE pointer (e.g.
+ *     torch.Tensor.data_ptr()) unless the name ends in _host; nothing is allocated or freed
+ *     behind the caller's back after gb200_fleet_create();
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are
+ *     asynchronous on that stream and safe to issue concurrently on distinct streams;
+ *   - return value: 0 = ok, negative = error; gb200_last_error() gives the thread-local text;
+ *   - a "fleet" is a set of M Machines sharing ONE topology (same widths / activations);
+ *     heterogeneous projects are bucketed by topology on the host, one fleet per bucket;
+ *   - matrices are row-major; Machine m owns rows [row_off[m], row_off[m+1]) of the
+ *     concatenated [rows_total, T] sample matrices;
+ *   - parameters are one flat float32 vector per Machine: for each Dense layer W[in][out]
+ *     then b[out]; for each LSTM layer W[in][4u], U[u][4u], b[4u] (gate order i,f,c,o),
+ *     then the output Dense.
+ */
+#ifndef GORDO_B200_H
+#define GORDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB200_MAX_LAYERS 16
+#define GB200_ABI_VERSION 1
+
+/* activation codes (Keras names: factories/feedforward_autoencoder.py:21-24) */
+enum { GB200_ACT_LINEAR = 0, GB200_ACT_TANH = 1, GB200_ACT_RELU = 2, GB200_ACT_SIGMOID = 3,
+       GB200_ACT_ELU = 4, GB200_ACT_SOFTPLUS = 5 };
+
+/* precision of the dense stacks */
+enum { GB200_PREC_F32 = 0,      /* fp32 FMA, bit-faithful ordering of the reference ops   */
+       GB200_PREC_BF16_TC = 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */ };
+
+/* Feed-forward topology: what gordo/machine/model/factories/feedforward_autoencoder.py:15-104
+ * builds as a Keras Sequential of Dense layers. */
+typedef struct {
+    int32_t n_layers;                        /* Dense layers (2*encoding_layers + 1 for hourglass) */
+    int32_t widths[GB200_MAX_LAYERS + 1];    /* widths[0] = n_features, widths[n_layers] = n_features_out */
+    int32_t acts[GB200_MAX_LAYERS];          /* GB200_ACT_* per layer */
+    float   l1[GB200_MAX_LAYERS];            /* activity_regularizer l1 coefficient per layer (0 = none) */
+} gb200_ff_arch;
+
+/* LSTM topology: gordo/machine/model/factories/lstm_autoencoder.py:15-103. */
+typedef struct {
+    int32_t n_layers;                        /* LSTM layers (encoder + decoder) */
+    int32_t n_features, n_features_out;
+    int32_t units[GB200_MAX_LAYERS];
+    int32_t acts[GB200_MAX_LAYERS];          /* `activation` of each LSTM layer */
+    int32_t out_act;                         /* activation of the final Dense */
+    int32_t lookback_window;                 /* models.py:467-470 */
+    int32_t lookahead;                       /* 0 = KerasLSTMAutoEncoder, 1 = KerasLSTMForecast (models.py:701-710) */
+} gb200_lstm_arch;
+
+/* Adam as [3P] keras.optimizers.Adam applies it. */
+typedef struct { float lr, beta_1, beta_2, epsilon; } gb200_adam;
+
+typedef struct gb200_fleet gb200_fleet;      /* opaque */
+
+int         gb200_abi_version(void);
+const char* gb200_last_error(void);
+/* number of SMs / device name of the current device (diagnostics for bench + tests) */
+int         gb200_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+
+/* Create the schedule for a fleet of M machines whose sample rows are laid out by
+ * row_off_host[M+1] (HOST pointer, int64).  Allocates the (small) device-side schedule once.
+ * Replaces the `for machine in machines` loop of gordo/builder/local_build.py:69-70 and the
+ * one-pod-per-Machine fan-out of argo-workflow.yml.template:1543-1557. */
+int  gb200_fleet_create(gb200_fleet** out, int32_t n_machines, const int64_t* row_off_host);
+/* Same, with an explicit row range [rows_lo_host[m], rows_hi_host[m]) per Machine (HOST int64):
+ * used to treat sub-ranges -- e.g. the TimeSeriesSplit test folds of diff.py:209-215 -- as
+ * virtual Machines of one launch.  Outputs are always indexed by absolute row. */
+int  gb200_fleet_create_ranges(gb200_fleet** out, int32_t n_machines, const int64_t* rows_lo_host,
+                               const int64_t* rows_hi_host);
+void gb200_fleet_destroy(gb200_fleet* f);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feed-forward autoencoder: forward + DiffBasedAnomalyDetector scoring, fused.
+ * Replaces, per Machine: Pipeline.predict = MinMaxScaler.transform + KerasAutoEncoder.predict
+ * (gordo/machine/model/models.py:289-300) and the column arithmetic of
+ * DiffBasedAnomalyDetector.anomaly (gordo/machine/model/anomaly/diff.py:336-444):
+ *   yhat                   = DenseStack(x * in_scale + in_min)
+ *   tag_anomaly_unscaled   = |yhat - y|                        (diff.py:371-382)
+ *   tag_anomaly_scaled     = |S(yhat) - S(y)| = |err_scale| * |yhat - y|   (diff.py:350-363)
+ *   total_anomaly_*        = mean_tags(tag_anomaly_*^2)        (diff.py:366-368, 383-385)
+ *   anomaly_confidence     = tag_anomaly_unscaled / feat_thr   (diff.py:420-434)
+ *   total_anomaly_conf     = total_anomaly_scaled / agg_thr    (diff.py:438-444)
+ * Any output pointer may be NULL (skipped).  y == NULL means y aliases x (autoencoder).
+ * params       : [M, P] fp32 (GB200_PREC_F32) -- always required
+ * packed_bf16  : [M, gb200_ff_packed_bytes()] from gb200_ff_pack_bf16 (GB200_PREC_BF16_TC), else NULL
+ * in_scale/in_min : [M, T_in] fp32 (NULL = identity); err_scale : [M, T_out] fp32 (NULL = 1)
+ * feat_thr : [M, T_out] or NULL; agg_thr : [M] or NULL
+ */
+int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
+                   const float* params, const void* packed_bf16,
+                   const float* in_scale, const float* in_min, const float* err_scale,
+                   const float* feat_thr, const float* agg_thr,
+                   const float* x, const float* y,
+                   float* model_out, float* tag_scaled, float* tag_unscaled,
+                   float* total_scaled, float* total_unscaled,
+                   float* conf, float* total_conf, void* stream);
+
+/* bytes per Machine of the tensor-core operand image (bf16 weights in the tcgen05 canonical
+ * K-major shared-memory layout + fp32 biases); 0 if the topology is not eligible (a width > 256) */
+int64_t gb200_ff_packed_bytes(const gb200_ff_arch* arch);
+int gb200_ff_pack_bf16(const gb200_ff_arch* arch, int32_t n_machines, const float* params,
+                       void* packed_bf16, void* stream);
+int64_t gb200_ff_param_count(const gb200_ff_arch* arch);
+
+/* ---------------------------------------------------------------------------------------------
+ * MinMaxScaler.fit for every Machine of the fleet (sklearn MinMaxScaler: examples/config.yaml:75-82,
+ * diff.py:173): per tag min / max over the Machine's rows [lo, hi) (job-relative, see below)
+ * -> scale = 1/(max-min) (1 where max == min), min_ = -min*scale.
+ * rows_lo / rows_hi: [n_jobs] int64 DEVICE arrays of absolute row ranges; outputs [n_jobs, T].
+ */
+int gb200_minmax_fit(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi,
+                     const float* x, int32_t n_tags, float* scale, float* min_, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Thresholds: pandas `.rolling(window).min().max()` per column over row ranges
+ * (diff.py:229-233, 241-248).  v: [rows_total, n_cols]; out: [n_jobs, n_cols] (NaN if the range
+ * has fewer than `window` rows).
+ */
+int gb200_rolling_min_max(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi,
+                          const float* v, int32_t n_cols, int32_t window, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feed-forward training: Keras Model.fit (models.py:243-287 -> scikeras -> [3P] keras) for
+ * n_jobs independent fits in one launch (CV folds and the final fit are separate jobs):
+ * float32, mini-batches of `batch_size` in the order given by `perm` (NULL = natural order),
+ * loss = MSE + sum_l l1[l]*sum|h_l| (l1_mean != 0 divides the activity term by the batch size),
+ * Keras-form Adam.  One CTA owns one job; weights + Adam moments stay in shared memory.
+ *   job_rows_lo/hi : [n_jobs] int64 absolute row range of the TRAINING rows in x / y
+ *   job_scale_slot : [n_jobs] int32 index into in_scale/in_min rows (NULL = job index)
+ *   perm           : [n_jobs] int64 offsets into perm_pool (int32 row indices relative to the
+ *                    job's rows_lo, epochs * n_rows entries per job) or NULL
+ *   params         : [n_jobs, P] fp32, in: initial weights, out: trained weights
+ *   adam_mv        : [n_jobs, 2P] fp32 Adam moments (m then v), in/out -- zero them for a fresh
+ *                    optimizer; a second fit on the same model continues from them, as Keras does
+ *                    (models.py:282: the model is only built when self.model is None)
+ *   adam_t         : [n_jobs] int64 optimizer step counts, in/out (NULL = start at 0, not stored)
+ *   hist_loss/acc  : [n_jobs, epochs] fp32 outputs (Keras History 'loss' / 'accuracy'), may be NULL
+ */
+int gb200_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int32_t n_jobs,
+                 const int64_t* job_rows_lo, const int64_t* job_rows_hi,
+                 const int32_t* job_scale_slot, const float* in_scale, const float* in_min,
+                 const float* x, const float* y,
+                 const int64_t* perm_off, const int32_t* perm_pool,
+                 int32_t epochs, int32_t batch_size, int32_t l1_mean,
+                 float* params, float* adam_mv, int64_t* adam_t,
+                 float* hist_loss, float* hist_acc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LSTM autoencoder / forecast: windows are never materialised; window k of a Machine is rows
+ * [k, k+L) of its (scaled) x and the target is row k + L - 1 + lookahead of y
+ * (models.py:713-793).  Output rows: n_rows - L + 1 - lookahead per Machine, written at
+ * out_row_off[m] (HOST-side layout is the caller's: gb200_lstm_out_rows()).
+ */
+int64_t gb200_lstm_param_count(const gb200_lstm_arch* arch);
+int64_t gb200_lstm_out_rows(const gb200_lstm_arch* arch, int64_t n_rows);
+/* scratch bytes the caller must provide for gb200_lstm_predict over `max_windows` windows at once */
+int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch* arch, int64_t max_windows);
+/* KerasLSTMBaseEstimator.predict (models.py:618-660): yhat for every window of every Machine.
+ * out_row_off: [M+1] int64 DEVICE offsets of each Machine's output rows in model_out
+ * (Machine m produces gb200_lstm_out_rows(arch, rows_m) rows). */
+int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, const float* params,
+                       const float* in_scale, const float* in_min, const float* x,
+                       const int64_t* out_row_off, float* model_out,
+                       void* scratch, int64_t scratch_bytes, void* stream);
+/* KerasLSTMBaseEstimator.fit (models.py:557-616): primer step on the first window, then
+ * time-ordered batches; one job per fit.  Returns Keras History 'loss' of the main fit in
+ * hist_loss [n_jobs, epochs] and the primer's loss in primer_loss [n_jobs]. */
+int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t n_jobs,
+                   const int64_t* job_rows_lo_host, const int64_t* job_rows_hi_host,
+                   const float* in_scale, const float* in_min, const float* x, const float* y,
+                   int32_t epochs, int32_t batch_size, float* params,
+                   float* hist_loss, float* primer_loss,
+                   void* scratch, int64_t scratch_bytes, void* stream);
+int64_t gb200_lstm_fit_scratch_bytes(const gb200_lstm_arch* arch, int32_t n_jobs, int32_t batch_size);
+
+/* Anomaly scoring of precomputed model output (used after gb200_lstm_predict, where the output
+ * is offset against y): same columns as gb200_ff_score.  out_row_off [M+1] / y_row_off [M] are DEVICE
+ * int64 arrays: Machine m's output rows [out_row_off[m], out_row_off[m+1]) align with rows of y
+ * starting at y_row_off[m] (diff.py:359-363 `[-len(data):]`). */
+int gb200_score_outputs(int32_t n_machines, const int64_t* out_row_off,
+                        const int64_t* y_row_off, int32_t n_tags,
+                        const float* model_out, const float* y, const float* err_scale,
+                        const float* feat_thr, const float* agg_thr,
+                        float* tag_scaled, float* tag_unscaled, float* total_scaled,
+                        float* total_unscaled, float* conf, float* total_conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORDO_B200_H */
