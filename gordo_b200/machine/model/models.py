@@ -1,0 +1,385 @@
+"""
+sklearn-compatible estimators with the surface of gordo/machine/model/models.py:
+
+    KerasBaseEstimator (:36-357), KerasAutoEncoder (:360-398),
+    KerasLSTMBaseEstimator (:463-698), KerasLSTMForecast (:701), KerasLSTMAutoEncoder (:707)
+
+Same constructor (``kind`` + kwargs), ``from_definition`` / ``into_definition`` hooks, ``fit`` /
+``predict`` / ``score`` / ``get_params`` / ``get_metadata``, error behaviour and pickling contract
+-- but ``self.model`` is a topology + a float32 parameter vector and every fit / predict is a
+launch of libgordo_b200.so on the current CUDA device (a fleet of ONE Machine; fleets of thousands
+go through gordo_b200.builder / gordo_b200.fleet).  There is no CPU fallback.
+
+Selectable purely from Machine YAML:
+    gordo_b200.machine.model.models.KerasAutoEncoder:
+        kind: feedforward_hourglass
+"""
+import importlib
+import logging
+from copy import copy, deepcopy
+from importlib.util import find_spec
+from typing import Any, Callable, Dict, Optional, Tuple, Union
+
+import numpy as np
+import pandas as pd
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.exceptions import NotFittedError
+from sklearn.metrics import explained_variance_score
+
+from gordo_b200.machine.model.base import GordoBase
+from gordo_b200.machine.model.factories import *  # noqa: F401,F403  (registers the factories)
+from gordo_b200.machine.model.register import register_model_builder
+
+logger = logging.getLogger(__name__)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("gordo_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def _values(a):
+    return a.values if hasattr(a, "values") and not isinstance(a, np.ndarray) else a
+
+
+class _Model:
+    """What ``self.model`` holds: the topology, the float32 parameters, the optimizer state."""
+
+    def __init__(self, topology, params: np.ndarray):
+        self.topology = topology
+        self.params = np.ascontiguousarray(params, np.float32)
+        self.adam_mv: Optional[np.ndarray] = None
+        self.adam_t: int = 0
+
+    def count_params(self) -> int:
+        return int(self.params.size)
+
+
+class History:
+    """Stand-in for keras.callbacks.History (attributes read at models.py:339-357)."""
+
+    def __init__(self, history=None, params=None, epoch=None):
+        self.history = history or {}
+        self.params = params or {}
+        self.epoch = epoch or []
+
+
+class KerasBaseEstimator(BaseEstimator, GordoBase):
+    supported_fit_args = ["batch_size", "epochs", "verbose", "callbacks", "validation_split", "shuffle",
+                          "class_weight", "initial_epoch", "steps_per_epoch", "validation_batch_size",
+                          "max_queue_size", "workers", "use_multiprocessing"]
+    # kwargs consumed by this implementation and never forwarded to a factory
+    _b200_args = ("precision", "l1_batch_norm")
+
+    def __init__(self, kind: Union[str, Callable], **kwargs) -> None:
+        """
+        kind: a registered factory name, a dotted path to a factory, or a factory callable
+        (registered on the fly) -- models.py:53-94.  kwargs: factory arguments and/or fit
+        arguments (epochs, batch_size, shuffle, validation_split ...), plus ``precision``
+        ("f32" default | "bf16": tensor-core inference) and ``l1_batch_norm`` ("sum" default, as
+        Keras 3.3.3 | "mean").
+        """
+        self.kind = self.load_kind(kind)
+        self.kwargs: Dict[str, Any] = kwargs
+        self._history = None
+        self.model = None
+
+    # ------------------------------------------------------------------ kind / definition codec
+    @staticmethod
+    def parse_module_path(module_path) -> Tuple[Optional[str], str]:
+        parts = module_path.split(".")
+        return (None, parts[0]) if len(parts) == 1 else (".".join(parts[:-1]), parts[-1])
+
+    def load_kind(self, kind):
+        if callable(kind):
+            register_model_builder(type=self.__class__.__name__)(kind)
+            return kind.__name__
+        module_name, class_name = self.parse_module_path(kind)
+        if module_name is None:
+            if class_name not in register_model_builder.factories.get(self.__class__.__name__, {}):
+                raise ValueError(f"kind: {kind} is not an available model for type: {class_name}!")
+        else:
+            has_error = True
+            try:
+                has_error = not find_spec(module_name)
+            except ModuleNotFoundError:
+                pass
+            if has_error:
+                raise ValueError(f"kind: {kind}, unable to find module: '{module_name}'")
+        return kind
+
+    @classmethod
+    def extract_supported_fit_args(cls, kwargs):
+        return {arg: kwargs[arg] for arg in cls.supported_fit_args if arg in kwargs}
+
+    @classmethod
+    def from_definition(cls, definition: dict):
+        """Handler for gordo.serializer.from_definition (models.py:146-159)."""
+        definition = copy(definition)
+        kind = definition.pop("kind")
+        return cls(kind, **definition)
+
+    def into_definition(self) -> dict:
+        """Handler for gordo.serializer.into_definition (models.py:161-171)."""
+        definition = copy(self.kwargs)
+        definition["kind"] = self.kind
+        return definition
+
+    @property
+    def sk_params(self):
+        return self.kwargs
+
+    def get_params(self, deep=False, **params):
+        out = {"kind": self.kind}
+        out.update(self.kwargs)
+        return out
+
+    def set_params(self, **params):
+        if "kind" in params:
+            self.kind = self.load_kind(params.pop("kind"))
+        self.kwargs.update(params)
+        return self
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(kind={self.kind!r}, " + ", ".join(f"{k}={v!r}" for k, v in self.kwargs.items()) + ")"
+
+    # ------------------------------------------------------------------ pickling (models.py:185-210)
+    def __getstate__(self):
+        return self.__dict__.copy()         # numpy + plain python only: no live GPU handle to strip
+
+    def __setstate__(self, state):
+        self.__dict__ = state
+        return self
+
+    # ------------------------------------------------------------------ shapes
+    @staticmethod
+    def get_n_features_out(y) -> Union[int, tuple]:
+        if len(y.shape) == 1:
+            raise ValueError("Unsupported number of the output dataset dimensions %d" % len(y.shape))
+        return y.shape[1] if len(y.shape) == 2 else y.shape[1:]
+
+    @staticmethod
+    def get_n_features(X) -> Union[int, tuple]:
+        if len(X.shape) == 1:
+            raise ValueError("Unsupported number of the output dataset dimensions %d" % len(X.shape))
+        return X.shape[1] if len(X.shape) == 2 else X.shape[2]
+
+    # ------------------------------------------------------------------ model construction
+    def _factory(self):
+        module_name, class_name = self.parse_module_path(self.kind)
+        if module_name is None:
+            return register_model_builder.factories[self.__class__.__name__][self.kind]
+        module = importlib.import_module(module_name)
+        if not hasattr(module, class_name):
+            raise ValueError("kind: %s, unable to find class %s in module '%s'" % (self.kind, class_name, module_name))
+        return getattr(module, class_name)
+
+    def _topology(self):
+        kw = {k: v for k, v in self.sk_params.items() if k not in self._b200_args}
+        return self._factory()(**deepcopy(kw))
+
+    def _fit_arg(self, name, default, overrides):
+        if name in overrides:
+            return overrides[name]
+        return self.kwargs.get(name, default)
+
+    @property
+    def _precision(self) -> str:
+        p = self.kwargs.get("precision", "f32")
+        if p not in ("f32", "bf16"):
+            raise ValueError("precision must be 'f32' or 'bf16'")
+        return p
+
+    def get_metadata(self):
+        """{"history": {metric: [per epoch], "params": {...}}} once fitted (models.py:339-357)."""
+        if self._history is not None:
+            history = self._history.history
+            history["params"] = self._history.params
+            return {"history": history}
+        return {}
+
+
+class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
+    """Feed-forward autoencoder estimator (models.py:360-398)."""
+
+    def fit(self, X, y, **kwargs):
+        torch = _torch()
+        from gordo_b200.fleet import FFFleet
+        if isinstance(y, np.ndarray) and y.ndim == 1:
+            y = y.reshape(-1, 1)
+        self.kwargs.update({"n_features": self.get_n_features(X), "n_features_out": self.get_n_features_out(y)})
+        same = y is X
+        X = np.asarray(_values(X)); y = X if same else np.asarray(_values(y))
+        if self._fit_arg("callbacks", None, kwargs):
+            raise NotImplementedError("Keras callbacks (EarlyStopping ...) are not implemented in gordo_b200 yet")
+        epochs = int(self._fit_arg("epochs", 1, kwargs))
+        batch_size = int(self._fit_arg("batch_size", None, kwargs) or 32)
+        shuffle = bool(self._fit_arg("shuffle", True, kwargs))
+        vsplit = float(self._fit_arg("validation_split", 0.0, kwargs) or 0.0)
+        l1_mean = self.kwargs.get("l1_batch_norm", "sum") == "mean"
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        seed = int(np.random.randint(0, 2 ** 31 - 1))            # np.random.seed(...) => reproducible builds
+        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        if self.model is None:
+            topo = self._topology()
+            if topo.n_in != X.shape[1] or topo.n_out != y.shape[1]:
+                raise ValueError("factory topology does not match the data shape")
+            self.model = _Model(topo, topo.glorot_init(1, gen, dev)[0].cpu().numpy())
+        topo = self.model.topology
+        n = len(X)
+        n_train = n if not vsplit else int(np.floor(n * (1.0 - vsplit)))
+        xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
+        yd = None if same or (X.shape == y.shape and np.array_equal(X, y)) else \
+            torch.as_tensor(np.ascontiguousarray(y, np.float32), device=dev)
+        fleet = FFFleet(topo, 1, dev)
+        params = torch.as_tensor(self.model.params[None].copy(), device=dev)
+        mv = None if self.model.adam_mv is None else torch.as_tensor(self.model.adam_mv[None].copy(), device=dev)
+        t = torch.tensor([self.model.adam_t], dtype=torch.int64, device=dev)
+        lo = torch.zeros(1, dtype=torch.int64, device=dev); hi = torch.full((1,), n_train, dtype=torch.int64, device=dev)
+        hist = {"loss": [], "accuracy": []}
+        if vsplit:
+            hist["val_loss"] = []
+        # with a validation split Keras evaluates after every epoch, so train one epoch per launch
+        for e0 in range(0, epochs, 1 if vsplit else epochs):
+            ne = 1 if vsplit else epochs
+            pool = poff = None
+            if shuffle and n_train > 0:
+                pool = torch.stack([torch.randperm(n_train, generator=gen, device=dev) for _ in range(ne)]
+                                   ).to(torch.int32).reshape(-1).contiguous()
+                poff = torch.zeros(1, dtype=torch.int64, device=dev)
+            hl, ha, mv, t = fleet.fit_jobs(xd, yd, lo, hi, params, epochs=ne, batch_size=batch_size,
+                                           perm_pool=pool, perm_off=poff, l1_mean=l1_mean, adam_mv=mv, adam_t=t)
+            hist["loss"] += [float(v) for v in hl[0].cpu()]
+            hist["accuracy"] += [float(v) for v in ha[0].cpu()]
+            if vsplit and n > n_train:
+                from gordo_b200.fleet import Schedule
+                fleet.set_params(params)
+                vs = Schedule(rows_lo=[n_train], rows_hi=[n], rows_total=n)
+                vp = fleet.score(vs, xd, yd, precision="f32", columns=("total-anomaly-unscaled",))
+                hist["val_loss"].append(float(vp["total-anomaly-unscaled"][n_train:n].mean()))
+        self.model.params = params[0].cpu().numpy()
+        self.model.adam_mv = mv[0].cpu().numpy()
+        self.model.adam_t = int(t[0])
+        steps = -(-n_train // batch_size)
+        self._history = History(hist, {"verbose": 0, "epochs": epochs, "steps": steps}, list(range(epochs)))
+        return self
+
+    def predict(self, X, **kwargs) -> np.ndarray:
+        """ŷ [len(X), n_features_out] float32 (models.py:289-300)."""
+        torch = _torch()
+        from gordo_b200.fleet import FFFleet, Schedule
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        X = np.asarray(_values(X))
+        topo = self.model.topology
+        if X.ndim != 2 or X.shape[1] != topo.n_in:
+            raise ValueError(f"X must be [n, {topo.n_in}], got {X.shape}")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        fleet = FFFleet(topo, 1, dev)
+        fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
+        xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
+        prec = self._precision if fleet.tc_eligible() else "f32"
+        return fleet.predict(Schedule([len(X)]), xd, precision=prec).cpu().numpy()
+
+    def transform(self, X, **kwargs) -> np.ndarray:
+        return self.predict(X, **kwargs)
+
+    def score(self, X, y, sample_weight: Optional[np.ndarray] = None, **kwargs) -> float:
+        """Explained variance of the reconstruction (models.py:365-398)."""
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        return explained_variance_score(_values(y), self.predict(X, **kwargs))
+
+
+class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin):
+    """Many-to-one LSTM autoencoder / 1-step forecast (models.py:463-698)."""
+
+    lookahead = 0
+
+    def __init__(self, kind: Union[Callable, str], lookback_window: int = 1, batch_size: int = 32, **kwargs) -> None:
+        self.lookback_window = lookback_window
+        self.batch_size = batch_size
+        kwargs["lookback_window"] = lookback_window
+        kwargs["batch_size"] = batch_size
+        super().__init__(kind, **kwargs)
+
+    def get_params(self, deep=False, **params):
+        out = super().get_params(deep)
+        out["lookback_window"] = self.lookback_window
+        out["batch_size"] = self.batch_size
+        return out
+
+    def get_metadata(self):
+        metadata = super().get_metadata()
+        metadata.update({"forecast_steps": self.lookahead})
+        return metadata
+
+    def _validate_and_fix_size_of_X(self, X):
+        if X.ndim == 1:
+            logger.info(f"Reshaping X from an array to an matrix of shape {(len(X), 1)}")
+            X = X.reshape(len(X), 1)
+        if self.lookback_window >= X.shape[0]:
+            raise ValueError("For KerasLSTMForecast lookback_window must be < size of X")
+        return X
+
+    def fit(self, X, y, **kwargs):
+        torch = _torch()
+        from gordo_b200.lstm import LSTMFleet
+        X = np.asarray(_values(X)); y = np.asarray(_values(y))
+        X = self._validate_and_fix_size_of_X(X)
+        if y.ndim == 1:
+            y = y.reshape(len(y), 1)
+        self.kwargs.update({"n_features": X.shape[1], "n_features_out": y.shape[1]})
+        epochs = int({**self.kwargs, **kwargs}.get("epochs", 1))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        gen = torch.Generator(device=dev); gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+        if self.model is None:
+            topo = self._topology()
+            self.model = _Model(topo, topo.init_params(1, gen, dev)[0].cpu().numpy())
+        topo = self.model.topology
+        fleet = LSTMFleet(topo, 1, self.lookahead, dev)
+        xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
+        yd = torch.as_tensor(np.ascontiguousarray(y, np.float32), device=dev)
+        params = torch.as_tensor(self.model.params[None].copy(), device=dev)
+        hl, pl = fleet.fit_jobs(xd, yd, np.array([0]), np.array([len(X)]), params, epochs=epochs,
+                                batch_size=int(self.batch_size))
+        self.model.params = params[0].cpu().numpy()
+        # gordo keeps the History of the PRIMER fit (models.py:285-286 captures it, :615 never refreshes it)
+        self._history = History({"loss": [float(pl[0])]}, {"verbose": 0, "epochs": 1, "steps": 1}, [0])
+        self.history_main_ = {"loss": [float(v) for v in hl[0].cpu()]}
+        return self
+
+    def predict(self, X, **kwargs) -> np.ndarray:
+        """[n - lookback_window + 1 - lookahead, n_features_out] float32 (models.py:618-660)."""
+        torch = _torch()
+        from gordo_b200.fleet import Schedule
+        from gordo_b200.lstm import LSTMFleet
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        X = self._validate_and_fix_size_of_X(np.asarray(_values(X)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        fleet = LSTMFleet(self.model.topology, 1, self.lookahead, dev)
+        fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
+        xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
+        out, _ = fleet.predict(Schedule([len(X)]), xd)
+        return out.cpu().numpy()
+
+    def transform(self, X, **kwargs):
+        return self.predict(X, **kwargs)
+
+    def score(self, X, y, sample_weight: Optional[np.ndarray] = None, **kwargs) -> float:
+        if self.model is None:
+            raise NotFittedError(f"This {self.__class__.__name__} has not been fitted yet.")
+        out = self.predict(X, **kwargs)
+        return explained_variance_score(np.asarray(_values(y))[-len(out):], out)
+
+
+class KerasLSTMForecast(KerasLSTMBaseEstimator):
+    lookahead = 1
+
+
+class KerasLSTMAutoEncoder(KerasLSTMBaseEstimator):
+    lookahead = 0

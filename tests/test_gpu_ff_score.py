@@ -1,11 +1,14 @@
 """
 -m gpu parity tests of the fused scorer, through the C-ABI (gordo_b200.fleet -> libgordo_b200.so),
 against the oracle on the same seeded inputs.  Tolerances:
-  GB200_PREC_F32     : |yhat - oracle| <= 2e-5 abs on O(1) outputs (fp32 FMA order vs BLAS);
-                       score columns <= 1e-4 rel (+1e-6 abs): float32 device arithmetic vs the
-                       reference's float64 pandas arithmetic on the same float32 yhat.
-  GB200_PREC_BF16_TC : vs a bf16-operand emulation of the same stack <= 4e-3 abs (tanh.approx +
-                       accumulation order); vs the fp32 oracle <= 3e-2 abs (bf16 operands, 7 layers).
+  GB200_PREC_F32     : |yhat - oracle| <= 2e-5 abs on O(1) outputs (fp32 FMA order vs BLAS); the
+                       derived columns inherit that error times their column factor (|err_scale|,
+                       1/threshold) plus 2e-4 rel: float32 device arithmetic vs the reference's
+                       float64 pandas arithmetic on the same float32 yhat.
+  GB200_PREC_BF16_TC : vs a bf16-operand emulation of the same stack: mean |err| <= 6e-4 and max
+                       <= 1e-2 (tanh.approx + accumulation order flip an occasional bf16 rounding
+                       of a hidden activation; a layout / descriptor error is O(1)); vs the fp32
+                       oracle <= 3e-2 abs (bf16 operands through 7 layers).
 """
 import numpy as np
 import pytest
@@ -34,10 +37,17 @@ def _compare(res, case, forward, tol_out, rtol, atol):
         want = oracle_score(case, m, forward)
         for key, w in want.items():
             got = res[key][off:off + n].double().cpu().numpy()
+            es = float(np.abs(case["err_scale"][m]).max())
+            ift = 1.0 / float(case["feat_thr"][m].min()) if case["feat_thr"] is not None else 1.0
             if key == "model-output":
                 np.testing.assert_allclose(got, w, rtol=0, atol=tol_out, err_msg=f"machine {m} {key}")
+            elif key.startswith("total-"):
+                # mean of squares: error ~ 2*|d|*|delta| -> relative to the value, plus a floor
+                np.testing.assert_allclose(got, w, rtol=20 * rtol, atol=atol, err_msg=f"machine {m} {key}")
             else:
-                np.testing.assert_allclose(got, w, rtol=rtol, atol=atol, err_msg=f"machine {m} {key}")
+                factor = {"tag-anomaly-unscaled": 1.0, "tag-anomaly-scaled": es, "anomaly-confidence": ift}[key]
+                np.testing.assert_allclose(got, w, rtol=rtol, atol=2 * tol_out * factor + atol,
+                                           err_msg=f"machine {m} {key}")
         off += n
 
 
@@ -64,8 +74,10 @@ def test_ff_score_tc_matches_bf16_emulation_and_oracle(name):
     for m, n in enumerate(case["row_counts"]):
         want = oracle_score(case, m, ff_forward_bf16)["model-output"]
         got = res["model-output"][off:off + n].cpu().numpy()
-        np.testing.assert_allclose(got, want, rtol=0, atol=4e-3 * max(1.0, float(np.abs(want).max(initial=0))),
-                                   err_msg=f"machine {m}")
+        scale = max(1.0, float(np.abs(want).max(initial=0)))
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-2 * scale, err_msg=f"machine {m}")
+        if n:
+            assert float(np.abs(got - want).mean()) <= 6e-4 * scale, f"machine {m}"
         off += n
     # (b) loose: against the fp32 oracle (the stated bf16 tolerance)
     off = 0
