@@ -1,0 +1,267 @@
+"""
+FleetModelBuilder -- the batched twin of gordo.builder.ModelBuilder._build
+(gordo/builder/build_model.py:192-339) for a whole project:
+
+    for machine in machines: ModelBuilder(machine).build()          # local_build.py:69-70
+
+becomes, per topology bucket, a handful of launches over ALL Machines:
+  MinMaxScaler.fit (every CV fold + final)  -> gb200_minmax_fit
+  Keras fit of every fold + the final model -> gb200_ff_fit        (one CTA per fit)
+  fold predictions + validation errors      -> gb200_ff_score      (test folds = virtual Machines)
+  rolling(6).min().max() thresholds         -> gb200_rolling_min_max
+and the result is materialised as the same fitted objects a per-Machine build produces
+(DiffBasedAnomalyDetector[Pipeline[MinMaxScaler, KerasAutoEncoder]]), ready for serializer.dump /
+gordo.server.  Machines whose model is not that standard composition are built one at a time
+through the estimator API (still on the GPU).
+"""
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+from sklearn.pipeline import Pipeline
+from sklearn.preprocessing import MinMaxScaler
+
+from gordo_b200 import serializer
+from gordo_b200.fleet import FFFleet, FFTopology, Schedule, time_series_split_bounds
+from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+from gordo_b200.machine.model.models import KerasAutoEncoder, History, _Model
+
+
+@dataclass
+class FleetMachine:
+    """What ModelBuilder needs of a Machine once its dataset is fetched (build_model.py:208-219)."""
+    name: str
+    X: Any                                  # DataFrame / ndarray [n, T]
+    y: Any = None                           # defaults to X (autoencoder)
+    model: Optional[dict] = None            # model definition (Machine YAML `model:`), default hourglass AE
+    evaluation: Dict[str, Any] = field(default_factory=dict)   # cv_mode, n_splits, seed
+
+    def definition(self):
+        return self.model or {
+            "gordo_b200.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {
+                "base_estimator": {"sklearn.pipeline.Pipeline": {"steps": [
+                    "sklearn.preprocessing.MinMaxScaler",
+                    {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass"}}]}}}}
+
+
+def segmented_randperm(lengths: Sequence[int], generator, device):
+    """Independent random permutations of range(len) for every segment, concatenated (int32)."""
+    import torch
+    lengths_t = torch.as_tensor(np.asarray(lengths, np.int64), device=device)
+    total = int(lengths_t.sum())
+    if total == 0:
+        return torch.empty(0, dtype=torch.int32, device=device)
+    seg = torch.repeat_interleave(torch.arange(len(lengths), device=device), lengths_t)
+    keys = torch.rand(total, generator=generator, device=device)
+    order = torch.argsort(keys)
+    order = order[torch.argsort(seg[order], stable=True)]          # random within, grouped by segment
+    starts = torch.cumsum(lengths_t, 0) - lengths_t
+    return (order - starts[seg]).to(torch.int32).contiguous()
+
+
+class FleetModelBuilder:
+    def __init__(self, machines: Sequence[FleetMachine], device: Optional[str] = None, cv_precision: str = "f32"):
+        self.machines = list(machines)
+        self.device = device
+        self.cv_precision = cv_precision
+
+    # ------------------------------------------------------------------ public
+    def build(self):
+        """Returns [(fitted model, metadata dict)] in the order of ``machines``."""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("gordo_b200 needs a CUDA device (there is no CPU fallback)")
+        dev = torch.device(self.device) if self.device else torch.device("cuda", torch.cuda.current_device())
+        results: List[Any] = [None] * len(self.machines)
+        buckets: Dict[Any, List[int]] = {}
+        prototypes: Dict[int, Any] = {}
+        for i, mc in enumerate(self.machines):
+            model = serializer.from_definition(mc.definition())
+            prototypes[i] = model
+            key = self._bucket_key(model, mc)
+            if key is None:
+                results[i] = self._build_one(model, mc)
+            else:
+                buckets.setdefault(key, []).append(i)
+        for key, idxs in buckets.items():
+            built = self._build_bucket([self.machines[i] for i in idxs], [prototypes[i] for i in idxs], dev)
+            for i, r in zip(idxs, built):
+                results[i] = r
+        return results
+
+    # ------------------------------------------------------------------ bucketing
+    @staticmethod
+    def _standard_parts(model):
+        if type(model) is not DiffBasedAnomalyDetector or model.window is not None or model.shuffle:
+            return None
+        if not isinstance(model.scaler, MinMaxScaler):
+            return None
+        be = model.base_estimator
+        if isinstance(be, Pipeline) and len(be.steps) == 2 and isinstance(be.steps[0][1], MinMaxScaler) \
+                and type(be.steps[1][1]) is KerasAutoEncoder:
+            return be.steps[1][1]
+        return None
+
+    def _bucket_key(self, model, mc: FleetMachine):
+        est = self._standard_parts(model)
+        if est is None or est.kwargs.get("callbacks") or est.kwargs.get("validation_split"):
+            return None
+        if mc.evaluation.get("cv_mode", "full_build") not in ("full_build", "build_only"):
+            return None
+        X = np.asarray(getattr(mc.X, "values", mc.X))
+        y = X if mc.y is None else np.asarray(getattr(mc.y, "values", mc.y))
+        est.kwargs.update({"n_features": X.shape[1], "n_features_out": y.shape[1]})
+        topo = est._topology()
+        fit = (int(est.kwargs.get("epochs", 1)), int(est.kwargs.get("batch_size") or 32),
+               bool(est.kwargs.get("shuffle", True)), est.kwargs.get("l1_batch_norm", "sum"),
+               mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
+               tuple(sorted(topo.adam.items())))
+        return (topo.key(), fit)
+
+    # ------------------------------------------------------------------ one-at-a-time fallback
+    def _build_one(self, model, mc: FleetMachine):
+        np.random.seed(int(mc.evaluation.get("seed", 0)))
+        X = mc.X if isinstance(mc.X, pd.DataFrame) else pd.DataFrame(np.asarray(mc.X))
+        y = X if mc.y is None else (mc.y if isinstance(mc.y, pd.DataFrame) else pd.DataFrame(np.asarray(mc.y)))
+        meta: Dict[str, Any] = {"name": mc.name}
+        t0 = time.time()
+        if mc.evaluation.get("cv_mode", "full_build") != "build_only" and hasattr(model, "cross_validate"):
+            from sklearn.model_selection import TimeSeriesSplit
+            model.cross_validate(X=X, y=y, cv=TimeSeriesSplit(n_splits=int(mc.evaluation.get("n_splits", 3))))
+            meta["cv_duration_sec"] = time.time() - t0
+        t1 = time.time()
+        model.fit(X, y)
+        meta["model_training_duration_sec"] = time.time() - t1
+        meta["model_offset"] = len(X) - len(model.predict(X))
+        meta["model"] = model.get_metadata() if hasattr(model, "get_metadata") else {}
+        return model, meta
+
+    # ------------------------------------------------------------------ the batched build
+    def _build_bucket(self, mcs: List[FleetMachine], protos: List[Any], dev):
+        import torch
+        est0 = self._standard_parts(protos[0])
+        topo: FFTopology = est0._topology()
+        epochs = int(est0.kwargs.get("epochs", 1)); batch = int(est0.kwargs.get("batch_size") or 32)
+        do_shuffle = bool(est0.kwargs.get("shuffle", True))
+        l1_mean = est0.kwargs.get("l1_batch_norm", "sum") == "mean"
+        cv_mode = mcs[0].evaluation.get("cv_mode", "full_build")
+        k = int(mcs[0].evaluation.get("n_splits", 3)) if cv_mode == "full_build" else 0
+        M, T, To, P = len(mcs), topo.n_in, topo.n_out, topo.n_params
+
+        Xs = [np.asarray(getattr(m.X, "values", m.X)) for m in mcs]
+        alias = all(m.y is None or m.y is m.X for m in mcs)
+        rows = np.array([len(x) for x in Xs], np.int64)
+        off = np.concatenate([[0], np.cumsum(rows)])
+        xd = torch.as_tensor(np.ascontiguousarray(np.concatenate(Xs), np.float32), device=dev)
+        yd = None if alias else torch.as_tensor(np.ascontiguousarray(
+            np.concatenate([np.asarray(getattr(m.y, "values", m.y)) if m.y is not None else x
+                            for m, x in zip(mcs, Xs)]), np.float32), device=dev)
+        ysrc = xd if yd is None else yd
+
+        # jobs: per Machine k CV folds (training prefix) + the final fit on all rows
+        lo, hi, te_lo, te_hi = [], [], [], []
+        for m in range(M):
+            bounds = time_series_split_bounds(int(rows[m]), k) if k else []
+            for (s, e) in bounds:
+                lo.append(off[m]); hi.append(off[m] + s); te_lo.append(off[m] + s); te_hi.append(off[m] + e)
+            lo.append(off[m]); hi.append(off[m] + rows[m])
+        J = len(lo)
+        per = k + 1
+        lo_t = torch.as_tensor(np.asarray(lo, np.int64), device=dev)
+        hi_t = torch.as_tensor(np.asarray(hi, np.int64), device=dev)
+        t_start = time.time()
+        fleet = FFFleet(topo, M, dev)
+        in_scale, in_min = FFFleet.minmax_fit(xd, lo_t, hi_t)                 # Pipeline's MinMaxScaler per job
+        err_scale, _ = FFFleet.minmax_fit(ysrc, lo_t, hi_t)                   # detector scaler per job (diff.py:173)
+        seed = int(mcs[0].evaluation.get("seed", 0))
+        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        params = topo.glorot_init(J, gen, dev)
+        n_job = (np.asarray(hi) - np.asarray(lo)).astype(np.int64)
+        pool = poff = None
+        if do_shuffle:
+            pool = segmented_randperm(np.repeat(n_job, epochs), gen, dev)
+            poff = torch.as_tensor(np.concatenate([[0], np.cumsum(n_job * epochs)[:-1]]).astype(np.int64), device=dev)
+        hl, ha, _, _ = fleet.fit_jobs(xd, yd, lo_t, hi_t, params, in_scale=in_scale, in_min=in_min, epochs=epochs,
+                                      batch_size=batch, perm_pool=pool, perm_off=poff, l1_mean=l1_mean)
+        torch.cuda.synchronize()
+        t_fit = time.time() - t_start
+
+        feat_pf = agg_pf = None
+        if k:
+            # score every test fold with its fold model: virtual Machines over sub-ranges
+            fold_jobs = np.array([m * per + i for m in range(M) for i in range(k)])
+            vfleet = FFFleet(topo, M * k, dev)
+            sel = torch.as_tensor(fold_jobs, device=dev)
+            vfleet.set_params(params[sel]); vfleet.in_scale = in_scale[sel].contiguous()
+            vfleet.in_min = in_min[sel].contiguous(); vfleet.err_scale = err_scale[sel].contiguous()
+            vs = Schedule(rows_lo=te_lo, rows_hi=te_hi, rows_total=int(off[-1]))
+            prec = self.cv_precision if vfleet.tc_eligible() else "f32"
+            res = vfleet.score(vs, xd, yd, precision=prec, columns=("tag-anomaly-unscaled", "total-anomaly-scaled"))
+            tl = torch.as_tensor(np.asarray(te_lo, np.int64), device=dev)
+            th = torch.as_tensor(np.asarray(te_hi, np.int64), device=dev)
+            feat_pf = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], tl, th, 6).reshape(M, k, To)
+            agg_pf = FFFleet.rolling_min_max(res["total-anomaly-scaled"], tl, th, 6).reshape(M, k)
+        final = torch.arange(M, device=dev) * per + k
+        fleet.set_params(params[final]); fleet.in_scale = in_scale[final].contiguous()
+        fleet.in_min = in_min[final].contiguous(); fleet.err_scale = err_scale[final].contiguous()
+        if k:
+            fleet.feat_thr = feat_pf[:, -1].contiguous(); fleet.agg_thr = agg_pf[:, -1].contiguous()
+        torch.cuda.synchronize()
+        t_total = time.time() - t_start
+        self.last_fleet = fleet
+        self.last_schedule_rows = rows
+
+        # ---- materialise the per-Machine objects a sequential build would have produced
+        P_host = fleet.params.cpu().numpy(); hl_h = hl.cpu().numpy(); ha_h = ha.cpu().numpy()
+        xs_lo = (1.0 / in_scale.double()).cpu().numpy()           # data_range
+        in_scale_h = in_scale.double().cpu().numpy(); in_min_h = in_min.double().cpu().numpy()
+        es_h = err_scale.double().cpu().numpy()
+        feat_h = feat_pf.double().cpu().numpy() if k else None
+        agg_h = agg_pf.double().cpu().numpy() if k else None
+        out = []
+        for m, (mc, model) in enumerate(zip(mcs, protos)):
+            j = m * per + k
+            est = self._standard_parts(model)
+            est.model = _Model(topo, P_host[m])
+            est._history = History({"loss": [float(v) for v in hl_h[j]], "accuracy": [float(v) for v in ha_h[j]]},
+                                   {"verbose": 0, "epochs": epochs, "steps": int(-(-rows[m] // batch))},
+                                   list(range(epochs)))
+            Xm = Xs[m]
+            ym = Xm if (mc.y is None or mc.y is mc.X) else np.asarray(getattr(mc.y, "values", mc.y))
+            _set_minmax(model.base_estimator.steps[0][1], in_scale_h[j], in_min_h[j], Xm, mc.X)
+            ymin = ym.min(axis=0) if len(ym) else np.zeros(To)
+            _set_minmax(model.scaler, es_h[j], -ymin * es_h[j], ym, mc.y if mc.y is not None else mc.X)
+            tags = list(mc.y.columns) if isinstance(mc.y, pd.DataFrame) else (
+                list(mc.X.columns) if isinstance(mc.X, pd.DataFrame) and alias else list(range(To)))
+            if k:
+                model.feature_thresholds_per_fold_ = pd.DataFrame(feat_h[m], index=[f"fold-{i}" for i in range(k)], columns=tags)
+                model.aggregate_thresholds_per_fold_ = {f"fold-{i}": float(agg_h[m, i]) for i in range(k)}
+                model.smooth_feature_thresholds_per_fold_ = pd.DataFrame()
+                model.smooth_aggregate_thresholds_per_fold_ = {}
+                model.feature_thresholds_ = pd.Series(feat_h[m, -1], index=tags, name=f"fold-{k - 1}")
+                model.aggregate_threshold_ = float(agg_h[m, -1])
+                model.smooth_aggregate_threshold_ = None
+                model.smooth_feature_thresholds_ = None
+            meta = {"name": mc.name, "model_offset": 0, "model": model.get_metadata(),
+                    "fleet": {"machines_in_launch": M, "fit_jobs": J, "fit_duration_sec": t_fit,
+                              "build_duration_sec": t_total},
+                    "cv_fold_history": {f"fold-{i}": {"loss": [float(v) for v in hl_h[m * per + i]]} for i in range(k)}}
+            out.append((model, meta))
+        return out
+
+
+def _set_minmax(scaler: MinMaxScaler, scale, min_, data, frame):
+    """Give a sklearn MinMaxScaler the fitted state computed on the GPU."""
+    scale = np.asarray(scale, np.float64); min_ = np.asarray(min_, np.float64)
+    data = np.asarray(data)
+    scaler.scale_ = scale
+    scaler.min_ = min_
+    scaler.data_min_ = data.min(axis=0).astype(np.float64) if len(data) else np.zeros_like(scale)
+    scaler.data_max_ = data.max(axis=0).astype(np.float64) if len(data) else np.zeros_like(scale)
+    scaler.data_range_ = scaler.data_max_ - scaler.data_min_
+    scaler.n_features_in_ = data.shape[1]
+    scaler.n_samples_seen_ = len(data)
+    if isinstance(frame, pd.DataFrame) and all(isinstance(c, str) for c in frame.columns):
+        scaler.feature_names_in_ = np.asarray(frame.columns, dtype=object)
