@@ -95,9 +95,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
         // a barrier that never completes is a bug (lost TMA / MMA completion): fail loudly
         // instead of hanging the device (each failed try_wait already sleeps in hardware)
         if (!done && ++spins > (1u << 24)) __trap();
@@ -155,16 +155,26 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_fast(int code, float z) {
-    switch (code) {
-        case GB200_ACT_TANH: { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z)); return r; }
-        case GB200_ACT_RELU: return fmaxf(z, 0.0f);
-        case GB200_ACT_SIGMOID: return __fdividef(1.0f, 1.0f + __expf(-z));
-        case GB200_ACT_ELU: return z > 0.0f ? z : __expf(z) - 1.0f;
-        case GB200_ACT_SOFTPLUS: return z > 15.0f ? z : __logf(1.0f + __expf(z));
-        default: return z;
-    }
+template <int ACT>
+__device__ __forceinline__ float act_t(float z) {
+    if (ACT == GB200_ACT_TANH) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z)); return r; }
+    if (ACT == GB200_ACT_RELU) return fmaxf(z, 0.0f);
+    if (ACT == GB200_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-z));
+    if (ACT == GB200_ACT_ELU) return z > 0.0f ? z : __expf(z) - 1.0f;
+    if (ACT == GB200_ACT_SOFTPLUS) return z > 15.0f ? z : __logf(1.0f + __expf(z));
+    return z;
 }
+
+// dispatch a per-layer activation code to a compile-time template argument (once per layer, not per element)
+#define GB_DISPATCH_ACT(code, CALL)                                    \
+    switch (code) {                                                    \
+        case GB200_ACT_TANH:     { constexpr int ACT = GB200_ACT_TANH; CALL; break; }     \
+        case GB200_ACT_RELU:     { constexpr int ACT = GB200_ACT_RELU; CALL; break; }     \
+        case GB200_ACT_SIGMOID:  { constexpr int ACT = GB200_ACT_SIGMOID; CALL; break; }  \
+        case GB200_ACT_ELU:      { constexpr int ACT = GB200_ACT_ELU; CALL; break; }      \
+        case GB200_ACT_SOFTPLUS: { constexpr int ACT = GB200_ACT_SOFTPLUS; CALL; break; } \
+        default:                 { constexpr int ACT = GB200_ACT_LINEAR; CALL; break; }   \
+    }
 
 struct TcArgs {
     gb200_ff_arch arch;
@@ -180,10 +190,10 @@ struct TcArgs {
     int nwg;                 // warpgroups per CTA
     int tmem_cols_wg;        // accumulator columns per warpgroup
     int tmem_cols_total;     // power of two >= 32
-    int xtile_bytes;         // 128*T_in*4 rounded to 16
+    int xtile_bytes;         // 128*T_in*4 rounded to 128
     int ytile_bytes;         // 0 when y aliases x
     int abuf_bytes;          // 128*max_Kp*2
-    int vec_floats;          // per-Machine vectors: in_scale,in_min [T_in], |es|, ft [T_out]
+    int vp;                  // padded length of each per-Machine vector (multiple of 16 floats)
 };
 
 __device__ __forceinline__ int find_machine(const int32_t* tile_off, int n, int tile) {
@@ -192,8 +202,26 @@ __device__ __forceinline__ int find_machine(const int32_t* tile_off, int n, int 
     return lo;
 }
 
-// Copy one warp's rows (cnt floats, contiguous in smem and in HBM) out, optionally transforming
-// by a per-column factor.  MODE 0: copy, 1: * vec[col], 2: / vec[col].
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void store_a8(uint8_t* dst, const float* v) {
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst) = pk;
+}
+__device__ __forceinline__ void load16_bcast(const float* p, float* o) {       // 16-byte aligned broadcast loads
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+        o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+    }
+}
+
+// Copy one warp's rows (cnt floats, contiguous in smem and in HBM) out, optionally scaled per
+// column on the way (MODE 1: * vec[col]).
 template <int MODE>
 __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const float* __restrict__ src, int cnt,
                                               int T, const float* __restrict__ vec, int lane, bool vec16) {
@@ -205,19 +233,118 @@ __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const flo
             if (MODE != 0) {
                 int c0 = col, c1 = c0 + 1 == T ? 0 : c0 + 1, c2 = c1 + 1 == T ? 0 : c1 + 1, c3 = c2 + 1 == T ? 0 : c2 + 1;
                 if (T < 4) { c0 = o % T; c1 = (o + 1) % T; c2 = (o + 2) % T; c3 = (o + 3) % T; }
-                if (MODE == 1) { v.x *= vec[c0]; v.y *= vec[c1]; v.z *= vec[c2]; v.w *= vec[c3]; }
-                else { v.x = v.x / vec[c0]; v.y = v.y / vec[c1]; v.z = v.z / vec[c2]; v.w = v.w / vec[c3]; }
+                v.x *= vec[c0]; v.y *= vec[c1]; v.z *= vec[c2]; v.w *= vec[c3];
                 col += step; if (col >= T) col -= T;
             }
-            *reinterpret_cast<float4*>(dst + o) = v;
+            __stcs(reinterpret_cast<float4*>(dst + o), v);
         }
     } else {
         for (int o = lane; o < cnt; o += 32) {
             float v = src[o];
             if (MODE == 1) v *= vec[o % T];
-            if (MODE == 2) v = v / vec[o % T];
             dst[o] = v;
         }
+    }
+}
+
+// hidden layer: accumulator (TMEM) -> +bias -> activation -> bf16 A operand of the next layer
+template <int ACT>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane, const float* __restrict__ bias, int n_chunks,
+                                                uint8_t* __restrict__ arow) {
+    for (int c = 0; c < n_chunks; ++c) {
+        float v[16], b[16];
+        tmem_ld16(tmem_lane + c * 16, v);
+        load16_bcast(bias + c * 16, b);
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j] + b[j]);
+        store_a8(arow + (c * 2) * 2048, v);
+        store_a8(arow + (c * 2 + 1) * 2048, v + 8);
+    }
+}
+
+// final layer, pass 1: d = |yhat - y| written in place over the y tile; returns the two row sums
+template <int ACT, bool EVEN>
+__device__ __forceinline__ void final_pass1(uint32_t tmem_lane, const float* __restrict__ bias,
+                                            const float* __restrict__ v_es, float* __restrict__ yrow,
+                                            int T_out, float& su_out, float& ss_out) {
+    float su = 0.0f, ss = 0.0f;
+    const int full = T_out >> 4;
+    for (int c = 0; c < full; ++c) {
+        float v[16], b[16], e[16], yv[16];
+        tmem_ld16(tmem_lane + c * 16, v);
+        load16_bcast(bias + c * 16, b);
+        load16_bcast(v_es + c * 16, e);
+        if (EVEN) {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 t = *reinterpret_cast<const float2*>(yrow + c * 16 + 2 * j);
+                yv[2 * j] = t.x; yv[2 * j + 1] = t.y;
+            }
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) yv[j] = yrow[c * 16 + j];
+        }
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float d = fabsf(act_t<ACT>(v[j] + b[j]) - yv[j]);
+            const float s = d * e[j];
+            su = fmaf(d, d, su); ss = fmaf(s, s, ss);
+            yv[j] = d;
+        }
+        if (EVEN) {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float2*>(yrow + c * 16 + 2 * j) = make_float2(yv[2 * j], yv[2 * j + 1]);
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) yrow[c * 16 + j] = yv[j];
+        }
+    }
+    if (T_out & 15) {                                   // ragged last chunk
+        const int n0 = full * 16;
+        float v[16];
+        tmem_ld16(tmem_lane + n0, v);
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            if (n < T_out) {
+                const float d = fabsf(act_t<ACT>(v[j] + bias[n]) - yrow[n]);
+                const float s = d * v_es[n];
+                su = fmaf(d, d, su); ss = fmaf(s, s, ss);
+                yrow[n] = d;
+            }
+        }
+    }
+    su_out = su; ss_out = ss;
+}
+
+// final layer, pass 2: yhat overwrites the tile
+template <int ACT, bool EVEN>
+__device__ __forceinline__ void final_pass2(uint32_t tmem_lane, const float* __restrict__ bias,
+                                            float* __restrict__ yrow, int T_out) {
+    const int full = T_out >> 4;
+    for (int c = 0; c < full; ++c) {
+        float v[16], b[16];
+        tmem_ld16(tmem_lane + c * 16, v);
+        load16_bcast(bias + c * 16, b);
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j] + b[j]);
+        if (EVEN) {
+            #pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float2*>(yrow + c * 16 + 2 * j) = make_float2(v[2 * j], v[2 * j + 1]);
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) yrow[c * 16 + j] = v[j];
+        }
+    }
+    if (T_out & 15) {
+        const int n0 = full * 16;
+        float v[16];
+        tmem_ld16(tmem_lane + n0, v);
+        #pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (n0 + j < T_out) yrow[n0 + j] = act_t<ACT>(v[j] + bias[n0 + j]);
     }
 }
 
@@ -237,12 +364,13 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
     const int L = a.arch.n_layers;
     const int T_in = a.arch.widths[0], T_out = a.arch.widths[L];
     const bool y_sep = a.ytile_bytes != 0;
+    const float inv_T = 1.0f / (float)T_out;
 
     // ---- shared memory carve-up
     uint8_t* w_img = smem;                                                    // operand image
-    float* vecs = reinterpret_cast<float*>(smem + a.lay.total_bytes);         // per-Machine vectors
-    float* v_scale = vecs; float* v_min = vecs + T_in; float* v_es = vecs + 2 * T_in; float* v_ft = v_es + T_out;
-    uint8_t* wg_base = smem + a.lay.total_bytes + gb_round_up_dev(a.vec_floats * 4, 128)
+    float* vecs = reinterpret_cast<float*>(smem + a.lay.total_bytes);         // per-Machine vectors, padded to vp
+    float* v_scale = vecs; float* v_min = vecs + a.vp; float* v_es = vecs + 2 * a.vp; float* v_ift = vecs + 3 * a.vp;
+    uint8_t* wg_base = smem + a.lay.total_bytes + 4 * a.vp * 4
                      + (size_t)wg * (a.xtile_bytes + a.ytile_bytes + a.abuf_bytes);
     float* xbuf = reinterpret_cast<float*>(wg_base);
     float* ybuf = y_sep ? reinterpret_cast<float*>(wg_base + a.xtile_bytes) : xbuf;
@@ -264,6 +392,7 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
     const int t_begin = blockIdx.x * per_cta;
     const int t_end = min(t_begin + per_cta, a.tiles_total);
     uint32_t w_phase = 0, x_phase = 0, mma_phase = 0;
+    uint8_t* const arow = abuf + (wtid >> 3) * 128 + (wtid & 7) * 16;     // this row's 16-byte slot per K chunk
 
     int seg_begin = t_begin;
     while (seg_begin < t_end) {
@@ -276,173 +405,144 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
         }
         __syncthreads();
         const int m = s_seg_m, seg_end = s_seg_end;
-        for (int i = tid; i < T_in; i += blockDim.x) {
-            v_scale[i] = a.in_scale ? a.in_scale[(size_t)m * T_in + i] : 1.0f;
-            v_min[i] = a.in_min ? a.in_min[(size_t)m * T_in + i] : 0.0f;
-        }
-        for (int i = tid; i < T_out; i += blockDim.x) {
-            v_es[i] = a.err_scale ? fabsf(a.err_scale[(size_t)m * T_out + i]) : 1.0f;
-            v_ft[i] = a.feat_thr ? a.feat_thr[(size_t)m * T_out + i] : 1.0f;
+        for (int i = tid; i < a.vp; i += blockDim.x) {
+            v_scale[i] = (i < T_in) ? (a.in_scale ? a.in_scale[(size_t)m * T_in + i] : 1.0f) : 0.0f;
+            v_min[i] = (i < T_in && a.in_min) ? a.in_min[(size_t)m * T_in + i] : 0.0f;
+            v_es[i] = (i < T_out) ? (a.err_scale ? fabsf(a.err_scale[(size_t)m * T_out + i]) : 1.0f) : 0.0f;
+            v_ift[i] = (i < T_out && a.feat_thr) ? 1.0f / a.feat_thr[(size_t)m * T_out + i] : 0.0f;
         }
         mbar_wait(&w_bar, w_phase); w_phase ^= 1;
         __syncthreads();
         const int64_t m_row0 = a.row_lo[m], m_row1 = a.row_hi[m];
-        const float agg = a.agg_thr ? a.agg_thr[m] : 1.0f;
+        const float inv_agg = a.agg_thr ? 1.0f / a.agg_thr[m] : 1.0f;
 
-        if (wg < a.nwg) {
-            for (int tile = seg_begin + wg; tile < seg_end; tile += a.nwg) {
-                const int64_t row0 = m_row0 + (int64_t)(tile - a.tile_off[m]) * TILE;
-                const int nrows = (int)min((int64_t)TILE, m_row1 - row0);
-                const bool valid = wtid < nrows;
-                // ---- tile load: one contiguous run of nrows*T floats
-                const float* xsrc = a.x + row0 * T_in;
-                const float* ysrc = y_sep ? a.y + row0 * T_out : xsrc;
-                const uint32_t xbytes = (uint32_t)nrows * T_in * 4, ybytes = (uint32_t)nrows * T_out * 4;
-                const bool x16 = ((reinterpret_cast<uintptr_t>(xsrc) | xbytes) & 15) == 0;
-                const bool y16 = !y_sep || ((reinterpret_cast<uintptr_t>(ysrc) | ybytes) & 15) == 0;
-                if (x16 && y16) {
-                    if (wtid == 0) {
-                        mbar_expect_tx(&x_bar[wg], xbytes + (y_sep ? ybytes : 0));
-                        bulk_g2s(xbuf, xsrc, xbytes, &x_bar[wg]);
-                        if (y_sep) bulk_g2s(ybuf, ysrc, ybytes, &x_bar[wg]);
-                    }
-                    mbar_wait(&x_bar[wg], x_phase); x_phase ^= 1;
-                } else {
-                    for (int i = wtid; i < nrows * T_in; i += WG_THREADS) xbuf[i] = xsrc[i];
-                    if (y_sep) for (int i = wtid; i < nrows * T_out; i += WG_THREADS) ybuf[i] = ysrc[i];
-                    named_bar_sync(1 + wg, WG_THREADS);
+        for (int tile = seg_begin + wg; tile < seg_end; tile += a.nwg) {
+            const int64_t row0 = m_row0 + (int64_t)(tile - a.tile_off[m]) * TILE;
+            const int nrows = (int)min((int64_t)TILE, m_row1 - row0);
+            // ---- tile load: one contiguous run of nrows*T floats
+            const float* xsrc = a.x + row0 * T_in;
+            const float* ysrc = y_sep ? a.y + row0 * T_out : xsrc;
+            const uint32_t xbytes = (uint32_t)nrows * T_in * 4, ybytes = (uint32_t)nrows * T_out * 4;
+            const bool x16 = ((reinterpret_cast<uintptr_t>(xsrc) | xbytes) & 15) == 0;
+            const bool y16 = !y_sep || ((reinterpret_cast<uintptr_t>(ysrc) | ybytes) & 15) == 0;
+            if (x16 && y16) {
+                if (wtid == 0) {
+                    mbar_expect_tx(&x_bar[wg], xbytes + (y_sep ? ybytes : 0));
+                    bulk_g2s(xbuf, xsrc, xbytes, &x_bar[wg]);
+                    if (y_sep) bulk_g2s(ybuf, ysrc, ybytes, &x_bar[wg]);
                 }
-                // ---- A operand of layer 0: bf16(x*scale+min), canonical K-major core matrices
-                {
-                    const int Kp = a.lay.Kp[0];
-                    const float* xr = xbuf + wtid * T_in;
-                    uint8_t* arow = abuf + (wtid >> 3) * 128 + (wtid & 7) * 16;
-                    for (int c = 0; c < Kp / 8; ++c) {
-                        float v[8];
-                        #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = c * 8 + j;
-                            v[j] = (valid && k < T_in) ? fmaf(xr[k], v_scale[k], v_min[k]) : 0.0f;
-                        }
-                        uint4 pk;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                        *reinterpret_cast<uint4*>(arow + c * 2048) = pk;
-                    }
-                }
-                // ---- the Dense stack
-                for (int l = 0; l < L; ++l) {
-                    const int Kp = a.lay.Kp[l], Np = a.lay.Np[l];
-                    fence_proxy_async();            // generic-proxy A stores -> visible to the tensor core
-                    tc_fence_before();
-                    named_bar_sync(1 + wg, WG_THREADS);
-                    if (wtid == 0) {
-                        tc_fence_after();
-                        const uint32_t idesc = make_idesc(TILE, Np);
-                        const uint32_t a_addr = smem_u32(abuf), b_addr = smem_u32(w_img + a.lay.w_off[l]);
-                        const uint32_t b_lbo = (uint32_t)(Np / 8) * 128;
-                        for (int ks = 0; ks < Kp / 16; ++ks) {
-                            const uint64_t da = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
-                            const uint64_t db = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
-                            umma_bf16(tmem_acc, da, db, idesc, ks > 0 ? 1u : 0u);
-                        }
-                        umma_commit(&mma_bar[wg]);
-                    }
-                    mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
-                    tc_fence_after();
-                    if (l == L - 1) break;
-                    // hidden-layer epilogue: bias + activation -> next A operand
-                    const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[l]);
-                    const int code = a.arch.acts[l];
-                    uint8_t* arow = abuf + (wtid >> 3) * 128 + (wtid & 7) * 16;
-                    for (int c = 0; c < Np / 16; ++c) {
-                        float v[16];
-                        tmem_ld16(tmem_lane + c * 16, v);
-                        #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = act_fast(code, v[j] + bias[c * 16 + j]);
-                        #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 pk;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[h * 8 + 0], v[h * 8 + 1]);
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[h * 8 + 2], v[h * 8 + 3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[h * 8 + 4], v[h * 8 + 5]);
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[h * 8 + 6], v[h * 8 + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                            *reinterpret_cast<uint4*>(arow + (c * 2 + h) * 2048) = pk;
-                        }
-                    }
-                }
-                // ---- final epilogue
-                const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[L - 1]);
-                const int code = a.arch.acts[L - 1];
-                const int NpL = a.lay.Np[L - 1];
-                float* yrow = ybuf + wtid * T_out;
-                // pass 1: d = |yhat - y| in place over y; row totals in registers
-                float su = 0.0f, ss = 0.0f;
-                for (int c = 0; c < NpL / 16; ++c) {
-                    float v[16];
-                    tmem_ld16(tmem_lane + c * 16, v);
-                    if (valid) {
-                        #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int n = c * 16 + j;
-                            if (n < T_out) {
-                                const float yh = act_fast(code, v[j] + bias[n]);
-                                const float d = fabsf(yh - yrow[n]);
-                                const float s = d * v_es[n];
-                                su = fmaf(d, d, su); ss = fmaf(s, s, ss);
-                                yrow[n] = d;
-                            }
-                        }
-                    }
-                }
-                if (valid) {
-                    const int64_t row = row0 + wtid;
-                    const float ts = ss / (float)T_out;
-                    if (a.total_scaled) a.total_scaled[row] = ts;
-                    if (a.total_unscaled) a.total_unscaled[row] = su / (float)T_out;
-                    if (a.total_conf && a.agg_thr) a.total_conf[row] = ts / agg;
-                }
-                __syncwarp();
-                {
-                    const int wrows = max(0, min(32, nrows - warp_in_wg * 32));
-                    const int cnt = wrows * T_out;
-                    const int64_t goff = (row0 + warp_in_wg * 32) * T_out;
-                    const float* src = ybuf + warp_in_wg * 32 * T_out;
-                    const bool v16 = (((goff * 4) | (int64_t)(cnt * 4)) & 15) == 0 && ((warp_in_wg * 32 * T_out * 4) & 15) == 0
-                                     && ((reinterpret_cast<uintptr_t>(a.model_out) | reinterpret_cast<uintptr_t>(a.tag_scaled) |
-                                          reinterpret_cast<uintptr_t>(a.tag_unscaled) | reinterpret_cast<uintptr_t>(a.conf)) & 15) == 0;
-                    if (cnt > 0) {
-                        if (a.tag_unscaled) warp_copy_out<0>(a.tag_unscaled + goff, src, cnt, T_out, nullptr, lane, v16);
-                        if (a.tag_scaled) warp_copy_out<1>(a.tag_scaled + goff, src, cnt, T_out, v_es, lane, v16);
-                        if (a.conf && a.feat_thr) warp_copy_out<2>(a.conf + goff, src, cnt, T_out, v_ft, lane, v16);
-                    }
-                    __syncwarp();
-                    // pass 2: yhat overwrites the tile, then goes out the same way
-                    if (a.model_out) {
-                        for (int c = 0; c < NpL / 16; ++c) {
-                            float v[16];
-                            tmem_ld16(tmem_lane + c * 16, v);
-                            if (valid) {
-                                #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int n = c * 16 + j;
-                                    if (n < T_out) yrow[n] = act_fast(code, v[j] + bias[n]);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (cnt > 0) warp_copy_out<0>(a.model_out + goff, src, cnt, T_out, nullptr, lane, v16);
-                    }
-                }
-                // the tile buffers are about to be overwritten through the async proxy
-                fence_proxy_async();
-                tc_fence_before();
+                mbar_wait(&x_bar[wg], x_phase); x_phase ^= 1;
+            } else {
+                for (int i = wtid; i < nrows * T_in; i += WG_THREADS) xbuf[i] = xsrc[i];
+                if (y_sep) for (int i = wtid; i < nrows * T_out; i += WG_THREADS) ybuf[i] = ysrc[i];
                 named_bar_sync(1 + wg, WG_THREADS);
             }
+            // ---- A operand of layer 0: bf16(x*scale+min).  Rows past nrows hold stale data: rows never
+            // mix inside a GEMM and those rows are never stored, so they need no masking.
+            {
+                const int Kp = a.lay.Kp[0];
+                const float* xr = xbuf + wtid * T_in;
+                const int full = T_in >> 3;
+                if ((T_in & 1) == 0) {
+                    for (int c = 0; c < full; ++c) {
+                        float v[8];
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 t = *reinterpret_cast<const float2*>(xr + c * 8 + 2 * j);
+                            v[2 * j] = t.x; v[2 * j + 1] = t.y;
+                        }
+                        const float4 s0 = *reinterpret_cast<const float4*>(v_scale + c * 8), s1 = *reinterpret_cast<const float4*>(v_scale + c * 8 + 4);
+                        const float4 m0 = *reinterpret_cast<const float4*>(v_min + c * 8), m1 = *reinterpret_cast<const float4*>(v_min + c * 8 + 4);
+                        v[0] = fmaf(v[0], s0.x, m0.x); v[1] = fmaf(v[1], s0.y, m0.y); v[2] = fmaf(v[2], s0.z, m0.z); v[3] = fmaf(v[3], s0.w, m0.w);
+                        v[4] = fmaf(v[4], s1.x, m1.x); v[5] = fmaf(v[5], s1.y, m1.y); v[6] = fmaf(v[6], s1.z, m1.z); v[7] = fmaf(v[7], s1.w, m1.w);
+                        store_a8(arow + c * 2048, v);
+                    }
+                } else {
+                    for (int c = 0; c < full; ++c) {
+                        float v[8];
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(xr[c * 8 + j], v_scale[c * 8 + j], v_min[c * 8 + j]);
+                        store_a8(arow + c * 2048, v);
+                    }
+                }
+                int c = full;
+                if (T_in & 7) {
+                    float v[8];
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = c * 8 + j;
+                        v[j] = k < T_in ? fmaf(xr[k], v_scale[k], v_min[k]) : 0.0f;
+                    }
+                    store_a8(arow + c * 2048, v);
+                    ++c;
+                }
+                for (; c < Kp / 8; ++c) *reinterpret_cast<uint4*>(arow + c * 2048) = make_uint4(0, 0, 0, 0);
+            }
+            // ---- the Dense stack
+            for (int l = 0; l < L; ++l) {
+                const int Kp = a.lay.Kp[l], Np = a.lay.Np[l];
+                fence_proxy_async();            // generic-proxy A stores -> visible to the tensor core
+                tc_fence_before();
+                named_bar_sync(1 + wg, WG_THREADS);
+                if (wtid == 0) {
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc(TILE, Np);
+                    const uint32_t a_addr = smem_u32(abuf), b_addr = smem_u32(w_img + a.lay.w_off[l]);
+                    const uint32_t b_lbo = (uint32_t)(Np / 8) * 128;
+                    for (int ks = 0; ks < Kp / 16; ++ks) {
+                        const uint64_t da = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
+                        const uint64_t db = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
+                        umma_bf16(tmem_acc, da, db, idesc, ks > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&mma_bar[wg]);
+                }
+                mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
+                tc_fence_after();
+                if (l == L - 1) break;
+                const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[l]);
+                GB_DISPATCH_ACT(a.arch.acts[l], hidden_epilogue<ACT>(tmem_lane, bias, Np / 16, arow));
+            }
+            // ---- final epilogue
+            const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[L - 1]);
+            const int code = a.arch.acts[L - 1];
+            float* yrow = ybuf + wtid * T_out;
+            const bool even = (T_out & 1) == 0;
+            float su, ss;
+            if (even) { GB_DISPATCH_ACT(code, (final_pass1<ACT, true>(tmem_lane, bias, v_es, yrow, T_out, su, ss))); }
+            else      { GB_DISPATCH_ACT(code, (final_pass1<ACT, false>(tmem_lane, bias, v_es, yrow, T_out, su, ss))); }
+            if (wtid < nrows) {
+                const int64_t row = row0 + wtid;
+                const float ts = ss * inv_T;
+                if (a.total_scaled) a.total_scaled[row] = ts;
+                if (a.total_unscaled) a.total_unscaled[row] = su * inv_T;
+                if (a.total_conf && a.agg_thr) a.total_conf[row] = ts * inv_agg;
+            }
+            __syncwarp();
+            {
+                const int wrows = max(0, min(32, nrows - warp_in_wg * 32));
+                const int cnt = wrows * T_out;
+                const int64_t goff = (row0 + warp_in_wg * 32) * T_out;
+                const float* src = ybuf + warp_in_wg * 32 * T_out;
+                const bool v16 = (((goff * 4) | (int64_t)(cnt * 4)) & 15) == 0 && ((warp_in_wg * 32 * T_out * 4) & 15) == 0
+                                 && ((reinterpret_cast<uintptr_t>(a.model_out) | reinterpret_cast<uintptr_t>(a.tag_scaled) |
+                                      reinterpret_cast<uintptr_t>(a.tag_unscaled) | reinterpret_cast<uintptr_t>(a.conf)) & 15) == 0;
+                if (cnt > 0) {
+                    if (a.tag_unscaled) warp_copy_out<0>(a.tag_unscaled + goff, src, cnt, T_out, nullptr, lane, v16);
+                    if (a.tag_scaled) warp_copy_out<1>(a.tag_scaled + goff, src, cnt, T_out, v_es, lane, v16);
+                    if (a.conf && a.feat_thr) warp_copy_out<1>(a.conf + goff, src, cnt, T_out, v_ift, lane, v16);
+                }
+                __syncwarp();
+                if (a.model_out) {
+                    if (even) { GB_DISPATCH_ACT(code, (final_pass2<ACT, true>(tmem_lane, bias, yrow, T_out))); }
+                    else      { GB_DISPATCH_ACT(code, (final_pass2<ACT, false>(tmem_lane, bias, yrow, T_out))); }
+                    __syncwarp();
+                    if (cnt > 0) warp_copy_out<0>(a.model_out + goff, src, cnt, T_out, nullptr, lane, v16);
+                }
+            }
+            // the tile buffers are about to be overwritten through the async proxy
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_sync(1 + wg, WG_THREADS);
         }
         __syncthreads();            // all warpgroups done with this Machine's operand image
         seg_begin = seg_end;
@@ -495,11 +595,11 @@ int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const
     a.xtile_bytes = gb_round_up(TILE * T_in * 4, 128);
     a.ytile_bytes = a.y ? gb_round_up(TILE * T_out * 4, 128) : 0;
     a.abuf_bytes = TILE * a.lay.max_Kp * 2;
-    a.vec_floats = 2 * T_in + 2 * T_out;
+    a.vp = gb_round_up(T_in > T_out ? T_in : T_out, 16);
     int cols = 32; while (cols < a.lay.max_Np) cols <<= 1;
     a.tmem_cols_wg = cols;
     const size_t cap = 227 * 1024 - 1024;
-    const size_t fixed = (size_t)a.lay.total_bytes + gb_round_up(a.vec_floats * 4, 128);
+    const size_t fixed = (size_t)a.lay.total_bytes + (size_t)4 * a.vp * 4;
     const size_t per_wg = (size_t)a.xtile_bytes + a.ytile_bytes + a.abuf_bytes;
     int nwg = MAX_WG;
     while (nwg > 1 && (fixed + nwg * per_wg > cap || nwg * cols > 512)) --nwg;

@@ -136,6 +136,10 @@ class KerasBaseEstimator(BaseEstimator, GordoBase):
         out.update(self.kwargs)
         return out
 
+    def __sklearn_is_fitted__(self):
+        # sklearn.pipeline.Pipeline.predict/score call check_is_fitted on the last step
+        return self.model is not None
+
     def set_params(self, **params):
         if "kind" in params:
             self.kind = self.load_kind(params.pop("kind"))

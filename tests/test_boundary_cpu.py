@@ -1,0 +1,199 @@
+"""
+CPU-only tests of the drop-in boundary: factories, `kind` registry, definition
+codec hooks, get_params / clone, pickling, the output-frame contract.  They mirror the reference's
+own tests (cited per test); nothing here computes on a device.
+"""
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+from sklearn.base import clone
+from sklearn.pipeline import Pipeline
+from sklearn.preprocessing import MinMaxScaler
+
+from gordo_b200 import serializer
+from gordo_b200.machine.model import utils as model_utils
+from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector, DiffBasedKFCVAnomalyDetector
+from gordo_b200.machine.model.base import GordoBase
+from gordo_b200.machine.model.factories import feedforward_autoencoder as ffa, lstm_autoencoder as lstma
+from gordo_b200.machine.model.factories.utils import hourglass_calc_dims, check_dim_func_len
+from gordo_b200.machine.model.models import KerasAutoEncoder, KerasLSTMAutoEncoder, KerasLSTMForecast
+from gordo_b200.machine.model.register import register_model_builder
+
+
+# tests/gordo/machine/model/test_factories_utils.py:8-24
+@pytest.mark.parametrize("args,expected", [
+    ((0.2, 4, 5), (4, 3, 2, 1)), ((0.5, 3, 10), (8, 7, 5)), ((0.5, 3, 3), (3, 2, 2)),
+    ((0.3, 3, 10), (8, 5, 3)), ((1, 3, 10), (10, 10, 10)), ((0, 3, 100000), (66667, 33334, 1))])
+def test_hourglass_calc_dims_check_dims(args, expected):
+    assert hourglass_calc_dims(*args) == expected
+
+
+def test_check_dim_func_len():       # test_factories_utils.py:27-36
+    with pytest.raises(ValueError):
+        check_dim_func_len("test", dim=(256, 128), func=("tanh", "tanh", "tanh"))
+    with pytest.raises(ValueError):
+        check_dim_func_len("test", dim=(256, 128, 56), func=("tanh", "tanh"))
+
+
+def test_factory_topologies():
+    # docstrings feedforward_autoencoder.py:225-238, lstm_autoencoder.py:235-248
+    assert ffa.feedforward_hourglass(10).widths == [10, 8, 7, 5, 5, 7, 8, 10]
+    assert ffa.feedforward_hourglass(5).widths == [5, 4, 4, 3, 3, 4, 4, 5]
+    assert ffa.feedforward_hourglass(10, encoding_layers=1).widths == [10, 5, 5, 10]
+    t = ffa.feedforward_hourglass(10)
+    assert t.acts == ["tanh"] * 6 + ["linear"] and t.l1 == [0.0, 10e-5, 10e-5, 0.0, 0.0, 0.0, 0.0]
+    assert ffa.feedforward_symmetric(6, dims=(4, 2), funcs=("relu", "tanh")).acts == ["relu", "tanh", "tanh", "relu", "linear"]
+    lt = lstma.lstm_hourglass(10, lookback_window=7)
+    assert lt.units == [8, 7, 5, 5, 7, 8] and lt.lookback_window == 7 and lt.n_features_out == 10
+    with pytest.raises(ValueError):
+        ffa.feedforward_symmetric(4, dims=())
+    with pytest.raises(ValueError):
+        ffa.feedforward_model(4, encoding_dim=(3, 2), encoding_func=("tanh",))
+    with pytest.raises(ValueError):
+        ffa.feedforward_hourglass(4, optimizer="SGD")        # Adam only, loudly
+
+
+def test_registry_and_kind_validation():     # models.py:109-128, register.py:48-75
+    assert {"feedforward_model", "feedforward_symmetric", "feedforward_hourglass"} <= set(
+        register_model_builder.factories["KerasAutoEncoder"])
+    assert {"lstm_model", "lstm_symmetric", "lstm_hourglass"} <= set(register_model_builder.factories["KerasLSTMAutoEncoder"])
+    assert "lstm_model" in register_model_builder.factories["KerasLSTMForecast"]
+    with pytest.raises(ValueError):
+        KerasAutoEncoder(kind="no_such_kind")
+    with pytest.raises(ValueError):
+        KerasAutoEncoder(kind="no.such.module.factory")
+    with pytest.raises(ValueError):
+        register_model_builder(type="KerasAutoEncoder")(lambda features: None)
+
+    def my_factory(n_features, n_features_out=None, **kw):
+        return ffa.feedforward_symmetric(n_features, n_features_out, dims=(3,), funcs=("tanh",))
+    m = KerasAutoEncoder(kind=my_factory)
+    assert m.kind == "my_factory" and "my_factory" in register_model_builder.factories["KerasAutoEncoder"]
+    KerasAutoEncoder(kind="gordo_b200.machine.model.factories.feedforward_autoencoder.feedforward_hourglass")
+
+
+def test_definition_hooks_params_clone_pickle():
+    # models.py:146-171 + tests/gordo/serializer/definition_test_model.py protocol
+    m = KerasAutoEncoder.from_definition({"kind": "feedforward_hourglass", "epochs": 3, "compression_factor": 0.3})
+    assert isinstance(m, GordoBase)
+    assert m.into_definition() == {"kind": "feedforward_hourglass", "epochs": 3, "compression_factor": 0.3}
+    assert m.get_params() == {"kind": "feedforward_hourglass", "epochs": 3, "compression_factor": 0.3}
+    c = clone(m)
+    assert c is not m and c.get_params() == m.get_params() and c.model is None
+    assert m.get_metadata() == {}
+    m2 = pickle.loads(pickle.dumps(m))
+    assert m2.get_params() == m.get_params()
+    l = KerasLSTMAutoEncoder(kind="lstm_hourglass", lookback_window=5)
+    assert l.lookahead == 0 and KerasLSTMForecast(kind="lstm_model").lookahead == 1
+    assert l.get_metadata() == {"forecast_steps": 0}
+    assert clone(l).lookback_window == 5
+    from sklearn.exceptions import NotFittedError
+    with pytest.raises(NotFittedError):
+        m.score(np.zeros((3, 2)), np.zeros((3, 2)))
+    with pytest.raises(ValueError):
+        KerasAutoEncoder.get_n_features(np.zeros(3))
+
+
+def test_example_config_model_block_loads():
+    # examples/config.yaml:72-82, with gordo.* paths redirected onto gordo_b200.*
+    import yaml
+    block = yaml.safe_load("""
+    gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector:
+      base_estimator:
+        sklearn.pipeline.Pipeline:
+          steps:
+            - sklearn.preprocessing.MinMaxScaler
+            - gordo.machine.model.models.KerasAutoEncoder:
+                kind: feedforward_hourglass
+    """)
+    model = serializer.from_definition(block, redirect_gordo=True)
+    assert type(model) is DiffBasedAnomalyDetector and isinstance(model.base_estimator, Pipeline)
+    assert isinstance(model.base_estimator.steps[0][1], MinMaxScaler)
+    assert type(model.base_estimator.steps[1][1]) is KerasAutoEncoder
+    assert model.base_estimator.steps[1][1].kind == "feedforward_hourglass"
+    d = serializer.into_definition(model)
+    again = serializer.from_definition(d)
+    assert type(again.base_estimator.steps[1][1]) is KerasAutoEncoder
+    assert clone(model).get_params().keys() == model.get_params().keys()
+
+
+def test_detector_params_metadata_surface():
+    # tests/gordo/machine/model/anomaly/test_anomaly_detectors.py:55-57, 675-732
+    base = KerasAutoEncoder(kind="feedforward_hourglass")
+    sc = MinMaxScaler()
+    det = DiffBasedAnomalyDetector(base_estimator=base, scaler=sc, shuffle=True)
+    assert det.get_params() == dict(base_estimator=base, scaler=sc, shuffle=True)
+    det2 = DiffBasedAnomalyDetector(base_estimator=base, scaler=sc, window=144)
+    assert det2.smoothing_method == "smm" and det2.get_params()["window"] == 144
+    assert det.kind == "feedforward_hourglass"            # transparent into base_estimator (diff.py:78-86)
+    k = DiffBasedKFCVAnomalyDetector(base_estimator=base, scaler=sc)
+    assert k.get_params()["threshold_percentile"] == 0.99 and k.window == 144 and k.shuffle is True
+    assert pickle.loads(pickle.dumps(det)).shuffle is True
+    md = det.get_metadata()
+    assert md["window"] is None and "feature-thresholds" not in md
+
+
+# tests/gordo/machine/model/test_utils.py:35-106
+@pytest.mark.parametrize("dates", [pd.date_range("2016-01-01", "2016-01-02", periods=10), None])
+@pytest.mark.parametrize("tags", [["tag1", "tag2"], ["tag"]])
+@pytest.mark.parametrize("target_tag_list", (["tag1", "tag2"], ["tag3", "tag4"], ["tagA"], ["tag1"],
+                                             ["tagA", "tagB", "tagC"], None))
+@pytest.mark.parametrize("output_offset", (0, 1, 2, 3))
+def test_base_dataframe_creation(dates, tags, target_tag_list, output_offset):
+    rng = np.random.default_rng(0)
+    n = 10
+    model_input = rng.random((n, len(tags)))
+    model_output = rng.random((n, len(target_tag_list or list(range(20)))))[output_offset:]
+    df = model_utils.make_base_dataframe(tags=tags, model_input=model_input, model_output=model_output,
+                                         target_tag_list=target_tag_list, index=dates)
+    assert np.array_equal(df["model-input"].values, model_input[-len(df):, :])
+    assert df["model-input"].columns.tolist() == tags
+    assert np.array_equal(df["model-output"].values, model_output[-len(df):, :])
+    if target_tag_list is not None:
+        assert target_tag_list == df["model-output"].columns.tolist()
+    elif model_output.shape[1] == len(tags):
+        assert tags == df["model-output"].columns.tolist()
+    else:
+        assert list(map(str, range(model_output.shape[1]))) == df["model-output"].columns.tolist()
+    if dates is not None:
+        assert np.array_equal(df.index.values, dates.values[output_offset:])
+    else:
+        assert np.array_equal(df.index.values, np.arange(0, len(df)))
+
+
+def test_metrics_wrapper():          # tests/gordo/machine/model/test_utils.py:12-32
+    from sklearn.metrics import mean_squared_error
+    y = np.array([[1, 1], [2, 2], [3, 3], [4, 4], [5, 5]]) * [1, 100]
+    f = model_utils.metric_wrapper(mean_squared_error)
+    assert not np.isclose(f(y, y * [0.8, 1]), f(y, y * [1, 0.8]))
+    scaler = MinMaxScaler().fit(y)
+    g = model_utils.metric_wrapper(mean_squared_error, scaler=scaler)
+    assert np.isclose(g(y, y * [0.8, 1]), g(y, y * [1, 0.8]))
+
+
+def test_frame_layout_matches_reference_golden():
+    """assemble_frame reproduces the column tuples / start / end the REAL reference produced."""
+    import json, os
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    meta = json.load(open(os.path.join(G, "golden_meta.json")))
+    npz = np.load(os.path.join(G, "detector_golden.npz"))
+    for ci, case in enumerate(meta["cases"]):
+        pre = f"c{ci}_"
+        tags = [f"tag-{j}" for j in range(case["t"])]
+        idx = (pd.date_range("2019-01-01", periods=case["n"], freq="10min") if case["index"] == "dates"
+               else pd.RangeIndex(case["n"]))
+        groups = []
+        for g in case["groups"]:
+            v = npz[pre + "col_" + g]
+            if v.ndim == 2 and v.shape[1] == 1 and g.startswith(("total", "smooth-total")):
+                v = v[:, 0]
+            groups.append((g, v, tags if v.ndim == 2 else None))
+        df = model_utils.assemble_frame(groups, idx, pd.Timedelta(minutes=10))
+        assert [list(map(str, c)) for c in df.columns] == case["columns"]
+        assert len(df) == case["n_rows"]
+        if case["index"] == "dates":
+            assert df[("start", "")].iloc[:3].tolist() == case["start"]
+            assert df[("end", "")].iloc[:3].tolist() == case["end"]
+        np.testing.assert_array_equal(df["model-output"].to_numpy(), npz[pre + "col_model-output"])
