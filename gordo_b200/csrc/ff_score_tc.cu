@@ -6,13 +6,14 @@
 //
 // Structure (one persistent CTA per SM, NWG warpgroups = NWG independent "tile engines"):
 //   * the Machine's operand image (bf16 weights pre-packed in the tcgen05 canonical K-major
-//     no-swizzle layout + fp32 biases) is brought in once per CTA per Machine with ONE 1-D bulk
+//     no-swizzle layout, the bias as one extra K row) is brought in once per CTA per Machine with ONE 1-D bulk
 //     async copy (cp.async.bulk -> UBLKCP, mbarrier complete_tx);
 //   * each warpgroup: bulk-copies its [128 x T] fp32 tile (a tile of consecutive rows of a
 //     row-major matrix is one contiguous run in HBM), builds the bf16 A operand in shared memory
 //     (thread = row = TMEM lane), then for every layer one elected thread issues Kp/16
 //     tcgen05.mma (M=128, N=Np, K=16, fp32 accumulate in TMEM) + tcgen05.commit; all 128
-//     threads pull the accumulator back with tcgen05.ld (32x32b.x16), add bias, apply the
+//     threads pull the accumulator back with tcgen05.ld (32x32b.x16) (bias already added by the
+//     GEMM through a ones column of A), apply the
 //     activation and write the next layer's A operand;
 //   * final epilogue: |yhat - y| is written IN PLACE over the y tile, the row totals are reduced in
 //     registers, and the tile goes back to HBM as full-row contiguous runs (tag-anomaly-unscaled,
@@ -35,7 +36,6 @@ struct PackLayout {
     int n_layers;
     int Kp[GB200_MAX_LAYERS], Np[GB200_MAX_LAYERS];
     int w_off[GB200_MAX_LAYERS];     // byte offset of layer l's B operand
-    int b_off[GB200_MAX_LAYERS];     // byte offset of layer l's bias (fp32 [Np])
     int total_bytes;                 // multiple of 16
     int max_Kp, max_Np;
 };
@@ -45,13 +45,12 @@ PackLayout make_layout(const gb200_ff_arch* a) {
     p.n_layers = a->n_layers;
     int off = 0;
     for (int l = 0; l < a->n_layers; ++l) {
-        p.Kp[l] = gb_round_up(a->widths[l], 16);
+        p.Kp[l] = gb_round_up(a->widths[l] + 1, 16);      // +1: the bias row (A carries a ones column)
         p.Np[l] = gb_round_up(a->widths[l + 1], 16);
         p.w_off[l] = off; off += p.Kp[l] * p.Np[l] * 2;
         if (p.Kp[l] > p.max_Kp) p.max_Kp = p.Kp[l];
         if (p.Np[l] > p.max_Np) p.max_Np = p.Np[l];
     }
-    for (int l = 0; l < a->n_layers; ++l) { p.b_off[l] = off; off += p.Np[l] * 4; }
     p.total_bytes = gb_round_up(off, 16);
     return p;
 }
@@ -70,13 +69,14 @@ __global__ void pack_bf16_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_p
         //   (k/8) * (Np/8)*64 + (n/8)*64 + (n%8)*8 + (k%8)      [bf16 elements]
         for (int i = threadIdx.x; i < Kp * Np; i += blockDim.x) {
             const int k = i / Np, n = i - k * Np;
-            const float w = (k < win && n < wout) ? P[go + (int64_t)k * wout + n] : 0.0f;
+            float w = 0.0f;
+            if (n < wout) {
+                if (k < win) w = P[go + (int64_t)k * wout + n];
+                else if (k == win) w = P[go + (int64_t)win * wout + n];      // bias row, multiplied by A's ones column
+            }
             B[(k >> 3) * (Np >> 3) * 64 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
         }
-        go += (int64_t)win * wout;
-        float* bias = reinterpret_cast<float*>(out + lay.b_off[l]);
-        for (int i = threadIdx.x; i < Np; i += blockDim.x) bias[i] = i < wout ? P[go + i] : 0.0f;
-        go += wout;
+        go += (int64_t)win * wout + wout;
     }
 }
 
@@ -221,19 +221,24 @@ __device__ __forceinline__ void load16_bcast(const float* p, float* o) {       /
 }
 
 // Copy one warp's rows (cnt floats, contiguous in smem and in HBM) out, optionally scaled per
-// column on the way (MODE 1: * vec[col]).
+// column on the way (MODE 1).  `pat` is the per-column factor repeated periodically
+// (pat[i] = vec[i % T], i < T + 4) so the 4 factors of a float4 are one contiguous read.
 template <int MODE>
 __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const float* __restrict__ src, int cnt,
-                                              int T, const float* __restrict__ vec, int lane, bool vec16) {
+                                              int T, const float* __restrict__ pat, int lane, bool vec16) {
     if (vec16) {
         int col = (lane * 4) % T;
         const int step = 128 % T;
+        const bool even = (T & 1) == 0;
         for (int o = lane * 4; o < cnt; o += 128) {
             float4 v = *reinterpret_cast<const float4*>(src + o);
             if (MODE != 0) {
-                int c0 = col, c1 = c0 + 1 == T ? 0 : c0 + 1, c2 = c1 + 1 == T ? 0 : c1 + 1, c3 = c2 + 1 == T ? 0 : c2 + 1;
-                if (T < 4) { c0 = o % T; c1 = (o + 1) % T; c2 = (o + 2) % T; c3 = (o + 3) % T; }
-                v.x *= vec[c0]; v.y *= vec[c1]; v.z *= vec[c2]; v.w *= vec[c3];
+                if (even) {
+                    const float2 p0 = *reinterpret_cast<const float2*>(pat + col), p1 = *reinterpret_cast<const float2*>(pat + col + 2);
+                    v.x *= p0.x; v.y *= p0.y; v.z *= p1.x; v.w *= p1.y;
+                } else {
+                    v.x *= pat[col]; v.y *= pat[col + 1]; v.z *= pat[col + 2]; v.w *= pat[col + 3];
+                }
                 col += step; if (col >= T) col -= T;
             }
             __stcs(reinterpret_cast<float4*>(dst + o), v);
@@ -241,38 +246,39 @@ __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const flo
     } else {
         for (int o = lane; o < cnt; o += 32) {
             float v = src[o];
-            if (MODE == 1) v *= vec[o % T];
+            if (MODE == 1) v *= pat[o % T];
             dst[o] = v;
         }
     }
 }
 
-// hidden layer: accumulator (TMEM) -> +bias -> activation -> bf16 A operand of the next layer
+// hidden layer: accumulator (TMEM, bias already inside the GEMM) -> activation -> bf16 A operand of
+// the next layer, whose column `wout` is the ones column that carries the next bias
 template <int ACT>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane, const float* __restrict__ bias, int n_chunks,
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane, int n_chunks, int wout, int kp_next,
                                                 uint8_t* __restrict__ arow) {
     for (int c = 0; c < n_chunks; ++c) {
-        float v[16], b[16];
+        float v[16];
         tmem_ld16(tmem_lane + c * 16, v);
-        load16_bcast(bias + c * 16, b);
         #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j] + b[j]);
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j]);
         store_a8(arow + (c * 2) * 2048, v);
         store_a8(arow + (c * 2 + 1) * 2048, v + 8);
     }
+    for (int c = n_chunks * 2; c < kp_next / 8; ++c) *reinterpret_cast<uint4*>(arow + c * 2048) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<unsigned short*>(arow + (wout >> 3) * 2048 + (wout & 7) * 2) = 0x3F80;     // bf16(1.0)
 }
 
 // final layer, pass 1: d = |yhat - y| written in place over the y tile; returns the two row sums
 template <int ACT, bool EVEN>
-__device__ __forceinline__ void final_pass1(uint32_t tmem_lane, const float* __restrict__ bias,
+__device__ __forceinline__ void final_pass1(uint32_t tmem_lane,
                                             const float* __restrict__ v_es, float* __restrict__ yrow,
                                             int T_out, float& su_out, float& ss_out) {
     float su = 0.0f, ss = 0.0f;
     const int full = T_out >> 4;
     for (int c = 0; c < full; ++c) {
-        float v[16], b[16], e[16], yv[16];
+        float v[16], e[16], yv[16];
         tmem_ld16(tmem_lane + c * 16, v);
-        load16_bcast(bias + c * 16, b);
         load16_bcast(v_es + c * 16, e);
         if (EVEN) {
             #pragma unroll
@@ -286,7 +292,7 @@ __device__ __forceinline__ void final_pass1(uint32_t tmem_lane, const float* __r
         }
         #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float d = fabsf(act_t<ACT>(v[j] + b[j]) - yv[j]);
+            const float d = fabsf(act_t<ACT>(v[j]) - yv[j]);
             const float s = d * e[j];
             su = fmaf(d, d, su); ss = fmaf(s, s, ss);
             yv[j] = d;
@@ -308,7 +314,7 @@ __device__ __forceinline__ void final_pass1(uint32_t tmem_lane, const float* __r
         for (int j = 0; j < 16; ++j) {
             const int n = n0 + j;
             if (n < T_out) {
-                const float d = fabsf(act_t<ACT>(v[j] + bias[n]) - yrow[n]);
+                const float d = fabsf(act_t<ACT>(v[j]) - yrow[n]);
                 const float s = d * v_es[n];
                 su = fmaf(d, d, su); ss = fmaf(s, s, ss);
                 yrow[n] = d;
@@ -320,15 +326,13 @@ __device__ __forceinline__ void final_pass1(uint32_t tmem_lane, const float* __r
 
 // final layer, pass 2: yhat overwrites the tile
 template <int ACT, bool EVEN>
-__device__ __forceinline__ void final_pass2(uint32_t tmem_lane, const float* __restrict__ bias,
-                                            float* __restrict__ yrow, int T_out) {
+__device__ __forceinline__ void final_pass2(uint32_t tmem_lane, float* __restrict__ yrow, int T_out) {
     const int full = T_out >> 4;
     for (int c = 0; c < full; ++c) {
-        float v[16], b[16];
+        float v[16];
         tmem_ld16(tmem_lane + c * 16, v);
-        load16_bcast(bias + c * 16, b);
         #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j] + b[j]);
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j]);
         if (EVEN) {
             #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -344,7 +348,7 @@ __device__ __forceinline__ void final_pass2(uint32_t tmem_lane, const float* __r
         tmem_ld16(tmem_lane + n0, v);
         #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (n0 + j < T_out) yrow[n0 + j] = act_t<ACT>(v[j] + bias[n0 + j]);
+            if (n0 + j < T_out) yrow[n0 + j] = act_t<ACT>(v[j]);
     }
 }
 
@@ -369,8 +373,9 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
     // ---- shared memory carve-up
     uint8_t* w_img = smem;                                                    // operand image
     float* vecs = reinterpret_cast<float*>(smem + a.lay.total_bytes);         // per-Machine vectors, padded to vp
-    float* v_scale = vecs; float* v_min = vecs + a.vp; float* v_es = vecs + 2 * a.vp; float* v_ift = vecs + 3 * a.vp;
-    uint8_t* wg_base = smem + a.lay.total_bytes + 4 * a.vp * 4
+    float* v_scale = vecs; float* v_min = vecs + a.vp; float* v_es = vecs + 2 * a.vp;
+    float* pat_es = vecs + 3 * a.vp; float* pat_ift = vecs + 4 * a.vp + 16;          // periodic copies, T_out + 4 long
+    uint8_t* wg_base = smem + a.lay.total_bytes + (5 * a.vp + 32) * 4
                      + (size_t)wg * (a.xtile_bytes + a.ytile_bytes + a.abuf_bytes);
     float* xbuf = reinterpret_cast<float*>(wg_base);
     float* ybuf = y_sep ? reinterpret_cast<float*>(wg_base + a.xtile_bytes) : xbuf;
@@ -409,7 +414,11 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
             v_scale[i] = (i < T_in) ? (a.in_scale ? a.in_scale[(size_t)m * T_in + i] : 1.0f) : 0.0f;
             v_min[i] = (i < T_in && a.in_min) ? a.in_min[(size_t)m * T_in + i] : 0.0f;
             v_es[i] = (i < T_out) ? (a.err_scale ? fabsf(a.err_scale[(size_t)m * T_out + i]) : 1.0f) : 0.0f;
-            v_ift[i] = (i < T_out && a.feat_thr) ? 1.0f / a.feat_thr[(size_t)m * T_out + i] : 0.0f;
+        }
+        for (int i = tid; i < T_out + 4; i += blockDim.x) {
+            const int c = i % T_out;
+            pat_es[i] = a.err_scale ? fabsf(a.err_scale[(size_t)m * T_out + c]) : 1.0f;
+            pat_ift[i] = a.feat_thr ? 1.0f / a.feat_thr[(size_t)m * T_out + c] : 0.0f;
         }
         mbar_wait(&w_bar, w_phase); w_phase ^= 1;
         __syncthreads();
@@ -477,6 +486,7 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                     ++c;
                 }
                 for (; c < Kp / 8; ++c) *reinterpret_cast<uint4*>(arow + c * 2048) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<unsigned short*>(arow + (T_in >> 3) * 2048 + (T_in & 7) * 2) = 0x3F80;   // ones column
             }
             // ---- the Dense stack
             for (int l = 0; l < L; ++l) {
@@ -499,17 +509,15 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                 mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
                 tc_fence_after();
                 if (l == L - 1) break;
-                const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[l]);
-                GB_DISPATCH_ACT(a.arch.acts[l], hidden_epilogue<ACT>(tmem_lane, bias, Np / 16, arow));
+                GB_DISPATCH_ACT(a.arch.acts[l], hidden_epilogue<ACT>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], arow));
             }
             // ---- final epilogue
-            const float* bias = reinterpret_cast<const float*>(w_img + a.lay.b_off[L - 1]);
             const int code = a.arch.acts[L - 1];
             float* yrow = ybuf + wtid * T_out;
             const bool even = (T_out & 1) == 0;
             float su, ss;
-            if (even) { GB_DISPATCH_ACT(code, (final_pass1<ACT, true>(tmem_lane, bias, v_es, yrow, T_out, su, ss))); }
-            else      { GB_DISPATCH_ACT(code, (final_pass1<ACT, false>(tmem_lane, bias, v_es, yrow, T_out, su, ss))); }
+            if (even) { GB_DISPATCH_ACT(code, (final_pass1<ACT, true>(tmem_lane, v_es, yrow, T_out, su, ss))); }
+            else      { GB_DISPATCH_ACT(code, (final_pass1<ACT, false>(tmem_lane, v_es, yrow, T_out, su, ss))); }
             if (wtid < nrows) {
                 const int64_t row = row0 + wtid;
                 const float ts = ss * inv_T;
@@ -528,13 +536,13 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                                       reinterpret_cast<uintptr_t>(a.tag_unscaled) | reinterpret_cast<uintptr_t>(a.conf)) & 15) == 0;
                 if (cnt > 0) {
                     if (a.tag_unscaled) warp_copy_out<0>(a.tag_unscaled + goff, src, cnt, T_out, nullptr, lane, v16);
-                    if (a.tag_scaled) warp_copy_out<1>(a.tag_scaled + goff, src, cnt, T_out, v_es, lane, v16);
-                    if (a.conf && a.feat_thr) warp_copy_out<1>(a.conf + goff, src, cnt, T_out, v_ift, lane, v16);
+                    if (a.tag_scaled) warp_copy_out<1>(a.tag_scaled + goff, src, cnt, T_out, pat_es, lane, v16);
+                    if (a.conf && a.feat_thr) warp_copy_out<1>(a.conf + goff, src, cnt, T_out, pat_ift, lane, v16);
                 }
                 __syncwarp();
                 if (a.model_out) {
-                    if (even) { GB_DISPATCH_ACT(code, (final_pass2<ACT, true>(tmem_lane, bias, yrow, T_out))); }
-                    else      { GB_DISPATCH_ACT(code, (final_pass2<ACT, false>(tmem_lane, bias, yrow, T_out))); }
+                    if (even) { GB_DISPATCH_ACT(code, (final_pass2<ACT, true>(tmem_lane, yrow, T_out))); }
+                    else      { GB_DISPATCH_ACT(code, (final_pass2<ACT, false>(tmem_lane, yrow, T_out))); }
                     __syncwarp();
                     if (cnt > 0) warp_copy_out<0>(a.model_out + goff, src, cnt, T_out, nullptr, lane, v16);
                 }
@@ -595,11 +603,11 @@ int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const
     a.xtile_bytes = gb_round_up(TILE * T_in * 4, 128);
     a.ytile_bytes = a.y ? gb_round_up(TILE * T_out * 4, 128) : 0;
     a.abuf_bytes = TILE * a.lay.max_Kp * 2;
-    a.vp = gb_round_up(T_in > T_out ? T_in : T_out, 16);
+    a.vp = gb_round_up((T_in > T_out ? T_in : T_out) + 4, 16);
     int cols = 32; while (cols < a.lay.max_Np) cols <<= 1;
     a.tmem_cols_wg = cols;
     const size_t cap = 227 * 1024 - 1024;
-    const size_t fixed = (size_t)a.lay.total_bytes + (size_t)4 * a.vp * 4;
+    const size_t fixed = (size_t)a.lay.total_bytes + (size_t)(5 * a.vp + 32) * 4;
     const size_t per_wg = (size_t)a.xtile_bytes + a.ytile_bytes + a.abuf_bytes;
     int nwg = MAX_WG;
     while (nwg > 1 && (fixed + nwg * per_wg > cap || nwg * cols > 512)) --nwg;

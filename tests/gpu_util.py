@@ -16,7 +16,8 @@ def ff_forward_bf16(spec, params, X):
     h = bf16_round(X)
     n = len(params)
     for li, ((W, b), a) in enumerate(zip(params, spec["acts"])):
-        z = (h.astype(np.float64) @ bf16_round(W).astype(np.float64)).astype(np.float32) + b
+        # the bias rides inside the GEMM as a bf16 row of B (A carries a ones column)
+        z = (h.astype(np.float64) @ bf16_round(W).astype(np.float64) + bf16_round(b).astype(np.float64)).astype(np.float32)
         h = dense.act_fwd(a, z).astype(np.float32)
         if li < n - 1:
             h = bf16_round(h)
