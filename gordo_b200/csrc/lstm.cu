@@ -1,14 +1,420 @@
-// LSTM autoencoder / forecast kernels -- placeholder translation unit while the kernels are
-// being brought up; every entry point fails loudly (no CPU fallback).
+// LSTM autoencoder / forecast: KerasLSTMBaseEstimator.predict / .fit (gordo/machine/model/models.py:557-660)
+// over the [3P] Keras LSTM cell the factories of lstm_autoencoder.py:77-102 build
+// (gate order i,f,c,o; z = x.W + h.U + b; i,f,o = sigmoid; c~ = act(z_c); c = f*c + i*c~; h = o*act(c)).
+//
+// Windows are never materialised (models.py:713-793 builds [B,L,T] copies on the host): sequence b of
+// a launch is window `seq_base + b` of its Machine, i.e. rows [start, start+L) of the Machine's
+// sample matrix, scaled on the fly (MinMaxScaler.transform fused into the layer-0 operand load).
+//
+// This round: exact fp32 arithmetic on CUDA cores, time-step-synchronous over all stacked layers
+// (state per layer, no [B,L,u] sequence buffers for inference):
+//   lstm_step_fwd      one (layer, t): tiled GEMM [seq x (in+u)] x [(in+u) x 4u] with the gate
+//                      non-linearities, cell update and h = o*act(c) fused in the epilogue
+//   lstm_dense_out     yhat = out_act(h_last . Wd + bd)
+// training adds the cached-activation forward, lstm_bwd_gates / lstm_bwd_data (BPTT),
+// lstm_wgrad (sum over batch x time as one reduction per weight), Keras-form Adam.
+// The tensor-core (tcgen05) recurrent kernel is the next step for this path.
 #include "common.cuh"
+#include <vector>
+
+namespace {
+
+constexpr int ST_SEQ = 32;      // sequences per CTA tile
+constexpr int ST_UNITS = 16;    // units per CTA tile (x4 gates = 64 GEMM columns)
+constexpr int ST_K = 32;        // K slab
+constexpr int ST_THREADS = 256;
+
+struct LayerDims { int in, u; int64_t w_off, u_off, b_off; };
+
+struct LstmPlan {
+    int n_layers, T_in, T_out, L, lookahead, out_act;
+    LayerDims ld[GB200_MAX_LAYERS];
+    int acts[GB200_MAX_LAYERS];
+    int64_t dense_w_off, dense_b_off, n_params;
+    int sum_u, max_u, max_in;
+};
+
+LstmPlan make_plan(const gb200_lstm_arch* a) {
+    LstmPlan p{};
+    p.n_layers = a->n_layers; p.T_in = a->n_features; p.T_out = a->n_features_out;
+    p.L = a->lookback_window; p.lookahead = a->lookahead; p.out_act = a->out_act;
+    int64_t off = 0; int in = a->n_features;
+    for (int l = 0; l < a->n_layers; ++l) {
+        const int u = a->units[l];
+        p.ld[l].in = in; p.ld[l].u = u;
+        p.ld[l].w_off = off; off += (int64_t)in * 4 * u;
+        p.ld[l].u_off = off; off += (int64_t)u * 4 * u;
+        p.ld[l].b_off = off; off += 4 * u;
+        p.acts[l] = a->acts[l];
+        p.sum_u += u; if (u > p.max_u) p.max_u = u; if (in > p.max_in) p.max_in = in;
+        in = u;
+    }
+    p.dense_w_off = off; off += (int64_t)in * a->n_features_out;
+    p.dense_b_off = off; off += a->n_features_out;
+    p.n_params = off;
+    return p;
+}
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// A group = one Machine (predict) or one fit job (training).  nb = sequences of the group in this launch.
+struct GroupCtx {
+    const int64_t* rows_lo;   // [G] first sample row of the group
+    const int32_t* n_win;     // [G] windows of the group
+    int seq_base;             // first window of this launch (same for all groups: lock-step)
+    int cap;                  // max sequences per group in this launch
+};
+__device__ __forceinline__ int group_nb(const GroupCtx& g, int grp) {
+    const int n = g.n_win[grp] - g.seq_base;
+    return n < 0 ? 0 : (n > g.cap ? g.cap : n);
+}
+
+struct StepArgs {
+    GroupCtx g;
+    int in, u, act, t, layer;
+    const float* params; int64_t n_params, w_off, u_off, b_off;     // per group: params + grp*n_params
+    // layer input: layer 0 reads the sample matrix (scaled), others a [seq][in] slab
+    const float* x; int T_in; const float* in_scale; const float* in_min;          // layer 0
+    const float* xin; int64_t xin_seq_stride, xin_grp_stride;                      // layer > 0
+    const float* h_prev; int64_t hprev_seq_stride, hprev_grp_stride;               // nullptr at t == 0
+    float* h_out; int64_t hout_seq_stride, hout_grp_stride;
+    const float* c_prev; int64_t cprev_seq_stride, cprev_grp_stride;               // nullptr at t == 0
+    float* c_out; int64_t cout_seq_stride, cout_grp_stride;
+    // optional caches for BPTT ([seq] x stride): gates i,f,g,o (4u) and act(c) (u)
+    float* gates; int64_t gates_seq_stride, gates_grp_stride;
+    float* actc; int64_t actc_seq_stride, actc_grp_stride;
+};
+
+__global__ void __launch_bounds__(ST_THREADS)
+lstm_step_fwd_kernel(const __grid_constant__ StepArgs a) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    const int s0 = blockIdx.x * ST_SEQ;
+    if (s0 >= nb) return;
+    const int u0 = blockIdx.y * ST_UNITS;
+    const int u = a.u, in = a.in, K = in + u;
+    const float* P = a.params + (size_t)grp * a.n_params;
+    const float* W = P + a.w_off; const float* U = P + a.u_off; const float* bias = P + a.b_off;
+
+    __shared__ float As[ST_SEQ][ST_K + 1];
+    __shared__ __align__(16) float Ws[ST_K][ST_UNITS * 4];            // [k][unit][gate]
+
+    const int tid = threadIdx.x;
+    const int s_l = tid >> 3;                // sequence within tile (0..31)
+    const int uj = (tid & 7) * 2;            // two units per thread
+    float acc[2][4];
+    #pragma unroll
+    for (int q = 0; q < 2; ++q)
+        #pragma unroll
+        for (int gte = 0; gte < 4; ++gte) {
+            const int uu = u0 + uj + q;
+            acc[q][gte] = uu < u ? bias[gte * u + uu] : 0.0f;
+        }
+    const int64_t row0 = a.layer == 0 ? a.g.rows_lo[grp] + a.g.seq_base + a.t : 0;
+    const float* sc = (a.layer == 0 && a.in_scale) ? a.in_scale + (size_t)grp * a.T_in : nullptr;
+    const float* mn = (a.layer == 0 && a.in_min) ? a.in_min + (size_t)grp * a.T_in : nullptr;
+
+    for (int k0 = 0; k0 < K; k0 += ST_K) {
+        // ---- A slab: [seq][k] = concat(x_t, h_{t-1})
+        for (int i = tid; i < ST_SEQ * ST_K; i += ST_THREADS) {
+            const int ss = i / ST_K, kk = i - ss * ST_K;
+            const int s = s0 + ss, k = k0 + kk;
+            float v = 0.0f;
+            if (s < nb && k < K) {
+                if (k < in) {
+                    if (a.layer == 0) {
+                        v = a.x[(row0 + s) * a.T_in + k];
+                        if (sc) v = fmaf(v, sc[k], mn[k]);
+                    } else {
+                        v = a.xin[(size_t)grp * a.xin_grp_stride + (size_t)s * a.xin_seq_stride + k];
+                    }
+                } else if (a.h_prev) {
+                    v = a.h_prev[(size_t)grp * a.hprev_grp_stride + (size_t)s * a.hprev_seq_stride + (k - in)];
+                }
+            }
+            As[ss][kk] = v;
+        }
+        // ---- weight slab: rows k of [W;U], the 4 gate columns of 16 units
+        for (int i = tid; i < ST_K * ST_UNITS * 4; i += ST_THREADS) {
+            const int kk = i / (ST_UNITS * 4), r = i - kk * (ST_UNITS * 4);
+            const int gte = r / ST_UNITS, ul = r - gte * ST_UNITS;          // consecutive threads: consecutive units
+            const int k = k0 + kk, uu = u0 + ul;
+            float v = 0.0f;
+            if (k < K && uu < u) v = (k < in) ? W[(size_t)k * 4 * u + gte * u + uu] : U[(size_t)(k - in) * 4 * u + gte * u + uu];
+            Ws[kk][ul * 4 + gte] = v;
+        }
+        __syncthreads();
+        #pragma unroll 8
+        for (int kk = 0; kk < ST_K; ++kk) {
+            const float av = As[s_l][kk];
+            const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk][uj * 4]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk][uj * 4 + 4]);
+            acc[0][0] = fmaf(av, w0.x, acc[0][0]); acc[0][1] = fmaf(av, w0.y, acc[0][1]);
+            acc[0][2] = fmaf(av, w0.z, acc[0][2]); acc[0][3] = fmaf(av, w0.w, acc[0][3]);
+            acc[1][0] = fmaf(av, w1.x, acc[1][0]); acc[1][1] = fmaf(av, w1.y, acc[1][1]);
+            acc[1][2] = fmaf(av, w1.z, acc[1][2]); acc[1][3] = fmaf(av, w1.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+    const int s = s0 + s_l;
+    if (s >= nb) return;
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int uu = u0 + uj + q;
+        if (uu >= u) continue;
+        const float ig = sigmoidf_(acc[q][0]), fg = sigmoidf_(acc[q][1]);
+        const float gg = gb_act(a.act, acc[q][2]), og = sigmoidf_(acc[q][3]);
+        const float cp = a.c_prev ? a.c_prev[(size_t)grp * a.cprev_grp_stride + (size_t)s * a.cprev_seq_stride + uu] : 0.0f;
+        const float cn = fmaf(fg, cp, ig * gg);
+        const float ac = gb_act(a.act, cn);
+        a.c_out[(size_t)grp * a.cout_grp_stride + (size_t)s * a.cout_seq_stride + uu] = cn;
+        a.h_out[(size_t)grp * a.hout_grp_stride + (size_t)s * a.hout_seq_stride + uu] = og * ac;
+        if (a.gates) {
+            float* gp = a.gates + (size_t)grp * a.gates_grp_stride + (size_t)s * a.gates_seq_stride;
+            gp[uu] = ig; gp[u + uu] = fg; gp[2 * u + uu] = gg; gp[3 * u + uu] = og;
+            a.actc[(size_t)grp * a.actc_grp_stride + (size_t)s * a.actc_seq_stride + uu] = ac;
+        }
+    }
+}
+
+struct DenseArgs {
+    GroupCtx g;
+    int u, T_out, act;
+    const float* params; int64_t n_params, w_off, b_off;
+    const float* h; int64_t h_seq_stride, h_grp_stride;
+    float* out; const int64_t* out_row_off;      // predict: rows out_row_off[grp] + seq_base + s
+    float* out_local; int64_t ol_seq_stride, ol_grp_stride;      // training: [grp][seq][T_out]
+};
+
+__global__ void lstm_dense_out_kernel(const __grid_constant__ DenseArgs a) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    const float* P = a.params + (size_t)grp * a.n_params;
+    const float* Wd = P + a.w_off; const float* bd = P + a.b_off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * a.T_out; i += gridDim.x * blockDim.x) {
+        const int s = i / a.T_out, n = i - s * a.T_out;
+        const float* h = a.h + (size_t)grp * a.h_grp_stride + (size_t)s * a.h_seq_stride;
+        float acc = bd[n];
+        for (int k = 0; k < a.u; ++k) acc = fmaf(h[k], Wd[(size_t)k * a.T_out + n], acc);
+        const float y = gb_act(a.act, acc);
+        if (a.out) a.out[(a.out_row_off[grp] + a.g.seq_base + s) * a.T_out + n] = y;
+        if (a.out_local) a.out_local[(size_t)grp * a.ol_grp_stride + (size_t)s * a.ol_seq_stride + n] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ training
+struct LossArgs {
+    GroupCtx g;
+    int u, T_out, act, L, lookahead;
+    const float* params; int64_t n_params, w_off, b_off;
+    const float* y; const float* yhat; int64_t yh_seq_stride, yh_grp_stride;
+    const float* h_last; int64_t h_seq_stride, h_grp_stride;
+    float* dzd; int64_t dzd_grp_stride;              // [grp][seq][T_out]  dLoss/dz_dense
+    float* loss_sum;                                 // [grp] sum of squared errors of this step (atomic)
+};
+
+// dzd = 2/(nb*T_out) * (yhat - y) * out_act'(yhat); accumulates the squared error
+__global__ void lstm_loss_kernel(const __grid_constant__ LossArgs a) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    if (nb == 0) return;
+    const float inv = 2.0f / (float)(nb * a.T_out);
+    float sq = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * a.T_out; i += gridDim.x * blockDim.x) {
+        const int s = i / a.T_out, n = i - s * a.T_out;
+        const float yh = a.yhat[(size_t)grp * a.yh_grp_stride + (size_t)s * a.yh_seq_stride + n];
+        // target row of window (seq_base + s): start + L - 1 + lookahead (models.py:713-793)
+        const int64_t row = a.g.rows_lo[grp] + a.g.seq_base + s + a.L - 1 + a.lookahead;
+        const float d = yh - a.y[row * a.T_out + n];
+        sq = fmaf(d, d, sq);
+        float gr;
+        switch (a.act) {
+            case GB200_ACT_TANH: gr = 1.0f - yh * yh; break;
+            case GB200_ACT_RELU: gr = yh > 0.0f ? 1.0f : 0.0f; break;
+            case GB200_ACT_SIGMOID: gr = yh * (1.0f - yh); break;
+            case GB200_ACT_ELU: gr = yh > 0.0f ? 1.0f : yh + 1.0f; break;
+            case GB200_ACT_SOFTPLUS: gr = 1.0f - expf(-yh); break;
+            default: gr = 1.0f;
+        }
+        a.dzd[(size_t)grp * a.dzd_grp_stride + (size_t)s * a.T_out + n] = inv * d * gr;
+    }
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(a.loss_sum + grp, sq);
+}
+
+// generic small reductions used by the backward pass -------------------------------------------------
+// out[grp][s][k] (+)= sum_n A[grp][s][n] * B[grp][k][n]   (rows of B contiguous: "NT")
+struct NTArgs {
+    GroupCtx g;
+    int N, Kout;
+    const float* A; int64_t a_seq_stride, a_grp_stride;
+    const float* B; int64_t b_row_stride, b_grp_stride;      // B row k at B + k*b_row_stride
+    float* out; int64_t o_seq_stride, o_grp_stride;
+    int accumulate;
+};
+__global__ void lstm_nt_kernel(const __grid_constant__ NTArgs a) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < nb * a.Kout; i += nwarps) {
+        const int s = i / a.Kout, k = i - s * a.Kout;
+        const float* ap = a.A + (size_t)grp * a.a_grp_stride + (size_t)s * a.a_seq_stride;
+        const float* bp = a.B + (size_t)grp * a.b_grp_stride + (size_t)k * a.b_row_stride;
+        float acc = 0.0f;
+        for (int n = lane; n < a.N; n += 32) acc = fmaf(ap[n], bp[n], acc);
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            float* op = a.out + (size_t)grp * a.o_grp_stride + (size_t)s * a.o_seq_stride + k;
+            *op = a.accumulate ? *op + acc : acc;
+        }
+    }
+}
+
+struct BwdGateArgs {
+    GroupCtx g;
+    int u, act, t, L;
+    const float* dh_above; int64_t da_seq_stride, da_grp_stride;   // dLoss/dh_t from the layer above (may be null)
+    const float* dh_rec; int64_t dr_seq_stride, dr_grp_stride;     // from t+1 (null at t == L-1)
+    float* dc; int64_t dc_seq_stride, dc_grp_stride;               // running dLoss/dc (in/out)
+    const float* gates; int64_t g_seq_stride, g_grp_stride;        // i,f,g,o at t
+    const float* actc; int64_t ac_seq_stride, ac_grp_stride;       // act(c_t)
+    const float* c_t; int64_t ct_seq_stride, ct_grp_stride;
+    const float* c_prev; int64_t cp_seq_stride, cp_grp_stride;     // null at t == 0
+    float* dz; int64_t dz_seq_stride, dz_grp_stride;               // [seq][4u] out
+};
+__device__ __forceinline__ float act_grad_h(int code, float h) {
+    switch (code) {
+        case GB200_ACT_TANH: return 1.0f - h * h;
+        case GB200_ACT_RELU: return h > 0.0f ? 1.0f : 0.0f;
+        case GB200_ACT_SIGMOID: return h * (1.0f - h);
+        case GB200_ACT_ELU: return h > 0.0f ? 1.0f : h + 1.0f;
+        case GB200_ACT_SOFTPLUS: return 1.0f - expf(-h);
+        default: return 1.0f;
+    }
+}
+__global__ void lstm_bwd_gates_kernel(const __grid_constant__ BwdGateArgs a) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    const int u = a.u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * u; i += gridDim.x * blockDim.x) {
+        const int s = i / u, j = i - s * u;
+        float dh = 0.0f;
+        if (a.dh_above) dh += a.dh_above[(size_t)grp * a.da_grp_stride + (size_t)s * a.da_seq_stride + j];
+        if (a.dh_rec) dh += a.dh_rec[(size_t)grp * a.dr_grp_stride + (size_t)s * a.dr_seq_stride + j];
+        const float* gp = a.gates + (size_t)grp * a.g_grp_stride + (size_t)s * a.g_seq_stride;
+        const float ig = gp[j], fg = gp[u + j], gg = gp[2 * u + j], og = gp[3 * u + j];
+        const float ac = a.actc[(size_t)grp * a.ac_grp_stride + (size_t)s * a.ac_seq_stride + j];
+        const float cp = a.c_prev ? a.c_prev[(size_t)grp * a.cp_grp_stride + (size_t)s * a.cp_seq_stride + j] : 0.0f;
+        float* dcp = a.dc + (size_t)grp * a.dc_grp_stride + (size_t)s * a.dc_seq_stride + j;
+        const float dc_in = (a.t == a.L - 1) ? 0.0f : *dcp;
+        const float d_o = dh * ac;
+        const float dc = dc_in + dh * og * act_grad_h(a.act, ac);
+        *dcp = dc * fg;
+        float* dz = a.dz + (size_t)grp * a.dz_grp_stride + (size_t)s * a.dz_seq_stride;
+        dz[j] = dc * gg * ig * (1.0f - ig);
+        dz[u + j] = dc * cp * fg * (1.0f - fg);
+        dz[2 * u + j] = dc * ig * act_grad_h(a.act, gg);
+        dz[3 * u + j] = d_o * og * (1.0f - og);
+    }
+}
+
+// g[grp][k][n] = sum over (t, s) of A_t[grp][s][k] * dZ_t[grp][s][n]; A is either the layer input
+// sequence or the h_{t-1} sequence (zero at t == 0).  One thread per (k, n).
+struct WgradArgs {
+    GroupCtx g;
+    int Kdim, N, L, layer, T_in, shift;      // shift = 1: A_t = seq[t-1] (recurrent weights)
+    const float* x; const float* in_scale; const float* in_min;        // layer 0 input from the sample matrix
+    const float* aseq; int64_t a_t_stride, a_seq_stride, a_grp_stride; // otherwise [t][seq][Kdim]
+    const float* dz; int64_t dz_t_stride, dz_seq_stride, dz_grp_stride;
+    float* grad; int64_t grad_grp_stride; int64_t grad_off;            // [Kdim][N] at grad + grad_off
+    float* gbias; int64_t gbias_off;                                   // [N] (only when shift == 0 pass)
+};
+__global__ void lstm_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    const int total = a.Kdim * a.N + (a.gbias ? a.N : 0);
+    const float* sc = (a.layer == 0 && a.x && a.in_scale) ? a.in_scale + (size_t)grp * a.T_in : nullptr;
+    const float* mn = sc ? a.in_min + (size_t)grp * a.T_in : nullptr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        if (i < a.Kdim * a.N) {
+            const int k = i / a.N, n = i - k * a.N;
+            for (int t = a.shift; t < a.L; ++t) {
+                const float* dzp = a.dz + (size_t)grp * a.dz_grp_stride + (size_t)t * a.dz_t_stride + n;
+                for (int s = 0; s < nb; ++s) {
+                    float av;
+                    if (a.x) {
+                        av = a.x[(a.g.rows_lo[grp] + a.g.seq_base + s + t) * a.T_in + k];
+                        if (sc) av = fmaf(av, sc[k], mn[k]);
+                    } else {
+                        av = a.aseq[(size_t)grp * a.a_grp_stride + (size_t)(t - a.shift) * a.a_t_stride + (size_t)s * a.a_seq_stride + k];
+                    }
+                    acc = fmaf(av, dzp[(size_t)s * a.dz_seq_stride], acc);
+                }
+            }
+            a.grad[(size_t)grp * a.grad_grp_stride + a.grad_off + i] = acc;
+        } else {
+            const int n = i - a.Kdim * a.N;
+            for (int t = 0; t < a.L; ++t)
+                for (int s = 0; s < nb; ++s)
+                    acc += a.dz[(size_t)grp * a.dz_grp_stride + (size_t)t * a.dz_t_stride + (size_t)s * a.dz_seq_stride + n];
+            a.gbias[(size_t)grp * a.grad_grp_stride + a.gbias_off + n] = acc;
+        }
+    }
+}
+
+struct AdamArgs {
+    GroupCtx g; gb200_adam adam; int64_t n_params;
+    float* params; const float* grad; float* mv; int64_t* tcount;
+};
+__global__ void lstm_adam_kernel(const __grid_constant__ AdamArgs a) {
+    const int grp = blockIdx.z;
+    if (group_nb(a.g, grp) == 0) return;               // this job has no batch in this step
+    const float tf = (float)(a.tcount[grp] + 1);
+    const float alpha = a.adam.lr * sqrtf(1.0f - powf(a.adam.beta_2, tf)) / (1.0f - powf(a.adam.beta_1, tf));
+    float* P = a.params + (size_t)grp * a.n_params;
+    const float* G = a.grad + (size_t)grp * a.n_params;
+    float* M = a.mv + (size_t)grp * 2 * a.n_params; float* V = M + a.n_params;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_params; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gr = G[i];
+        float m = M[i], v = V[i];
+        m += (gr - m) * (1.0f - a.adam.beta_1);
+        v += (gr * gr - v) * (1.0f - a.adam.beta_2);
+        M[i] = m; V[i] = v;
+        P[i] -= alpha * m / (sqrtf(v) + a.adam.epsilon);
+    }
+}
+__global__ void lstm_step_end_kernel(GroupCtx g, int n_groups, int64_t* tcount, const float* loss_sum,
+                                     float* epoch_acc, int T_out, float* primer_loss) {
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= n_groups) return;
+    const int nb = group_nb(g, grp);
+    if (nb == 0) return;
+    tcount[grp] += 1;
+    const float batch_loss = loss_sum[grp] / (float)(nb * T_out);
+    if (primer_loss) primer_loss[grp] = batch_loss;
+    else epoch_acc[grp] += batch_loss * nb;            // Keras: sample-weighted running mean
+}
+__global__ void lstm_epoch_end_kernel(int n_groups, const int32_t* n_win, float* epoch_acc, float* hist, int epochs, int e) {
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= n_groups) return;
+    hist[(size_t)grp * epochs + e] = n_win[grp] > 0 ? epoch_acc[grp] / (float)n_win[grp] : NAN;
+    epoch_acc[grp] = 0.0f;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
 
 extern "C" {
 
 int64_t gb200_lstm_param_count(const gb200_lstm_arch* a) {
     if (!a || a->n_layers < 1 || a->n_layers > GB200_MAX_LAYERS) return 0;
-    int64_t n = 0, in = a->n_features;
-    for (int l = 0; l < a->n_layers; ++l) { const int64_t u = a->units[l]; n += in * 4 * u + u * 4 * u + 4 * u; in = u; }
-    return n + in * a->n_features_out + a->n_features_out;
+    return make_plan(a).n_params;
 }
 
 int64_t gb200_lstm_out_rows(const gb200_lstm_arch* a, int64_t n_rows) {
@@ -17,20 +423,315 @@ int64_t gb200_lstm_out_rows(const gb200_lstm_arch* a, int64_t n_rows) {
     return n > 0 ? n : 0;
 }
 
-int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch*, int64_t) { return 0; }
-int64_t gb200_lstm_fit_scratch_bytes(const gb200_lstm_arch*, int32_t, int32_t) { return 0; }
-
-int gb200_lstm_predict(gb200_fleet*, const gb200_lstm_arch*, const float*, const float*, const float*,
-                       const float*, const int64_t*, float*, void*, int64_t, void*) {
-    gb_set_error("gb200_lstm_predict: not implemented in this build");
-    return GB_ERR_UNSUPPORTED;
+// predict scratch: per layer two h buffers + one c buffer of [max_windows][u]
+int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch* a, int64_t max_windows) {
+    if (!a || a->n_layers < 1 || a->n_layers > GB200_MAX_LAYERS || max_windows < 1) return 0;
+    const LstmPlan p = make_plan(a);
+    return (int64_t)align256((size_t)3 * p.sum_u * max_windows * sizeof(float)) + 1024;
 }
 
-int gb200_lstm_fit(const gb200_lstm_arch*, const gb200_adam*, int32_t, const int64_t*, const int64_t*,
-                   const float*, const float*, const float*, const float*, int32_t, int32_t, float*,
-                   float*, float*, void*, int64_t, void*) {
-    gb_set_error("gb200_lstm_fit: not implemented in this build");
-    return GB_ERR_UNSUPPORTED;
+static int check_lstm_arch(const gb200_lstm_arch* a) {
+    GB_REQUIRE(a != nullptr, "arch is NULL");
+    GB_REQUIRE(a->n_layers >= 1 && a->n_layers <= GB200_MAX_LAYERS, "n_layers=%d out of range", a->n_layers);
+    GB_REQUIRE(a->n_features >= 1 && a->n_features_out >= 1, "bad feature counts");
+    GB_REQUIRE(a->lookback_window >= 1 && a->lookahead >= 0, "bad lookback_window / lookahead");
+    for (int l = 0; l < a->n_layers; ++l) GB_REQUIRE(a->units[l] >= 1, "units[%d] must be >= 1", l);
+    return GB_OK;
+}
+
+int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, const float* params,
+                       const float* in_scale, const float* in_min, const float* x,
+                       const int64_t* out_row_off, float* model_out,
+                       void* scratch, int64_t scratch_bytes, void* stream_) {
+    GB_REQUIRE(f != nullptr, "fleet is NULL");
+    int rc = check_lstm_arch(arch); if (rc) return rc;
+    GB_REQUIRE(params && x && out_row_off && model_out && scratch, "NULL argument");
+    GB_REQUIRE((in_scale == nullptr) == (in_min == nullptr), "in_scale and in_min must be given together");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const LstmPlan p = make_plan(arch);
+    const int64_t cap64 = (scratch_bytes - 1024) / ((int64_t)3 * p.sum_u * sizeof(float));
+    GB_REQUIRE(cap64 >= 1, "scratch too small (see gb200_lstm_scratch_bytes)");
+    const int cap = (int)(cap64 > (1 << 22) ? (1 << 22) : cap64);
+    float* base = (float*)scratch;
+    // per Machine n_win lives on the device next to the schedule: build a tiny array in the scratch tail
+    int32_t* d_nwin = (int32_t*)((char*)scratch + scratch_bytes - 1024);
+    for (int m = 0; m < f->n_machines; ++m) {
+        const int64_t rows = f->h_row_hi[m] - f->h_row_lo[m];
+        const int64_t n_win = rows - p.L + 1 - p.lookahead;
+        if (rows <= 0) continue;
+        GB_REQUIRE(p.L < rows, "For KerasLSTMForecast lookback_window must be < size of X (machine %d)", m);
+        if (n_win <= 0) continue;
+        const int32_t nw32 = (int32_t)n_win;
+        GB_CUDA_CHECK(cudaMemcpyAsync(d_nwin, &nw32, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+        for (int64_t k0 = 0; k0 < n_win; k0 += cap) {
+            const int nb = (int)((n_win - k0) < cap ? (n_win - k0) : cap);
+            GroupCtx g{f->d_row_lo + m, d_nwin, (int)k0, cap};
+            // state layout: for layer l: hA[cap][u], hB[cap][u], c[cap][u]
+            size_t off = 0;
+            float* hA[GB200_MAX_LAYERS]; float* hB[GB200_MAX_LAYERS]; float* cS[GB200_MAX_LAYERS];
+            for (int l = 0; l < p.n_layers; ++l) {
+                hA[l] = base + off; off += (size_t)cap * p.ld[l].u;
+                hB[l] = base + off; off += (size_t)cap * p.ld[l].u;
+                cS[l] = base + off; off += (size_t)cap * p.ld[l].u;
+            }
+            for (int t = 0; t < p.L; ++t) {
+                for (int l = 0; l < p.n_layers; ++l) {
+                    StepArgs a{};
+                    a.g = g; a.in = p.ld[l].in; a.u = p.ld[l].u; a.act = p.acts[l]; a.t = t; a.layer = l;
+                    a.params = params + (size_t)m * p.n_params; a.n_params = 0;
+                    a.w_off = p.ld[l].w_off; a.u_off = p.ld[l].u_off; a.b_off = p.ld[l].b_off;
+                    a.x = x; a.T_in = p.T_in;
+                    a.in_scale = in_scale ? in_scale + (size_t)m * p.T_in : nullptr;
+                    a.in_min = in_min ? in_min + (size_t)m * p.T_in : nullptr;
+                    float* hcur = (t & 1) ? hB[l] : hA[l];
+                    float* hprev = (t & 1) ? hA[l] : hB[l];
+                    if (l > 0) { a.xin = (t & 1) ? hB[l - 1] : hA[l - 1]; a.xin_seq_stride = p.ld[l - 1].u; }
+                    a.h_prev = t > 0 ? hprev : nullptr; a.hprev_seq_stride = a.u;
+                    a.h_out = hcur; a.hout_seq_stride = a.u;
+                    a.c_prev = t > 0 ? cS[l] : nullptr; a.cprev_seq_stride = a.u;
+                    a.c_out = cS[l]; a.cout_seq_stride = a.u;
+                    dim3 grid(cdiv(nb, ST_SEQ), cdiv(a.u, ST_UNITS), 1);
+                    lstm_step_fwd_kernel<<<grid, ST_THREADS, 0, stream>>>(a);
+                }
+            }
+            DenseArgs d{};
+            d.g = g; d.u = p.ld[p.n_layers - 1].u; d.T_out = p.T_out; d.act = p.out_act;
+            d.params = params + (size_t)m * p.n_params; d.n_params = 0; d.w_off = p.dense_w_off; d.b_off = p.dense_b_off;
+            d.h = ((p.L - 1) & 1) ? hB[p.n_layers - 1] : hA[p.n_layers - 1]; d.h_seq_stride = d.u;
+            d.out = model_out; d.out_row_off = out_row_off + m;
+            int blocks = cdiv(nb * p.T_out, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+            lstm_dense_out_kernel<<<dim3(blocks, 1, 1), 256, 0, stream>>>(d);
+            GB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    return GB_OK;
+}
+
+// ---- training scratch (per job): see the layout in gb200_lstm_fit
+static size_t fit_floats_per_job(const LstmPlan& p, int B) {
+    size_t n = 0;
+    const size_t BL = (size_t)B * p.L;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const size_t u = p.ld[l].u;
+        n += BL * u * 3;            // hs, cs, act(c)
+        n += BL * 4 * u * 2;        // gates, dz
+        n += BL * u;                // dH (dLoss/dh_t delivered to this layer from above)
+        n += (size_t)B * u * 2;     // dh_rec, dc
+    }
+    n += (size_t)B * p.T_out * 2;   // yhat, dzd
+    n += (size_t)p.n_params * 3;    // grad, m, v
+    return n + 64;
+}
+
+int64_t gb200_lstm_fit_scratch_bytes(const gb200_lstm_arch* a, int32_t n_jobs, int32_t batch_size) {
+    if (!a || a->n_layers < 1 || a->n_layers > GB200_MAX_LAYERS || n_jobs < 1 || batch_size < 1) return 0;
+    const LstmPlan p = make_plan(a);
+    return (int64_t)align256(fit_floats_per_job(p, batch_size) * sizeof(float)) * n_jobs + 4096 + (int64_t)n_jobs * 64;
+}
+
+int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t n_jobs,
+                   const int64_t* job_rows_lo_host, const int64_t* job_rows_hi_host,
+                   const float* in_scale, const float* in_min, const float* x, const float* y,
+                   int32_t epochs, int32_t batch_size, float* params,
+                   float* hist_loss, float* primer_loss,
+                   void* scratch, int64_t scratch_bytes, void* stream_) {
+    int rc = check_lstm_arch(arch); if (rc) return rc;
+    GB_REQUIRE(adam && job_rows_lo_host && job_rows_hi_host && x && params && scratch, "NULL argument");
+    GB_REQUIRE(n_jobs >= 1 && epochs >= 1 && batch_size >= 1, "bad n_jobs / epochs / batch_size");
+    GB_REQUIRE((in_scale == nullptr) == (in_min == nullptr), "in_scale and in_min must be given together");
+    GB_REQUIRE(y != nullptr || arch->n_features == arch->n_features_out, "y may alias x only when n_features == n_features_out");
+    GB_REQUIRE(scratch_bytes >= gb200_lstm_fit_scratch_bytes(arch, n_jobs, batch_size), "scratch too small (see gb200_lstm_fit_scratch_bytes)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const LstmPlan p = make_plan(arch);
+    const int J = n_jobs, B = batch_size, L = p.L;
+    const float* ysrc = y ? y : x;
+
+    // ---- control block at the tail of the scratch: rows_lo[J] (i64), n_win[J] (i32), tcount[J] (i64), loss_sum[J], epoch_acc[J]
+    char* tail = (char*)scratch + scratch_bytes - (4096 + (size_t)J * 64);
+    int64_t* d_rows_lo = (int64_t*)tail;
+    int64_t* d_tcount = d_rows_lo + J;
+    int32_t* d_nwin = (int32_t*)(d_tcount + J);
+    float* d_loss = (float*)(d_nwin + J);
+    float* d_epoch = d_loss + J;
+    std::vector<int64_t> rows_lo(J); std::vector<int32_t> nwin(J); int max_win = 0;
+    for (int j = 0; j < J; ++j) {
+        const int64_t rows = job_rows_hi_host[j] - job_rows_lo_host[j];
+        GB_REQUIRE(L < rows, "For KerasLSTMForecast lookback_window must be < size of X (job %d)", j);
+        rows_lo[j] = job_rows_lo_host[j];
+        const int64_t nw = rows - L + 1 - p.lookahead;
+        nwin[j] = (int32_t)(nw > 0 ? nw : 0);
+        if (nwin[j] > max_win) max_win = nwin[j];
+    }
+    GB_CUDA_CHECK(cudaMemcpyAsync(d_rows_lo, rows_lo.data(), sizeof(int64_t) * J, cudaMemcpyHostToDevice, stream));
+    GB_CUDA_CHECK(cudaMemcpyAsync(d_nwin, nwin.data(), sizeof(int32_t) * J, cudaMemcpyHostToDevice, stream));
+    GB_CUDA_CHECK(cudaMemsetAsync(d_tcount, 0, sizeof(int64_t) * J, stream));
+    GB_CUDA_CHECK(cudaMemsetAsync(d_epoch, 0, sizeof(float) * J, stream));
+    GB_CUDA_CHECK(cudaStreamSynchronize(stream));       // host vectors go out of scope safely; one-off
+
+    const size_t per_job = align256(fit_floats_per_job(p, B) * sizeof(float)) / sizeof(float);
+    float* S = (float*)scratch;
+    // per-job layout offsets (floats)
+    size_t o = 0;
+    size_t hs_o[GB200_MAX_LAYERS], cs_o[GB200_MAX_LAYERS], ac_o[GB200_MAX_LAYERS], gt_o[GB200_MAX_LAYERS],
+           dz_o[GB200_MAX_LAYERS], dH_o[GB200_MAX_LAYERS], dr_o[GB200_MAX_LAYERS], dc_o[GB200_MAX_LAYERS];
+    const size_t BL = (size_t)B * L;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const size_t u = p.ld[l].u;
+        hs_o[l] = o; o += BL * u; cs_o[l] = o; o += BL * u; ac_o[l] = o; o += BL * u;
+        gt_o[l] = o; o += BL * 4 * u; dz_o[l] = o; o += BL * 4 * u; dH_o[l] = o; o += BL * u;
+        dr_o[l] = o; o += (size_t)B * u; dc_o[l] = o; o += (size_t)B * u;
+    }
+    const size_t yh_o = o; o += (size_t)B * p.T_out;
+    const size_t dzd_o = o; o += (size_t)B * p.T_out;
+    const size_t grad_o = o; o += p.n_params;
+    const size_t mv_o = o; o += 2 * (size_t)p.n_params;
+    for (int j = 0; j < J; ++j)
+        GB_CUDA_CHECK(cudaMemsetAsync(S + (size_t)j * per_job + mv_o, 0, sizeof(float) * 2 * p.n_params, stream));
+    const int64_t gs = (int64_t)per_job;            // group stride of everything in the scratch
+
+    // sequence buffers are [t][seq][width]: t stride = B*width, seq stride = width
+    auto run_step = [&](int seq_base, int cap, float* primer_out) -> int {
+        GroupCtx g{d_rows_lo, d_nwin, seq_base, cap};
+        GB_CUDA_CHECK(cudaMemsetAsync(d_loss, 0, sizeof(float) * J, stream));
+        // ---------------- forward with caches
+        for (int t = 0; t < L; ++t) {
+            for (int l = 0; l < p.n_layers; ++l) {
+                const int u = p.ld[l].u;
+                StepArgs a{};
+                a.g = g; a.in = p.ld[l].in; a.u = u; a.act = p.acts[l]; a.t = t; a.layer = l;
+                a.params = params; a.n_params = p.n_params;
+                a.w_off = p.ld[l].w_off; a.u_off = p.ld[l].u_off; a.b_off = p.ld[l].b_off;
+                a.x = x; a.T_in = p.T_in; a.in_scale = in_scale; a.in_min = in_min;
+                if (l > 0) { a.xin = S + hs_o[l - 1] + (size_t)t * B * p.ld[l - 1].u; a.xin_seq_stride = p.ld[l - 1].u; a.xin_grp_stride = gs; }
+                a.h_prev = t > 0 ? S + hs_o[l] + (size_t)(t - 1) * B * u : nullptr; a.hprev_seq_stride = u; a.hprev_grp_stride = gs;
+                a.h_out = S + hs_o[l] + (size_t)t * B * u; a.hout_seq_stride = u; a.hout_grp_stride = gs;
+                a.c_prev = t > 0 ? S + cs_o[l] + (size_t)(t - 1) * B * u : nullptr; a.cprev_seq_stride = u; a.cprev_grp_stride = gs;
+                a.c_out = S + cs_o[l] + (size_t)t * B * u; a.cout_seq_stride = u; a.cout_grp_stride = gs;
+                a.gates = S + gt_o[l] + (size_t)t * B * 4 * u; a.gates_seq_stride = 4 * u; a.gates_grp_stride = gs;
+                a.actc = S + ac_o[l] + (size_t)t * B * u; a.actc_seq_stride = u; a.actc_grp_stride = gs;
+                lstm_step_fwd_kernel<<<dim3(cdiv(cap, ST_SEQ), cdiv(u, ST_UNITS), J), ST_THREADS, 0, stream>>>(a);
+            }
+        }
+        const int ul = p.ld[p.n_layers - 1].u;
+        const float* h_last = S + hs_o[p.n_layers - 1] + (size_t)(L - 1) * B * ul;
+        {
+            DenseArgs d{};
+            d.g = g; d.u = ul; d.T_out = p.T_out; d.act = p.out_act;
+            d.params = params; d.n_params = p.n_params; d.w_off = p.dense_w_off; d.b_off = p.dense_b_off;
+            d.h = h_last; d.h_seq_stride = ul; d.h_grp_stride = gs;
+            d.out_local = S + yh_o; d.ol_seq_stride = p.T_out; d.ol_grp_stride = gs;
+            lstm_dense_out_kernel<<<dim3(cdiv(cap * p.T_out, 256), 1, J), 256, 0, stream>>>(d);
+            LossArgs la{};
+            la.g = g; la.u = ul; la.T_out = p.T_out; la.act = p.out_act; la.L = L; la.lookahead = p.lookahead;
+            la.params = params; la.n_params = p.n_params; la.y = ysrc;
+            la.yhat = S + yh_o; la.yh_seq_stride = p.T_out; la.yh_grp_stride = gs;
+            la.dzd = S + dzd_o; la.dzd_grp_stride = gs; la.loss_sum = d_loss;
+            lstm_loss_kernel<<<dim3(cdiv(cap * p.T_out, 256), 1, J), 256, 0, stream>>>(la);
+        }
+        // ---------------- backward: dense
+        {
+            // grad Wd[k][n] = sum_s h_last[s][k] * dzd[s][n]; grad bd[n] = sum_s dzd[s][n]  (L = 1 "time step")
+            WgradArgs w{};
+            w.g = g; w.Kdim = ul; w.N = p.T_out; w.L = 1; w.layer = 1; w.shift = 0;
+            w.aseq = h_last; w.a_t_stride = 0; w.a_seq_stride = ul; w.a_grp_stride = gs;
+            w.dz = S + dzd_o; w.dz_t_stride = 0; w.dz_seq_stride = p.T_out; w.dz_grp_stride = gs;
+            w.grad = S + grad_o; w.grad_grp_stride = gs; w.grad_off = p.dense_w_off;
+            w.gbias = S + grad_o; w.gbias_off = p.dense_b_off;
+            lstm_wgrad_kernel<<<dim3(cdiv(ul * p.T_out + p.T_out, 256), 1, J), 256, 0, stream>>>(w);
+            // dH of the last layer: zero everywhere except t = L-1 where it is dzd . Wd^T
+            GB_CUDA_CHECK(cudaGetLastError());
+            NTArgs n{};
+            n.g = g; n.N = p.T_out; n.Kout = ul;
+            n.A = S + dzd_o; n.a_seq_stride = p.T_out; n.a_grp_stride = gs;
+            n.B = params + p.dense_w_off; n.b_row_stride = p.T_out; n.b_grp_stride = p.n_params;
+            n.out = S + dH_o[p.n_layers - 1] + (size_t)(L - 1) * B * ul; n.o_seq_stride = ul; n.o_grp_stride = gs;
+            lstm_nt_kernel<<<dim3(cdiv(cap * ul * 32, 256), 1, J), 256, 0, stream>>>(n);
+        }
+        // ---------------- backward: BPTT, top layer first
+        for (int l = p.n_layers - 1; l >= 0; --l) {
+            const int u = p.ld[l].u, in = p.ld[l].in;
+            const bool top = (l == p.n_layers - 1);
+            for (int t = L - 1; t >= 0; --t) {
+                BwdGateArgs b{};
+                b.g = g; b.u = u; b.act = p.acts[l]; b.t = t; b.L = L;
+                // the top layer only receives a gradient at t = L-1 (return_sequences=False)
+                b.dh_above = (!top || t == L - 1) ? S + dH_o[l] + (size_t)t * B * u : nullptr; b.da_seq_stride = u; b.da_grp_stride = gs;
+                b.dh_rec = t < L - 1 ? S + dr_o[l] : nullptr; b.dr_seq_stride = u; b.dr_grp_stride = gs;
+                b.dc = S + dc_o[l]; b.dc_seq_stride = u; b.dc_grp_stride = gs;
+                b.gates = S + gt_o[l] + (size_t)t * B * 4 * u; b.g_seq_stride = 4 * u; b.g_grp_stride = gs;
+                b.actc = S + ac_o[l] + (size_t)t * B * u; b.ac_seq_stride = u; b.ac_grp_stride = gs;
+                b.c_t = S + cs_o[l] + (size_t)t * B * u; b.ct_seq_stride = u; b.ct_grp_stride = gs;
+                b.c_prev = t > 0 ? S + cs_o[l] + (size_t)(t - 1) * B * u : nullptr; b.cp_seq_stride = u; b.cp_grp_stride = gs;
+                b.dz = S + dz_o[l] + (size_t)t * B * 4 * u; b.dz_seq_stride = 4 * u; b.dz_grp_stride = gs;
+                lstm_bwd_gates_kernel<<<dim3(cdiv(cap * u, 256), 1, J), 256, 0, stream>>>(b);
+                // dh_rec = dz . U^T (needed by t-1); dX_t = dz . W^T -> dH of the layer below
+                if (t > 0) {
+                    NTArgs n{};
+                    n.g = g; n.N = 4 * u; n.Kout = u;
+                    n.A = b.dz; n.a_seq_stride = 4 * u; n.a_grp_stride = gs;
+                    n.B = params + p.ld[l].u_off; n.b_row_stride = 4 * u; n.b_grp_stride = p.n_params;
+                    n.out = S + dr_o[l]; n.o_seq_stride = u; n.o_grp_stride = gs;
+                    lstm_nt_kernel<<<dim3(cdiv(cap * u * 32, 256), 1, J), 256, 0, stream>>>(n);
+                }
+                if (l > 0) {
+                    NTArgs n{};
+                    n.g = g; n.N = 4 * u; n.Kout = in;
+                    n.A = b.dz; n.a_seq_stride = 4 * u; n.a_grp_stride = gs;
+                    n.B = params + p.ld[l].w_off; n.b_row_stride = 4 * u; n.b_grp_stride = p.n_params;
+                    n.out = S + dH_o[l - 1] + (size_t)t * B * in; n.o_seq_stride = in; n.o_grp_stride = gs;
+                    lstm_nt_kernel<<<dim3(cdiv(cap * in * 32, 256), 1, J), 256, 0, stream>>>(n);
+                }
+            }
+            // weight gradients of this layer: one reduction over (t, seq) per weight
+            WgradArgs w{};
+            w.g = g; w.Kdim = in; w.N = 4 * u; w.L = L; w.layer = l; w.T_in = p.T_in; w.shift = 0;
+            if (l == 0) { w.x = x; w.in_scale = in_scale; w.in_min = in_min; }
+            else { w.aseq = S + hs_o[l - 1]; w.a_t_stride = (int64_t)B * in; w.a_seq_stride = in; w.a_grp_stride = gs; }
+            w.dz = S + dz_o[l]; w.dz_t_stride = (int64_t)B * 4 * u; w.dz_seq_stride = 4 * u; w.dz_grp_stride = gs;
+            w.grad = S + grad_o; w.grad_grp_stride = gs; w.grad_off = p.ld[l].w_off;
+            w.gbias = S + grad_o; w.gbias_off = p.ld[l].b_off;
+            lstm_wgrad_kernel<<<dim3(cdiv(in * 4 * u + 4 * u, 256), 1, J), 256, 0, stream>>>(w);
+            WgradArgs r{};
+            r.g = g; r.Kdim = u; r.N = 4 * u; r.L = L; r.layer = 1; r.shift = 1;
+            r.aseq = S + hs_o[l]; r.a_t_stride = (int64_t)B * u; r.a_seq_stride = u; r.a_grp_stride = gs;
+            r.dz = w.dz; r.dz_t_stride = w.dz_t_stride; r.dz_seq_stride = w.dz_seq_stride; r.dz_grp_stride = gs;
+            r.grad = S + grad_o; r.grad_grp_stride = gs; r.grad_off = p.ld[l].u_off;
+            lstm_wgrad_kernel<<<dim3(cdiv(u * 4 * u, 256), 1, J), 256, 0, stream>>>(r);
+        }
+        // ---------------- Adam
+        AdamArgs ad{};
+        ad.g = g; ad.adam = *adam; ad.n_params = p.n_params; ad.params = params;
+        ad.grad = S + grad_o; ad.mv = S + mv_o; ad.tcount = d_tcount;
+        // grad and mv live inside the per-job scratch: strides differ from n_params, so fix the bases
+        // (kernel indexes grad + grp*n_params): launch per job instead
+        for (int j = 0; j < J; ++j) {
+            AdamArgs aj = ad;
+            aj.g.rows_lo = d_rows_lo + j; aj.g.n_win = d_nwin + j;
+            aj.params = params + (size_t)j * p.n_params; aj.grad = S + (size_t)j * per_job + grad_o;
+            aj.mv = S + (size_t)j * per_job + mv_o; aj.tcount = d_tcount + j;
+            int blocks = cdiv((int)((p.n_params + 255) / 256), 1); if (blocks > 148 * 4) blocks = 148 * 4;
+            lstm_adam_kernel<<<dim3(blocks, 1, 1), 256, 0, stream>>>(aj);
+        }
+        lstm_step_end_kernel<<<cdiv(J, 128), 128, 0, stream>>>(g, J, d_tcount, d_loss, d_epoch, p.T_out, primer_out);
+        GB_CUDA_CHECK(cudaGetLastError());
+        return GB_OK;
+    };
+
+    // (1) primer: ONE Adam step on the first window alone (models.py:585-597)
+    rc = run_step(0, 1, primer_loss ? primer_loss : d_epoch + 0 /*unused sink*/);
+    if (rc) return rc;
+    if (!primer_loss) GB_CUDA_CHECK(cudaMemsetAsync(d_epoch, 0, sizeof(float) * J, stream));
+    // (2) main fit: time-ordered batches, shuffle=False (models.py:599-615)
+    for (int e = 0; e < epochs; ++e) {
+        for (int s0 = 0; s0 < max_win; s0 += B) {
+            rc = run_step(s0, B, nullptr);
+            if (rc) return rc;
+        }
+        if (hist_loss) lstm_epoch_end_kernel<<<cdiv(J, 128), 128, 0, stream>>>(J, d_nwin, d_epoch, hist_loss, epochs, e);
+        else GB_CUDA_CHECK(cudaMemsetAsync(d_epoch, 0, sizeof(float) * J, stream));
+    }
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
 }
 
 }  // extern "C"

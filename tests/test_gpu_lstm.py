@@ -1,0 +1,138 @@
+"""
+-m gpu parity tests of the LSTM path (gb200_lstm_predict / gb200_lstm_fit through gordo_b200.lstm
+and the KerasLSTM* estimators) against the oracle on the same seeded inputs and weights.
+fp32 kernels: |yhat - oracle| <= 3e-5 abs; after the primer + a few Adam steps weights <= 3e-4 abs.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import factories, lstm as olstm
+from oracle.scaler import MinMaxScaler as OMinMax
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _spec(T, L, enc=(6, 3), dec=(3, 5), funcs=("tanh", "tanh"), T_out=None, out_func="linear"):
+    return factories.lstm_model(T, T_out, lookback_window=L, encoding_dim=enc, encoding_func=funcs,
+                                decoding_dim=dec, decoding_func=funcs, out_func=out_func)
+
+
+def _topo(spec):
+    from gordo_b200.lstm import LSTMTopology
+    return LSTMTopology(spec["n_features"], spec["n_features_out"], spec["units"], spec["acts"], spec["out_func"],
+                        spec["lookback_window"])
+
+
+@pytest.mark.parametrize("lookahead,L,funcs", [(0, 5, ("tanh", "tanh")), (1, 4, ("relu", "tanh")), (0, 1, ("tanh", "sigmoid"))])
+def test_lstm_predict_matches_oracle(lookahead, L, funcs):
+    from gordo_b200.fleet import Schedule
+    from gordo_b200.lstm import LSTMFleet
+    rng = np.random.default_rng(3)
+    T, rows = 4, [60, 37, 90]
+    spec = _spec(T, L, funcs=funcs)
+    topo = _topo(spec)
+    Xs = [rng.random((n, T)).astype(np.float32) * 4 - 1 for n in rows]
+    P = [olstm.lstm_init(spec, rng) for _ in rows]
+    scal = [OMinMax().fit(X) for X in Xs]
+    fl = LSTMFleet(topo, len(rows), lookahead, DEV)
+    fl.set_params(torch.from_numpy(np.stack([olstm.lstm_flatten(p) for p in P])))
+    fl.in_scale = torch.from_numpy(np.stack([s.scale_ for s in scal]).astype(np.float32)).to(DEV)
+    fl.in_min = torch.from_numpy(np.stack([s.min_ for s in scal]).astype(np.float32)).to(DEV)
+    out, off = fl.predict(Schedule(rows), torch.from_numpy(np.concatenate(Xs)).to(DEV), max_windows=40)   # forces chunking
+    torch.cuda.synchronize()
+    for m, (X, p, s) in enumerate(zip(Xs, P, scal)):
+        want = olstm.lstm_predict(spec, p, s.transform(X).astype(np.float32), L, lookahead)
+        got = out[off[m]:off[m + 1]].cpu().numpy()
+        assert got.shape == want.shape == (rows[m] - L + 1 - lookahead, T)          # models.py:618-660
+        np.testing.assert_allclose(got, want, atol=3e-5)
+
+
+def test_lstm_predict_wider_layers_and_tile_edges():
+    from gordo_b200.fleet import Schedule
+    from gordo_b200.lstm import LSTMFleet
+    rng = np.random.default_rng(4)
+    T, L, n = 20, 6, 150
+    spec = factories.lstm_hourglass(T, lookback_window=L)            # units 17-13-10-10-13-17 (> one 16-unit tile)
+    X = rng.random((n, T)).astype(np.float32)
+    p = olstm.lstm_init(spec, rng)
+    fl = LSTMFleet(_topo(spec), 1, 0, DEV)
+    fl.set_params(torch.from_numpy(olstm.lstm_flatten(p)[None]))
+    out, _ = fl.predict(Schedule([n]), torch.from_numpy(X).to(DEV))
+    np.testing.assert_allclose(out.cpu().numpy(), olstm.lstm_predict(spec, p, X, L, 0), atol=3e-5)
+
+
+@pytest.mark.parametrize("lookahead", [0, 1])
+def test_lstm_fit_matches_oracle(lookahead):
+    from gordo_b200.lstm import LSTMFleet
+    rng = np.random.default_rng(5)
+    T, L, B, epochs = 3, 4, 8, 2
+    spec = _spec(T, L, enc=(5,), dec=(4,), funcs=("tanh",))
+    rows = [45, 30]
+    X = rng.random((sum(rows), T)).astype(np.float32)
+    Y = rng.random((sum(rows), T)).astype(np.float32)
+    lo = np.array([0, rows[0]]); hi = np.array([rows[0], sum(rows)])
+    inits = [olstm.lstm_init(spec, rng) for _ in rows]
+    want, hist = [], []
+    for j in range(2):
+        p = olstm.lstm_unflatten(olstm.lstm_flatten(inits[j]), spec)
+        hp, hm, _ = olstm.lstm_fit(spec, p, X[lo[j]:hi[j]], Y[lo[j]:hi[j]], lookback_window=L, lookahead=lookahead,
+                                   batch_size=B, epochs=epochs)
+        want.append(olstm.lstm_flatten(p)); hist.append((hp, hm))
+    fl = LSTMFleet(_topo(spec), 2, lookahead, DEV)
+    params = torch.from_numpy(np.stack([olstm.lstm_flatten(p) for p in inits])).to(DEV)
+    hl, pl = fl.fit_jobs(torch.from_numpy(X).to(DEV), torch.from_numpy(Y).to(DEV), lo, hi, params, epochs=epochs, batch_size=B)
+    torch.cuda.synchronize()
+    for j in range(2):
+        np.testing.assert_allclose(params[j].cpu().numpy(), want[j], atol=3e-4, err_msg=f"job {j}")
+        np.testing.assert_allclose(float(pl[j]), hist[j][0]["loss"][0], rtol=1e-4)
+        np.testing.assert_allclose(hl[j].cpu().numpy(), hist[j][1]["loss"], rtol=1e-3)
+
+
+def test_lstm_estimators_surface():
+    """tests/gordo/machine/model/test_model.py:161-236, 324-338; test_builder.py:99-115 offsets."""
+    from gordo_b200.machine.model.models import KerasLSTMAutoEncoder, KerasLSTMForecast
+    rng = np.random.default_rng(6)
+    xTrain, yTrain = rng.random((5, 3)), rng.random((5, 3))
+    model = KerasLSTMAutoEncoder(kind="lstm_model", lookback_window=3, encoding_dim=(4,), encoding_func=("tanh",),
+                                 decoding_dim=(4,), decoding_func=("tanh",)).fit(xTrain, yTrain)
+    assert model.predict(rng.random((4, 3))).shape == (2, 3)             # test_lstmae_predict_output
+    with pytest.raises(ValueError):                                      # lookback_window >= rows
+        model.predict(xTrain[-3:-1, :])
+    with pytest.raises(ValueError):
+        KerasLSTMAutoEncoder(kind="lstm_model", lookback_window=11).fit(rng.random(10), rng.random(10))
+    for lb in (5, 6):
+        with pytest.raises(ValueError):
+            KerasLSTMForecast(kind="lstm_model", lookback_window=lb).fit(rng.random((5, 2)), rng.random((5, 2)))
+    # 1-D arrays are reshaped (test_keras_ae_reshapes_array / forecast)
+    X1 = rng.random(100)
+    small = dict(encoding_dim=(3,), encoding_func=("tanh",), decoding_dim=(3,), decoding_func=("tanh",))
+    KerasLSTMAutoEncoder(kind="lstm_model", **small).fit(X1, X1).predict(X1)
+    f = KerasLSTMForecast(kind="lstm_symmetric", lookback_window=13, dims=(4,), funcs=("tanh",)).fit(rng.random((100, 2)), rng.random((100, 2)))
+    X = rng.random((100, 2))
+    assert len(X) - len(f.predict(X)) == 13                              # Forecast L=13 -> offset 13
+    a = KerasLSTMAutoEncoder(kind="lstm_hourglass", lookback_window=10, epochs=2).fit(X, X)
+    assert len(X) - len(a.predict(X)) == 9                               # LSTM-AE L=10 -> offset 9
+    md = a.get_metadata()
+    assert md["forecast_steps"] == 0 and len(md["history"]["loss"]) == 1 and len(a.history_main_["loss"]) == 2
+    assert a.score(X, X) <= 1.0
+    import pickle
+    b = pickle.loads(pickle.dumps(a))
+    assert np.allclose(b.predict(X), a.predict(X))
+
+
+def test_lstm_detector_offsets_in_anomaly_frame():
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_b200.machine.model.models import KerasLSTMAutoEncoder
+    rng = np.random.default_rng(7)
+    X = pd.DataFrame(rng.random((120, 3)), columns=list("abc"), index=pd.date_range("2021-01-01", periods=120, freq="1min"))
+    np.random.seed(0)
+    det = DiffBasedAnomalyDetector(base_estimator=KerasLSTMAutoEncoder(kind="lstm_hourglass", lookback_window=6), require_thresholds=False)
+    det.fit(X, X)
+    f = det.anomaly(X, X)
+    assert len(f) == 115 and f.index[0] == X.index[5]                    # aligned to the LAST len(output) rows
+    np.testing.assert_array_equal(f["model-input"].to_numpy(), X.to_numpy()[5:])
+    d = np.abs(f["model-output"].to_numpy() - X.to_numpy()[5:])
+    np.testing.assert_allclose(f["tag-anomaly-unscaled"].to_numpy(), d, rtol=1e-6, atol=1e-9)
