@@ -208,8 +208,10 @@ def run_ours(args):
     xh = x_host.numpy()
     params = np.empty((M, topo.n_params), np.float32)
     ft = np.empty((M, T_TAGS), np.float32); at = np.empty((M,), np.float32)
-    for i in range(M):
-        rng, X = machine_data(rank + i * world)
+    from gordo_b200.partition import round_robin
+    my_machines = round_robin(M * world, world, rank)          # global ids rank, rank + world, ...
+    for i, gid in enumerate(my_machines):
+        rng, X = machine_data(gid)
         xh[i * N_ROWS:(i + 1) * N_ROWS] = X
         params[i] = machine_params(rng, widths)
         ft[i] = rng.uniform(0.1, 0.5, T_TAGS); at[i] = rng.uniform(0.01, 0.1)
@@ -321,7 +323,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--machines", type=int, default=0, help="Machines per GPU (default 128)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--cpu-machines", type=int, default=4, help="Machines in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--cpu-machines", type=int, default=32, help="Machines in the cpu_baseline sample (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
