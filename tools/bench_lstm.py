@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""
+Secondary measurement: LSTM autoencoder predict (BASELINE.json configs[3] shape: 200 tags,
+lookback 128, hourglass units 167-133-100-100-133-167) on one Machine, windows/s and the
+fraction of the bf16 tensor roofline (2.31e8 FLOP/window), with the CPU oracle on a small sample.
+
+  python tools/bench_lstm.py [--rows 20000] [--tags 200] [--lookback 128] [--cpu-windows 64]
+"""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=20000)
+    ap.add_argument("--tags", type=int, default=200)
+    ap.add_argument("--lookback", type=int, default=128)
+    ap.add_argument("--cpu-windows", type=int, default=64)
+    ap.add_argument("--max-windows", type=int, default=16384)
+    a = ap.parse_args()
+    import torch
+    from gordo_b200.fleet import Schedule
+    from gordo_b200.lstm import LSTMFleet
+    from gordo_b200.machine.model.factories.lstm_autoencoder import lstm_hourglass
+    dev = torch.device("cuda:0")
+    topo = lstm_hourglass(a.tags, lookback_window=a.lookback)
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    fl = LSTMFleet(topo, 1, 0, dev)
+    fl.set_params(topo.init_params(1, g, dev))
+    X = torch.rand((a.rows, a.tags), generator=g, device=dev)
+    sched = Schedule([a.rows])
+    fl.predict(sched, X, max_windows=a.max_windows); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out, off = fl.predict(sched, X, max_windows=a.max_windows); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n_win = int(off[-1])
+    flops_per_window = a.lookback * sum(8 * u * (i + u) for i, u in zip([a.tags] + topo.units[:-1], topo.units)) \
+        + 2 * topo.units[-1] * a.tags
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    res = {"windows": n_win, "ms": ms, "windows_per_s": n_win / (ms * 1e-3), "flops_per_window": flops_per_window,
+           "achieved_tflops": n_win * flops_per_window / (ms * 1e-3) / 1e12, "peak_tflops": peak,
+           "frac_of_bf16_tensor_peak": n_win * flops_per_window / (ms * 1e-3) / 1e12 / peak, "units": topo.units}
+    from oracle import factories, lstm as olstm
+    spec = factories.lstm_hourglass(a.tags, lookback_window=a.lookback)
+    p = olstm.lstm_unflatten(fl.params[0].cpu().numpy(), spec)
+    Xc = X[: a.cpu_windows + a.lookback - 1].cpu().numpy()
+    t0 = time.time(); want = olstm.lstm_predict(spec, p, Xc, a.lookback, 0); dt = time.time() - t0
+    res["cpu_oracle_windows_per_s_1core"] = a.cpu_windows / dt
+    res["max_abs_err_vs_oracle"] = float(np.abs(out[: a.cpu_windows].cpu().numpy() - want).max())
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
