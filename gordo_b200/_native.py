@@ -49,8 +49,8 @@ SIGNATURES = {
     "gb200_ff_fit": (C.c_int, [C.POINTER(FFArch), C.POINTER(Adam), _I32] + [_P] * 9 + [_I32] * 3 + [_P] * 6),
     "gb200_lstm_param_count": (_I64, [C.POINTER(LSTMArch)]),
     "gb200_lstm_out_rows": (_I64, [C.POINTER(LSTMArch), _I64]),
-    "gb200_lstm_scratch_bytes": (_I64, [C.POINTER(LSTMArch), _I64]),
-    "gb200_lstm_predict": (C.c_int, [_P, C.POINTER(LSTMArch)] + [_P] * 6 + [_P, _I64, _P]),
+    "gb200_lstm_scratch_bytes": (_I64, [C.POINTER(LSTMArch), _I64, C.c_int]),
+    "gb200_lstm_predict": (C.c_int, [_P, C.POINTER(LSTMArch), C.c_int] + [_P] * 6 + [_P, _I64, _P]),
     "gb200_lstm_fit_scratch_bytes": (_I64, [C.POINTER(LSTMArch), _I32, _I32]),
     "gb200_lstm_fit": (C.c_int, [C.POINTER(LSTMArch), C.POINTER(Adam), _I32, C.POINTER(_I64), C.POINTER(_I64)]
                        + [_P] * 4 + [_I32, _I32] + [_P] * 3 + [_P, _I64, _P]),

@@ -424,8 +424,9 @@ int64_t gb200_lstm_out_rows(const gb200_lstm_arch* a, int64_t n_rows) {
 }
 
 // predict scratch: per layer two h buffers + one c buffer of [max_windows][u]
-int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch* a, int64_t max_windows) {
+int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch* a, int64_t max_windows, int precision) {
     if (!a || a->n_layers < 1 || a->n_layers > GB200_MAX_LAYERS || max_windows < 1) return 0;
+    if (precision == GB200_PREC_BF16_TC) return gb_lstm_tc_scratch_bytes(a, max_windows);
     const LstmPlan p = make_plan(a);
     return (int64_t)align256((size_t)3 * p.sum_u * max_windows * sizeof(float)) + 1024;
 }
@@ -439,7 +440,7 @@ static int check_lstm_arch(const gb200_lstm_arch* a) {
     return GB_OK;
 }
 
-int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, const float* params,
+int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, int precision, const float* params,
                        const float* in_scale, const float* in_min, const float* x,
                        const int64_t* out_row_off, float* model_out,
                        void* scratch, int64_t scratch_bytes, void* stream_) {
@@ -447,7 +448,15 @@ int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, const float*
     int rc = check_lstm_arch(arch); if (rc) return rc;
     GB_REQUIRE(params && x && out_row_off && model_out && scratch, "NULL argument");
     GB_REQUIRE((in_scale == nullptr) == (in_min == nullptr), "in_scale and in_min must be given together");
+    GB_REQUIRE(precision == GB200_PREC_F32 || precision == GB200_PREC_BF16_TC, "unknown precision %d", precision);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (precision == GB200_PREC_BF16_TC) {
+        // host-side prefix of the per-Machine output rows (out_row_off is its device twin)
+        std::vector<int64_t> off(f->n_machines + 1, 0);
+        for (int m = 0; m < f->n_machines; ++m)
+            off[m + 1] = off[m] + gb200_lstm_out_rows(arch, f->h_row_hi[m] - f->h_row_lo[m]);
+        return gb_lstm_predict_tc(f, arch, params, in_scale, in_min, x, off.data(), model_out, scratch, scratch_bytes, stream);
+    }
     const LstmPlan p = make_plan(arch);
     const int64_t cap64 = (scratch_bytes - 1024) / ((int64_t)3 * p.sum_u * sizeof(float));
     GB_REQUIRE(cap64 >= 1, "scratch too small (see gb200_lstm_scratch_bytes)");

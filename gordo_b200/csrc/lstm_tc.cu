@@ -1,0 +1,448 @@
+// lstm_tc: the stacked-LSTM forward (KerasLSTMBaseEstimator.predict, models.py:618-660) on tcgen05.
+//
+// One launch = one (layer, timestep) for a chunk of S windows (time-step-synchronous over the
+// stack, like lstm.cu).  Everything a tile needs is kept IN HBM IN THE UMMA CANONICAL LAYOUT, so
+// every operand is a plain 1-D bulk async copy (no tensor maps, no repacking on the way in):
+//   * Xc   : bf16(x*scale+min) of the chunk's rows, K-chunk-major [Kx/8][rows][8]: the 128
+//            consecutive rows of a window tile at time t are one contiguous 2 KB run per K chunk
+//            (windows are never materialised: window w at time t is row w+t);
+//   * h_l  : bf16 hidden state, per 128-window tile [Kh/8][128][8] (ping-pong over t);
+//   * W|U  : per 16-unit block the B operand [K/8][8][8][8] with columns ordered unit*4+gate, so
+//            a 16-column tcgen05.ld delivers the i,f,c,o pre-activations of 4 units;
+//   * c_l  : fp32 cell state, unit-major [units][S] (coalesced over windows).
+// CTA = one 128-window tile (TMEM lane = window), 2 warpgroups alternating over the layer's unit
+// blocks: while one warpgroup runs the gate epilogue of block b the other's MMAs of block b+1
+// execute, and each prefetches its next B block as soon as its MMAs have committed.
+// bf16 operands / fp32 accumulate / fp32 cell state; gates via tanh.approx (sigmoid = .5*tanh(.5z)+.5).
+#include "common.cuh"
+#include "ptx.cuh"
+
+using namespace gbptx;
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int UB = 16;             // units per block -> 64 GEMM columns
+constexpr int NB_COLS = UB * 4;
+constexpr int WG = 128;
+
+struct TcLayer {
+    int in, u, Kx, Kh, n_blocks, act;
+    int64_t w_off, u_off, b_off;   // offsets in the Keras parameter vector
+    size_t wp_off;                 // byte offset of this layer's packed blocks
+    size_t bias_off;               // float offset of this layer's interleaved biases
+    size_t h_off[2];               // byte offsets of the two h buffers
+    size_t c_off;                  // byte offset of the cell state
+};
+
+struct TcPlan {
+    int n_layers, T_in, T_out, L, lookahead, out_act;
+    TcLayer ly[GB200_MAX_LAYERS];
+    int64_t dense_w_off, dense_b_off, n_params;
+    size_t wp_bytes, bias_floats;
+    size_t smem_bytes;             // max over layers
+    bool eligible;
+};
+
+TcPlan make_tc_plan(const gb200_lstm_arch* a) {
+    TcPlan p{};
+    p.n_layers = a->n_layers; p.T_in = a->n_features; p.T_out = a->n_features_out;
+    p.L = a->lookback_window; p.lookahead = a->lookahead; p.out_act = a->out_act;
+    int64_t off = 0; int in = a->n_features;
+    size_t wp = 0, bf = 0, smem = 0;
+    for (int l = 0; l < a->n_layers; ++l) {
+        TcLayer& y = p.ly[l];
+        y.in = in; y.u = a->units[l]; y.act = a->acts[l];
+        y.Kx = l == 0 ? gb_round_up(in, 16) : p.ly[l - 1].Kh;
+        y.Kh = gb_round_up(y.u, 16);
+        y.n_blocks = (y.u + UB - 1) / UB;
+        y.w_off = off; off += (int64_t)in * 4 * y.u;
+        y.u_off = off; off += (int64_t)y.u * 4 * y.u;
+        y.b_off = off; off += 4 * y.u;
+        y.wp_off = wp; wp += (size_t)y.n_blocks * (y.Kx + y.Kh) * NB_COLS * 2;
+        y.bias_off = bf; bf += (size_t)y.n_blocks * NB_COLS;
+        const size_t s = (size_t)TILE * (y.Kx + y.Kh) * 2 + 2 * (size_t)(y.Kx + y.Kh) * NB_COLS * 2;
+        if (s > smem) smem = s;
+        in = y.u;
+    }
+    p.dense_w_off = off; off += (int64_t)in * a->n_features_out;
+    p.dense_b_off = off; off += a->n_features_out;
+    p.n_params = off; p.wp_bytes = wp; p.bias_floats = bf;
+    p.smem_bytes = smem + 1024;
+    p.eligible = p.smem_bytes <= 227 * 1024 - 1024;
+    return p;
+}
+
+size_t tc_state_bytes(TcPlan& p, int64_t S, bool assign) {
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~(size_t)255; return r; };
+    const size_t wp = take(p.wp_bytes), bias = take(p.bias_floats * 4);
+    const size_t xc = take((size_t)(p.ly[0].Kx / 8) * (S + p.L) * 16);
+    (void)wp; (void)bias; (void)xc;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const size_t h0 = take((size_t)p.ly[l].Kh * S * 2), h1 = take((size_t)p.ly[l].Kh * S * 2);
+        const size_t c = take((size_t)p.ly[l].n_blocks * UB * S * 4);
+        if (assign) { p.ly[l].h_off[0] = h0; p.ly[l].h_off[1] = h1; p.ly[l].c_off = c; }
+    }
+    return o + 1024;
+}
+
+// ---------------------------------------------------------------- packing
+// B blocks of one layer: block b, element (n = unit_local*4 + gate, k) at
+//   (k/8)*(8*64) + (n/8)*64 + (n%8)*8 + (k%8)   [bf16 elements], k = [x rows | h rows]
+__global__ void lstm_pack_w_kernel(TcLayer y, const float* __restrict__ P, uint8_t* __restrict__ wp,
+                                   float* __restrict__ bias) {
+    const int b = blockIdx.x;
+    const int K = y.Kx + y.Kh;
+    __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(wp + y.wp_off + (size_t)b * K * NB_COLS * 2);
+    for (int i = threadIdx.x; i < K * NB_COLS; i += blockDim.x) {
+        const int k = i / NB_COLS, n = i - k * NB_COLS;
+        const int unit = b * UB + (n >> 2), gate = n & 3;
+        float w = 0.0f;
+        if (unit < y.u) {
+            if (k < y.Kx) { if (k < y.in) w = P[y.w_off + (int64_t)k * 4 * y.u + gate * y.u + unit]; }
+            else { const int kh = k - y.Kx; if (kh < y.u) w = P[y.u_off + (int64_t)kh * 4 * y.u + gate * y.u + unit]; }
+        }
+        B[(k >> 3) * (8 * 64) + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
+    }
+    for (int n = threadIdx.x; n < NB_COLS; n += blockDim.x) {
+        const int unit = b * UB + (n >> 2), gate = n & 3;
+        bias[y.bias_off + (size_t)b * NB_COLS + n] = unit < y.u ? P[y.b_off + gate * y.u + unit] : 0.0f;
+    }
+}
+
+// Xc[(k/8)][row][k%8] = bf16(x[row0+row][k]*scale[k]+min[k]); rows past the Machine's end are zero
+__global__ void lstm_pack_x_kernel(const float* __restrict__ x, int64_t row0, int64_t rows_avail, int64_t rows_chunk,
+                                   int T, int Kx, const float* __restrict__ sc, const float* __restrict__ mn,
+                                   __nv_bfloat16* __restrict__ xc) {
+    const int64_t total = rows_chunk * (Kx / 8);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i % rows_chunk; const int c = (int)(i / rows_chunk);
+        uint4 pk;
+        uint32_t w[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[2];
+            #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = c * 8 + j * 2 + h;
+                float t = 0.0f;
+                if (r < rows_avail && k < T) { t = x[(row0 + r) * T + k]; if (sc) t = fmaf(t, sc[k], mn[k]); }
+                v[h] = t;
+            }
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[0], v[1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        pk.x = w[0]; pk.y = w[1]; pk.z = w[2]; pk.w = w[3];
+        *reinterpret_cast<uint4*>(xc + ((size_t)c * rows_chunk + r) * 8) = pk;
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fast(float z) {
+    if (ACT == GB200_ACT_TANH) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z)); return r; }
+    if (ACT == GB200_ACT_RELU) return fmaxf(z, 0.0f);
+    if (ACT == GB200_ACT_SIGMOID) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(0.5f * z)); return fmaf(0.5f, r, 0.5f); }
+    if (ACT == GB200_ACT_ELU) return z > 0.0f ? z : __expf(z) - 1.0f;
+    if (ACT == GB200_ACT_SOFTPLUS) return z > 15.0f ? z : __logf(1.0f + __expf(z));
+    return z;
+}
+__device__ __forceinline__ float sigmoid_fast(float z) {
+    float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(0.5f * z));
+    return fmaf(0.5f, r, 0.5f);
+}
+
+struct StepTc {
+    int Kx, Kh, n_blocks, t, layer, S, tiles;
+    int64_t xc_rows;                       // rows of Xc (layer 0)
+    const uint8_t* x_src;                  // layer 0: Xc; else h_{l-1} (current t) tiles
+    const uint8_t* h_prev;                 // this layer's h at t-1 (tiles)
+    uint8_t* h_out;                        // this layer's h at t
+    float* c;                              // [n_blocks*UB][S]
+    const uint8_t* wp; const float* bias;  // this layer's packed blocks / biases
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// one slice of a weight block, delivered to the same offset in every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// CTA = 2 epilogue/MMA warpgroups + 1 loader warp.  A thread-block cluster of C CTAs (C window
+// tiles of the same launch) shares every weight block: each CTA fetches 1/C of the block and
+// multicasts it to all C shared memories, so the L2 -> SM weight traffic drops by C.
+template <int ACT>
+__global__ void __launch_bounds__(2 * WG + 32, 1)
+lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t a_bar[2];          // x part, h part of the A operand
+    __shared__ __align__(8) uint64_t b_bar[2];          // B block landed (per warpgroup buffer)
+    __shared__ __align__(8) uint64_t e_bar[2];          // B buffer free in EVERY CTA of the cluster
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, wg = tid / WG, wtid = tid - wg * WG, warp = wtid >> 5;
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    const bool active = (int)blockIdx.x < a.tiles;               // padding CTAs of the last cluster only relay loads
+    const int tile = active ? blockIdx.x : a.tiles - 1;
+    const int K = a.Kx + a.Kh;
+    const bool has_h = a.t > 0;
+    const uint32_t blk_bytes = (uint32_t)K * NB_COLS * 2;
+    uint8_t* A = smem;                                           // [K/8][128][16 B]
+    uint8_t* Bbase = smem + (size_t)TILE * K * 2;
+
+    if (tid == 0) {
+        mbar_init(&a_bar[0], 1); mbar_init(&a_bar[1], 1);
+        mbar_init(&b_bar[0], 1); mbar_init(&b_bar[1], 1);
+        mbar_init(&e_bar[0], csize); mbar_init(&e_bar[1], csize);
+        mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) tmem_alloc(&s_tmem, 2 * NB_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (csize > 1) cluster_sync_all();            // every CTA's barriers exist before any multicast lands
+
+    if (wg == 2) {
+        // ===================== loader warp =====================
+        if (tid == 2 * WG) {
+            const uint32_t xb = (uint32_t)a.Kx * 256;
+            mbar_expect_tx(&a_bar[0], xb);
+            if (a.layer == 0) {
+                for (int c = 0; c < a.Kx / 8; ++c)
+                    bulk_g2s(A + c * 2048, a.x_src + ((size_t)c * a.xc_rows + (size_t)tile * TILE + a.t) * 16, 2048, &a_bar[0]);
+            } else {
+                bulk_g2s(A, a.x_src + (size_t)tile * xb, xb, &a_bar[0]);
+            }
+            if (has_h) {
+                const uint32_t hb = (uint32_t)a.Kh * 256;
+                mbar_expect_tx(&a_bar[1], hb);
+                bulk_g2s(A + xb, a.h_prev + (size_t)tile * hb, hb, &a_bar[1]);
+            }
+            const uint32_t slice = blk_bytes / csize;
+            const uint16_t mask = (uint16_t)((1u << csize) - 1);
+            uint32_t e_phase[2] = {0, 0};
+            for (int b = 0; b < a.n_blocks; ++b) {
+                const int w = b & 1;
+                if (b >= 2) { mbar_wait(&e_bar[w], e_phase[w]); e_phase[w] ^= 1; }      // all C copies of buffer w are free
+                uint8_t* dst = Bbase + (size_t)w * blk_bytes + (size_t)crank * slice;
+                const uint8_t* src = a.wp + (size_t)b * blk_bytes + (size_t)crank * slice;
+                mbar_expect_tx(&b_bar[w], blk_bytes);
+                if (csize > 1) bulk_g2s_multicast(dst, src, slice, &b_bar[w], mask);
+                else bulk_g2s(dst, src, slice, &b_bar[w]);
+            }
+        }
+    } else {
+        // ===================== MMA + gate-epilogue warpgroups =====================
+        uint8_t* Bbuf = Bbase + (size_t)wg * blk_bytes;
+        const uint32_t tmem_acc = s_tmem + (uint32_t)(wg * NB_COLS);
+        const uint32_t tmem_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+        const int w = tile * TILE + wtid;                 // window index inside the chunk
+        uint32_t b_phase = 0, m_phase = 0;
+        bool a_ready = false;
+        for (int b = wg; b < a.n_blocks; b += 2) {
+            // cell state of this block's 16 units: 16 independent coalesced loads issued BEFORE the MMA
+            // wait, so their HBM/L2 latency hides behind the tensor-core work
+            float cprev[UB];
+            #pragma unroll
+            for (int ul = 0; ul < UB; ++ul)
+                cprev[ul] = has_h ? __ldcg(a.c + (size_t)(b * UB + ul) * a.S + w) : 0.0f;
+            if (wtid == 0) {
+                mbar_wait(&b_bar[wg], b_phase);
+                if (!a_ready) { mbar_wait(&a_bar[0], 0); if (has_h) mbar_wait(&a_bar[1], 0); }
+                tc_fence_after();
+                const uint32_t idesc = make_idesc(TILE, NB_COLS);
+                const uint32_t a_addr = smem_u32(A), b_addr = smem_u32(Bbuf);
+                const int ksteps = (has_h ? K : a.Kx) / 16;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t da = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
+                    const uint64_t db = make_desc(b_addr + ks * 2 * 1024, 1024, 128);
+                    umma_bf16(tmem_acc, da, db, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(&mma_bar[wg]);
+            }
+            a_ready = true; b_phase ^= 1;
+            mbar_wait(&mma_bar[wg], m_phase); m_phase ^= 1;
+            tc_fence_after();
+            // this CTA's copy of buffer `wg` is free: tell every loader in the cluster
+            if (wtid == 0 && b + 2 < a.n_blocks)
+                for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(&e_bar[wg], r);
+            // ---- gate epilogue: 4 chunks of 16 columns = 4 units x (i,f,c~,o)
+            const float* bias = a.bias + (size_t)b * NB_COLS;
+            float hreg[8];
+            #pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float v[16];
+                tmem_ld16(tmem_lane + c4 * 16, v);
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ul = c4 * 4 + q;
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ul * 4));
+                    const float ig = sigmoid_fast(v[q * 4 + 0] + bb.x), fg = sigmoid_fast(v[q * 4 + 1] + bb.y);
+                    const float gg = act_fast<ACT>(v[q * 4 + 2] + bb.z), og = sigmoid_fast(v[q * 4 + 3] + bb.w);
+                    const float cn = fmaf(fg, cprev[ul], ig * gg);
+                    if (active) __stcg(a.c + (size_t)(b * UB + ul) * a.S + w, cn);
+                    hreg[(c4 & 1) * 4 + q] = og * act_fast<ACT>(cn);
+                }
+                if (c4 & 1) {
+                    uint4 pk;
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(hreg[0], hreg[1]), t1 = __floats2bfloat162_rn(hreg[2], hreg[3]);
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(hreg[4], hreg[5]), t3 = __floats2bfloat162_rn(hreg[6], hreg[7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                    const int chunk = b * 2 + (c4 >> 1);
+                    if (active)
+                        *reinterpret_cast<uint4*>(a.h_out + (size_t)tile * a.Kh * 256 + (size_t)chunk * 2048 + wtid * 16) = pk;
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(1 + wg, WG);          // every lane has drained TMEM before the next block's MMAs
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (csize > 1) cluster_sync_all();            // no CTA leaves while peers may still multicast into it
+    if (tid < 32) tmem_dealloc(s_tmem, 2 * NB_COLS);
+}
+
+// yhat = out_act(h_last . Wd + bd) with h_last read from the canonical bf16 tiles
+__global__ void lstm_dense_tc_kernel(const uint8_t* __restrict__ h, int Kh, int u, int T_out, int act,
+                                     const float* __restrict__ Wd, const float* __restrict__ bd,
+                                     int nb, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * T_out; i += gridDim.x * blockDim.x) {
+        const int s = i / T_out, n = i - s * T_out;
+        const __nv_bfloat16* tile = reinterpret_cast<const __nv_bfloat16*>(h + (size_t)(s / TILE) * Kh * 256);
+        const int r = s % TILE;
+        float acc = bd[n];
+        for (int k = 0; k < u; ++k)
+            acc = fmaf(__bfloat162float(tile[(k >> 3) * 1024 + r * 8 + (k & 7)]), Wd[(size_t)k * T_out + n], acc);
+        out[(size_t)s * T_out + n] = gb_act(act, acc);
+    }
+}
+
+template <int ACT>
+void launch_step(const StepTc& a, int tiles, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;                 // per instantiation
+    if (smem > configured) {
+        cudaFuncSetAttribute(lstm_step_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    // clusters of 4 window tiles share every weight block (multicast); 148 SMs = 37 clusters
+    const int csize = tiles >= 4 ? 4 : (tiles >= 2 ? 2 : 1);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((tiles + csize - 1) / csize * csize);
+    cfg.blockDim = dim3(2 * WG + 32);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, lstm_step_tc_kernel<ACT>, a);
+}
+
+}  // namespace
+
+int64_t gb_lstm_tc_scratch_bytes(const gb200_lstm_arch* arch, int64_t max_windows) {
+    TcPlan p = make_tc_plan(arch);
+    if (!p.eligible) return 0;
+    const int64_t S = (max_windows + TILE - 1) / TILE * TILE;
+    return (int64_t)tc_state_bytes(p, S, false);
+}
+
+int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const float* params,
+                       const float* in_scale, const float* in_min, const float* x,
+                       const int64_t* out_row_off_host, float* model_out,
+                       void* scratch, int64_t scratch_bytes, cudaStream_t stream) {
+    TcPlan p = make_tc_plan(arch);
+    GB_REQUIRE(p.eligible, "LSTM topology too wide for the tensor-core step kernel (use GB200_PREC_F32)");
+    // largest chunk (multiple of 128 windows) that fits the scratch
+    int64_t S = TILE;
+    while (true) {
+        TcPlan q = p;
+        if ((int64_t)tc_state_bytes(q, S * 2, false) > scratch_bytes || S * 2 > (1 << 20)) break;
+        S *= 2;
+    }
+    {
+        TcPlan q = p;
+        GB_REQUIRE((int64_t)tc_state_bytes(q, S, false) <= scratch_bytes, "scratch too small (see gb200_lstm_scratch_bytes)");
+        // grow linearly past the last power of two
+        while ((int64_t)tc_state_bytes(q, S + TILE, false) <= scratch_bytes && S + TILE <= (1 << 20)) S += TILE;
+    }
+    tc_state_bytes(p, S, true);
+    uint8_t* base = (uint8_t*)scratch;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~(size_t)255; return r; };
+    uint8_t* wp = base + take(p.wp_bytes);
+    float* bias = (float*)(base + take(p.bias_floats * 4));
+    __nv_bfloat16* xc = (__nv_bfloat16*)(base + take((size_t)(p.ly[0].Kx / 8) * (S + p.L) * 16));
+    const size_t state0 = o;
+    // re-derive the state offsets relative to `base` (tc_state_bytes assigned them with the same walk)
+    (void)state0;
+
+    for (int m = 0; m < f->n_machines; ++m) {
+        const int64_t rows = f->h_row_hi[m] - f->h_row_lo[m];
+        if (rows <= 0) continue;
+        GB_REQUIRE(p.L < rows, "For KerasLSTMForecast lookback_window must be < size of X (machine %d)", m);
+        const int64_t n_win = rows - p.L + 1 - p.lookahead;
+        if (n_win <= 0) continue;
+        const float* P = params + (size_t)m * p.n_params;
+        for (int l = 0; l < p.n_layers; ++l)
+            lstm_pack_w_kernel<<<p.ly[l].n_blocks, 256, 0, stream>>>(p.ly[l], P, wp, bias);
+        const float* sc = in_scale ? in_scale + (size_t)m * p.T_in : nullptr;
+        const float* mn = in_min ? in_min + (size_t)m * p.T_in : nullptr;
+        // balanced chunks (each a multiple of 128 windows, <= S): no tiny tail launch
+        const int64_t n_chunks = (n_win + S - 1) / S;
+        const int64_t Sc = ((n_win + n_chunks - 1) / n_chunks + TILE - 1) / TILE * TILE;
+        for (int64_t k0 = 0; k0 < n_win; k0 += Sc) {
+            const int nb = (int)((n_win - k0) < Sc ? (n_win - k0) : Sc);
+            const int tiles = (nb + TILE - 1) / TILE;
+            const int64_t rows_chunk = S + p.L;
+            const int64_t row0 = f->h_row_lo[m] + k0;
+            const int64_t rows_avail = f->h_row_hi[m] - row0;
+            lstm_pack_x_kernel<<<148 * 4, 256, 0, stream>>>(x, row0, rows_avail, rows_chunk, p.T_in, p.ly[0].Kx, sc, mn, xc);
+            for (int t = 0; t < p.L; ++t) {
+                for (int l = 0; l < p.n_layers; ++l) {
+                    const TcLayer& y = p.ly[l];
+                    StepTc a{};
+                    a.Kx = y.Kx; a.Kh = y.Kh; a.n_blocks = y.n_blocks; a.t = t; a.layer = l; a.S = (int)S; a.tiles = tiles;
+                    a.xc_rows = rows_chunk;
+                    a.x_src = l == 0 ? (const uint8_t*)xc : base + p.ly[l - 1].h_off[t & 1];
+                    a.h_prev = base + y.h_off[(t + 1) & 1];
+                    a.h_out = base + y.h_off[t & 1];
+                    a.c = (float*)(base + y.c_off);
+                    a.wp = wp + y.wp_off; a.bias = bias + y.bias_off;
+                    const size_t smem = (size_t)TILE * (y.Kx + y.Kh) * 2 + 2 * (size_t)(y.Kx + y.Kh) * NB_COLS * 2;
+                    switch (y.act) {
+                        case GB200_ACT_TANH: launch_step<GB200_ACT_TANH>(a, tiles, smem, stream); break;
+                        case GB200_ACT_RELU: launch_step<GB200_ACT_RELU>(a, tiles, smem, stream); break;
+                        case GB200_ACT_SIGMOID: launch_step<GB200_ACT_SIGMOID>(a, tiles, smem, stream); break;
+                        case GB200_ACT_ELU: launch_step<GB200_ACT_ELU>(a, tiles, smem, stream); break;
+                        case GB200_ACT_SOFTPLUS: launch_step<GB200_ACT_SOFTPLUS>(a, tiles, smem, stream); break;
+                        default: launch_step<GB200_ACT_LINEAR>(a, tiles, smem, stream); break;
+                    }
+                }
+            }
+            const TcLayer& yl = p.ly[p.n_layers - 1];
+            int blocks = (nb * p.T_out + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+            lstm_dense_tc_kernel<<<blocks, 256, 0, stream>>>(base + yl.h_off[(p.L - 1) & 1], yl.Kh, yl.u, p.T_out, p.out_act,
+                                                              P + p.dense_w_off, P + p.dense_b_off, nb,
+                                                              model_out + (out_row_off_host[m] + k0) * p.T_out);
+            GB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    return GB_OK;
+}

@@ -94,10 +94,13 @@ class LSTMFleet:
             self._scratch = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=self.device)
         return self._scratch
 
-    def predict(self, sched: Schedule, x: torch.Tensor, max_windows: int = 16384):
+    def tc_eligible(self) -> bool:
+        return N.lib().gb200_lstm_scratch_bytes(C.byref(self.arch), 128, N.PREC_BF16_TC) > 0
+
+    def predict(self, sched: Schedule, x: torch.Tensor, max_windows: int = 16384, precision: str = "f32"):
         """
         KerasLSTMBaseEstimator.predict for every Machine.  Returns (model_out [sum out_rows, T_out],
-        out_row_off np.int64[M+1]).
+        out_row_off np.int64[M+1]).  precision "f32" (exact) or "bf16" (tcgen05 step kernel).
         """
         if self.params is None:
             raise RuntimeError("fleet has no parameters")
@@ -107,10 +110,13 @@ class LSTMFleet:
             raise ValueError("For KerasLSTMForecast lookback_window must be < size of X")
         out_off = np.concatenate([[0], np.cumsum([self.out_rows(r) for r in rows])]).astype(np.int64)
         out = torch.empty((int(out_off[-1]), self.topo.n_features_out), dtype=torch.float32, device=x.device)
-        nbytes = N.lib().gb200_lstm_scratch_bytes(C.byref(self.arch), int(max_windows))
+        prec = {"f32": N.PREC_F32, "bf16": N.PREC_BF16_TC}[precision]
+        nbytes = N.lib().gb200_lstm_scratch_bytes(C.byref(self.arch), int(max_windows), prec)
+        if nbytes <= 0:
+            raise ValueError("LSTM topology is not eligible for this precision")
         scratch = self._get_scratch(nbytes)
         d_off = torch.from_numpy(out_off).to(x.device)
-        N.check(N.lib().gb200_lstm_predict(sched.handle, C.byref(self.arch), N.ptr(self.params), N.ptr(self.in_scale),
+        N.check(N.lib().gb200_lstm_predict(sched.handle, C.byref(self.arch), prec, N.ptr(self.params), N.ptr(self.in_scale),
                                            N.ptr(self.in_min), N.ptr(x), N.ptr(d_off), N.ptr(out), N.ptr(scratch),
                                            int(nbytes), _stream_ptr()), "gb200_lstm_predict")
         return out, out_off

@@ -167,12 +167,15 @@ int gb200_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int32_t n_jo
  */
 int64_t gb200_lstm_param_count(const gb200_lstm_arch* arch);
 int64_t gb200_lstm_out_rows(const gb200_lstm_arch* arch, int64_t n_rows);
-/* scratch bytes the caller must provide for gb200_lstm_predict over `max_windows` windows at once */
-int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch* arch, int64_t max_windows);
+/* scratch bytes the caller must provide for gb200_lstm_predict over `max_windows` windows at once
+ * (depends on the precision: the tensor-core path keeps bf16 state tiles + packed weights there);
+ * 0 if the topology is not eligible for that precision */
+int64_t gb200_lstm_scratch_bytes(const gb200_lstm_arch* arch, int64_t max_windows, int precision);
 /* KerasLSTMBaseEstimator.predict (models.py:618-660): yhat for every window of every Machine.
- * out_row_off: [M+1] int64 DEVICE offsets of each Machine's output rows in model_out
- * (Machine m produces gb200_lstm_out_rows(arch, rows_m) rows). */
-int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, const float* params,
+ * out_row_off: [M+1] int64 DEVICE offsets of each Machine's output rows in model_out: the prefix
+ * sum of gb200_lstm_out_rows(arch, rows_m).  precision: GB200_PREC_F32 (exact fp32 FMAs) or
+ * GB200_PREC_BF16_TC (tcgen05 step kernel, bf16 operands / fp32 accumulate and cell state). */
+int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, int precision, const float* params,
                        const float* in_scale, const float* in_min, const float* x,
                        const int64_t* out_row_off, float* model_out,
                        void* scratch, int64_t scratch_bytes, void* stream);

@@ -136,3 +136,40 @@ def test_lstm_detector_offsets_in_anomaly_frame():
     np.testing.assert_array_equal(f["model-input"].to_numpy(), X.to_numpy()[5:])
     d = np.abs(f["model-output"].to_numpy() - X.to_numpy()[5:])
     np.testing.assert_allclose(f["tag-anomaly-unscaled"].to_numpy(), d, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("T,L,units,funcs", [(20, 6, None, "tanh"), (7, 9, (40, 18), "tanh"), (5, 4, (3,), "relu")])
+def test_lstm_predict_tensor_core_path(T, L, units, funcs):
+    """
+    tcgen05 step kernel (bf16 operands, fp32 accumulate + cell state, tanh.approx gates) against the
+    fp32 oracle.  Stated tolerance: 3e-2 abs on O(1) outputs after L recurrent steps through the stack
+    (bf16 rounding of h at every step); mean error <= 5e-3.
+    """
+    from gordo_b200.fleet import Schedule
+    from gordo_b200.lstm import LSTMFleet
+    rng = np.random.default_rng(40 + T)
+    rows = [300, 129, 140 + L]
+    if units is None:
+        spec = factories.lstm_hourglass(T, lookback_window=L, func=funcs)
+    else:
+        spec = factories.lstm_symmetric(T, lookback_window=L, dims=units, funcs=tuple([funcs] * len(units)))
+    Xs = [rng.random((n, T)).astype(np.float32) * 3 - 1 for n in rows]
+    P = [olstm.lstm_init(spec, rng) for _ in rows]
+    scal = [OMinMax().fit(X) for X in Xs]
+    fl = LSTMFleet(_topo(spec), len(rows), 0, DEV)
+    assert fl.tc_eligible()
+    fl.set_params(torch.from_numpy(np.stack([olstm.lstm_flatten(p) for p in P])))
+    fl.in_scale = torch.from_numpy(np.stack([s.scale_ for s in scal]).astype(np.float32)).to(DEV)
+    fl.in_min = torch.from_numpy(np.stack([s.min_ for s in scal]).astype(np.float32)).to(DEV)
+    X = torch.from_numpy(np.concatenate(Xs)).to(DEV)
+    out, off = fl.predict(Schedule(rows), X, max_windows=256, precision="bf16")      # 300 rows -> 2 chunks
+    ref, _ = fl.predict(Schedule(rows), X, precision="f32")
+    torch.cuda.synchronize()
+    for m, (Xm, p, s) in enumerate(zip(Xs, P, scal)):
+        want = olstm.lstm_predict(spec, p, s.transform(Xm).astype(np.float32), L, 0)
+        got = out[off[m]:off[m + 1]].cpu().numpy()
+        assert got.shape == want.shape
+        scale = max(1.0, float(np.abs(want).max()))
+        np.testing.assert_allclose(got, want, atol=3e-2 * scale, err_msg=f"machine {m}")
+        assert float(np.abs(got - want).mean()) < 5e-3 * scale
+    assert float((out - ref).abs().max()) < 3e-2 * max(1.0, float(ref.abs().max()))

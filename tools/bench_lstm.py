@@ -18,7 +18,8 @@ def main():
     ap.add_argument("--tags", type=int, default=200)
     ap.add_argument("--lookback", type=int, default=128)
     ap.add_argument("--cpu-windows", type=int, default=64)
-    ap.add_argument("--max-windows", type=int, default=16384)
+    ap.add_argument("--max-windows", type=int, default=18944)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     a = ap.parse_args()
     import torch
     from gordo_b200.fleet import Schedule
@@ -31,9 +32,9 @@ def main():
     fl.set_params(topo.init_params(1, g, dev))
     X = torch.rand((a.rows, a.tags), generator=g, device=dev)
     sched = Schedule([a.rows])
-    fl.predict(sched, X, max_windows=a.max_windows); torch.cuda.synchronize()
+    fl.predict(sched, X, max_windows=a.max_windows, precision=a.precision); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out, off = fl.predict(sched, X, max_windows=a.max_windows); e1.record(); torch.cuda.synchronize()
+    e0.record(); out, off = fl.predict(sched, X, max_windows=a.max_windows, precision=a.precision); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     n_win = int(off[-1])
     flops_per_window = a.lookback * sum(8 * u * (i + u) for i, u in zip([a.tags] + topo.units[:-1], topo.units)) \
@@ -46,7 +47,7 @@ def main():
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     res = {"windows": n_win, "ms": ms, "windows_per_s": n_win / (ms * 1e-3), "flops_per_window": flops_per_window,
            "achieved_tflops": n_win * flops_per_window / (ms * 1e-3) / 1e12, "peak_tflops": peak,
-           "frac_of_bf16_tensor_peak": n_win * flops_per_window / (ms * 1e-3) / 1e12 / peak, "units": topo.units}
+           "frac_of_bf16_tensor_peak": n_win * flops_per_window / (ms * 1e-3) / 1e12 / peak, "units": topo.units, "precision": a.precision}
     from oracle import factories, lstm as olstm
     spec = factories.lstm_hourglass(a.tags, lookback_window=a.lookback)
     p = olstm.lstm_unflatten(fl.params[0].cpu().numpy(), spec)
