@@ -25,12 +25,13 @@
 // Replaces models.py:289-300 + diff.py:336-444.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int TILE = 128;
 constexpr int WG_THREADS = 128;
-constexpr int MAX_WG = 4;
+constexpr int MAX_WG = 5;
 
 // ---------------------------------------------------------------- packed operand image
 struct PackLayout {
@@ -120,7 +121,7 @@ struct TcArgs {
     int tmem_cols_total;     // power of two >= 32
     int xtile_bytes;         // 128*T_in*4 rounded to 128
     int ytile_bytes;         // 0 when y aliases x
-    int abuf_bytes;          // 128*max_Kp*2
+    int tmem_a_off;          // column offset of the bf16 A operand inside a warpgroup's TMEM slice
     int vp;                  // padded length of each per-Machine vector (multiple of 16 floats)
 };
 
@@ -134,11 +135,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ void store_a8(uint8_t* dst, const float* v) {
-    uint4 pk;
-    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst) = pk;
+// 8 activations -> 4 TMEM columns of the A operand (this thread's lane = its row)
+__device__ __forceinline__ void store_a8(uint32_t taddr, const float* v) {
+    uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
+    tmem_st4(taddr, pk);
+}
+__device__ __forceinline__ void store_a16(uint32_t taddr, const float* v) {
+    uint32_t pk[8];
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    tmem_st8(taddr, pk);
 }
 __device__ __forceinline__ void load16_bcast(const float* p, float* o) {       // 16-byte aligned broadcast loads
     #pragma unroll
@@ -181,20 +187,30 @@ __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const flo
 }
 
 // hidden layer: accumulator (TMEM, bias already inside the GEMM) -> activation -> bf16 A operand of
-// the next layer, whose column `wout` is the ones column that carries the next bias
+// the next layer, written straight back to TENSOR MEMORY (tcgen05.st): activations never touch
+// shared memory.  Column `wout` of the next A is the ones column that carries the next bias.
 template <int ACT>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane, int n_chunks, int wout, int kp_next,
-                                                uint8_t* __restrict__ arow) {
+                                                uint32_t tmem_a_lane) {
+    const int c_one = wout >> 4, j_one = wout & 15;
     for (int c = 0; c < n_chunks; ++c) {
         float v[16];
         tmem_ld16(tmem_lane + c * 16, v);
         #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j]);
-        store_a8(arow + (c * 2) * 2048, v);
-        store_a8(arow + (c * 2 + 1) * 2048, v + 8);
+        if (c == c_one) {
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (j == j_one) ? 1.0f : v[j];
+        }
+        store_a16(tmem_a_lane + c * 8, v);
     }
-    for (int c = n_chunks * 2; c < kp_next / 8; ++c) *reinterpret_cast<uint4*>(arow + c * 2048) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<unsigned short*>(arow + (wout >> 3) * 2048 + (wout & 7) * 2) = 0x3F80;     // bf16(1.0)
+    if (kp_next > n_chunks * 16) {                     // wout is a multiple of 16: the ones column opens a new chunk
+        float v[16];
+        #pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (j == j_one) ? 1.0f : 0.0f;
+        store_a16(tmem_a_lane + n_chunks * 8, v);
+    }
+    tmem_wait_st();
 }
 
 // final layer, pass 1: d = |yhat - y| written in place over the y tile; returns the two row sums
@@ -304,10 +320,9 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
     float* v_scale = vecs; float* v_min = vecs + a.vp; float* v_es = vecs + 2 * a.vp;
     float* pat_es = vecs + 3 * a.vp; float* pat_ift = vecs + 4 * a.vp + 16;          // periodic copies, T_out + 4 long
     uint8_t* wg_base = smem + a.lay.total_bytes + (5 * a.vp + 32) * 4
-                     + (size_t)wg * (a.xtile_bytes + a.ytile_bytes + a.abuf_bytes);
+                     + (size_t)wg * (a.xtile_bytes + a.ytile_bytes);
     float* xbuf = reinterpret_cast<float*>(wg_base);
     float* ybuf = y_sep ? reinterpret_cast<float*>(wg_base + a.xtile_bytes) : xbuf;
-    uint8_t* abuf = wg_base + a.xtile_bytes + a.ytile_bytes;
 
     if (tid == 0) {
         mbar_init(&w_bar, 1);
@@ -320,12 +335,13 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
     tc_fence_after();
     const uint32_t tmem_acc = s_tmem_base + (uint32_t)(wg * a.tmem_cols_wg);          // column offset
     const uint32_t tmem_lane = tmem_acc + ((uint32_t)(warp_in_wg * 32) << 16);        // this warp's lanes
+    const uint32_t tmem_a = tmem_acc + (uint32_t)a.tmem_a_off;                        // bf16 A operand columns
+    const uint32_t tmem_a_lane = tmem_a + ((uint32_t)(warp_in_wg * 32) << 16);
 
     const int per_cta = (a.tiles_total + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * per_cta;
     const int t_end = min(t_begin + per_cta, a.tiles_total);
     uint32_t w_phase = 0, x_phase = 0, mma_phase = 0;
-    uint8_t* const arow = abuf + (wtid >> 3) * 128 + (wtid & 7) * 16;     // this row's 16-byte slot per K chunk
 
     int seg_begin = t_begin;
     while (seg_begin < t_end) {
@@ -374,8 +390,8 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                 if (y_sep) for (int i = wtid; i < nrows * T_out; i += WG_THREADS) ybuf[i] = ysrc[i];
                 named_bar_sync(1 + wg, WG_THREADS);
             }
-            // ---- A operand of layer 0: bf16(x*scale+min).  Rows past nrows hold stale data: rows never
-            // mix inside a GEMM and those rows are never stored, so they need no masking.
+            // ---- A operand of layer 0: bf16(x*scale+min), written to tensor memory.  Rows past nrows
+            // hold stale data: rows never mix inside a GEMM and those rows are never stored.
             {
                 const int Kp = a.lay.Kp[0];
                 const float* xr = xbuf + wtid * T_in;
@@ -392,52 +408,48 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                         const float4 m0 = *reinterpret_cast<const float4*>(v_min + c * 8), m1 = *reinterpret_cast<const float4*>(v_min + c * 8 + 4);
                         v[0] = fmaf(v[0], s0.x, m0.x); v[1] = fmaf(v[1], s0.y, m0.y); v[2] = fmaf(v[2], s0.z, m0.z); v[3] = fmaf(v[3], s0.w, m0.w);
                         v[4] = fmaf(v[4], s1.x, m1.x); v[5] = fmaf(v[5], s1.y, m1.y); v[6] = fmaf(v[6], s1.z, m1.z); v[7] = fmaf(v[7], s1.w, m1.w);
-                        store_a8(arow + c * 2048, v);
+                        store_a8(tmem_a_lane + c * 4, v);
                     }
                 } else {
                     for (int c = 0; c < full; ++c) {
                         float v[8];
                         #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = fmaf(xr[c * 8 + j], v_scale[c * 8 + j], v_min[c * 8 + j]);
-                        store_a8(arow + c * 2048, v);
+                        store_a8(tmem_a_lane + c * 4, v);
                     }
                 }
-                int c = full;
-                if (T_in & 7) {
+                // the chunk holding column T_in (the ones column that carries the first bias), then zero padding
+                for (int c = full; c < Kp / 8; ++c) {
                     float v[8];
                     #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = c * 8 + j;
-                        v[j] = k < T_in ? fmaf(xr[k], v_scale[k], v_min[k]) : 0.0f;
+                        v[j] = k < T_in ? fmaf(xr[k], v_scale[k], v_min[k]) : (k == T_in ? 1.0f : 0.0f);
                     }
-                    store_a8(arow + c * 2048, v);
-                    ++c;
+                    store_a8(tmem_a_lane + c * 4, v);
                 }
-                for (; c < Kp / 8; ++c) *reinterpret_cast<uint4*>(arow + c * 2048) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<unsigned short*>(arow + (T_in >> 3) * 2048 + (T_in & 7) * 2) = 0x3F80;   // ones column
+                tmem_wait_st();
             }
             // ---- the Dense stack
             for (int l = 0; l < L; ++l) {
                 const int Kp = a.lay.Kp[l], Np = a.lay.Np[l];
-                fence_proxy_async();            // generic-proxy A stores -> visible to the tensor core
-                tc_fence_before();
+                tc_fence_before();              // A stores (tcgen05.st, already waited) ordered before the MMAs
                 named_bar_sync(1 + wg, WG_THREADS);
                 if (wtid == 0) {
                     tc_fence_after();
                     const uint32_t idesc = make_idesc(TILE, Np);
-                    const uint32_t a_addr = smem_u32(abuf), b_addr = smem_u32(w_img + a.lay.w_off[l]);
+                    const uint32_t b_addr = smem_u32(w_img + a.lay.w_off[l]);
                     const uint32_t b_lbo = (uint32_t)(Np / 8) * 128;
                     for (int ks = 0; ks < Kp / 16; ++ks) {
-                        const uint64_t da = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
                         const uint64_t db = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
-                        umma_bf16(tmem_acc, da, db, idesc, ks > 0 ? 1u : 0u);
+                        umma_bf16_ts(tmem_acc, tmem_a + ks * 8, db, idesc, ks > 0 ? 1u : 0u);      // K=16 bf16 = 8 columns of A
                     }
                     umma_commit(&mma_bar[wg]);
                 }
                 mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
                 tc_fence_after();
                 if (l == L - 1) break;
-                GB_DISPATCH_ACT(a.arch.acts[l], hidden_epilogue<ACT>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], arow));
+                GB_DISPATCH_ACT(a.arch.acts[l], hidden_epilogue<ACT>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], tmem_a_lane));
             }
             // ---- final epilogue
             const int code = a.arch.acts[L - 1];
@@ -497,7 +509,7 @@ int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch) {
     // a layer fits one UMMA (N <= 256) and one accumulator slice (<= 512 TMEM columns)
     if (lay.max_Np > 256 || lay.max_Kp > 256) return 0;
     const int T_in = arch->widths[0], T_out = arch->widths[arch->n_layers];
-    const int64_t per_wg = gb_round_up(TILE * T_in * 4, 16) + gb_round_up(TILE * T_out * 4, 16) + TILE * lay.max_Kp * 2;
+    const int64_t per_wg = gb_round_up(TILE * T_in * 4, 128) + gb_round_up(TILE * T_out * 4, 128);
     if (lay.total_bytes + 4096 + per_wg > 227 * 1024 - 2048) return 0;
     return lay.total_bytes;
 }
@@ -530,14 +542,16 @@ int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const
     const int T_in = arch->widths[0], T_out = arch->widths[arch->n_layers];
     a.xtile_bytes = gb_round_up(TILE * T_in * 4, 128);
     a.ytile_bytes = a.y ? gb_round_up(TILE * T_out * 4, 128) : 0;
-    a.abuf_bytes = TILE * a.lay.max_Kp * 2;
     a.vp = gb_round_up((T_in > T_out ? T_in : T_out) + 4, 16);
-    int cols = 32; while (cols < a.lay.max_Np) cols <<= 1;
+    // TMEM slice of a warpgroup: fp32 accumulator (max_Np columns) + bf16 A operand (max_Kp/2 columns)
+    a.tmem_a_off = a.lay.max_Np;
+    const int cols = a.lay.max_Np + a.lay.max_Kp / 2;
     a.tmem_cols_wg = cols;
     const size_t cap = 227 * 1024 - 1024;
     const size_t fixed = (size_t)a.lay.total_bytes + (size_t)(5 * a.vp + 32) * 4;
-    const size_t per_wg = (size_t)a.xtile_bytes + a.ytile_bytes + a.abuf_bytes;
+    const size_t per_wg = (size_t)a.xtile_bytes + a.ytile_bytes;
     int nwg = MAX_WG;
+    { const char* e = getenv("GB200_FF_NWG"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_WG) nwg = atoi(e); }   // tuning knob
     while (nwg > 1 && (fixed + nwg * per_wg > cap || nwg * cols > 512)) --nwg;
     GB_REQUIRE(fixed + nwg * per_wg <= cap, "ff_score_tc: topology does not fit in shared memory");
     a.nwg = nwg;

@@ -16,6 +16,7 @@
 // bf16 operands / fp32 accumulate / fp32 cell state; gates via tanh.approx (sigmoid = .5*tanh(.5z)+.5).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 using namespace gbptx;
 
@@ -341,8 +342,12 @@ void launch_step(const StepTc& a, int tiles, size_t smem, cudaStream_t stream) {
         cudaFuncSetAttribute(lstm_step_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    // clusters of 4 window tiles share every weight block (multicast); 148 SMs = 37 clusters
-    const int csize = tiles >= 4 ? 4 : (tiles >= 2 ? 2 : 1);
+    // optional clusters of 2/4 window tiles share every weight block by multicast (GB200_LSTM_CLUSTER)
+    static int forced = -1;                        // debug knob: GB200_LSTM_CLUSTER=1|2|4
+    if (forced < 0) { const char* e = getenv("GB200_LSTM_CLUSTER"); forced = e ? atoi(e) : 0; }
+    int csize = 1;      // measured on B200 (c4 shape): 1 -> 971k, 2 -> 824k, 4 -> 731k windows/s: the cluster
+                        // lock-step costs more than the multicast saves while the per-block chain is latency-bound
+    if (forced == 1 || forced == 2 || forced == 4) csize = forced > tiles ? 1 : forced;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((tiles + csize - 1) / csize * csize);
     cfg.blockDim = dim3(2 * WG + 32);
