@@ -10,13 +10,13 @@
 //   * W|U  : per 16-unit block the B operand [K/8][8][8][8] with columns ordered unit*4+gate, so
 //            a 16-column tcgen05.ld delivers the i,f,c,o pre-activations of 4 units;
 //   * c_l  : fp32 cell state, unit-major [units][S] (coalesced over windows).
-// CTA = one 128-window tile (TMEM lane = window), 2 warpgroups alternating over the layer's unit
-// blocks: while one warpgroup runs the gate epilogue of block b the other's MMAs of block b+1
-// execute, and each prefetches its next B block as soon as its MMAs have committed.
+// CTA = one 128-window tile (TMEM lane = window): loader warp + MMA warp + 4 gate-epilogue
+// warpgroups over a 2-stage weight ring and 4 accumulator stages (see lstm_step_tc_kernel).
+// (A cluster-multicast variant of the weight loads was measured slower -- 971k / 824k / 731k
+// windows/s at cluster size 1 / 2 / 4 on the c4 shape -- and dropped.)
 // bf16 operands / fp32 accumulate / fp32 cell state; gates via tanh.approx (sigmoid = .5*tanh(.5z)+.5).
 #include "common.cuh"
 #include "ptx.cuh"
-#include <stdlib.h>
 
 using namespace gbptx;
 
@@ -26,6 +26,7 @@ constexpr int TILE = 128;
 constexpr int UB = 16;             // units per block -> 64 GEMM columns
 constexpr int NB_COLS = UB * 4;
 constexpr int WG = 128;
+constexpr int B_STAGES_HOST = 4;    // == B_STAGES of the step kernel
 
 struct TcLayer {
     int in, u, Kx, Kh, n_blocks, act;
@@ -62,7 +63,7 @@ TcPlan make_tc_plan(const gb200_lstm_arch* a) {
         y.b_off = off; off += 4 * y.u;
         y.wp_off = wp; wp += (size_t)y.n_blocks * (y.Kx + y.Kh) * NB_COLS * 2;
         y.bias_off = bf; bf += (size_t)y.n_blocks * NB_COLS;
-        const size_t s = (size_t)TILE * (y.Kx + y.Kh) * 2 + 2 * (size_t)(y.Kx + y.Kh) * NB_COLS * 2;
+        const size_t s = (size_t)TILE * (y.Kx + y.Kh) * 2 + (size_t)B_STAGES_HOST * (y.Kx > y.Kh ? y.Kx : y.Kh) * NB_COLS * 2;
         if (s > smem) smem = s;
         in = y.u;
     }
@@ -163,64 +164,58 @@ struct StepTc {
     const uint8_t* wp; const float* bias;  // this layer's packed blocks / biases
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
-}
-// one slice of a weight block, delivered to the same offset in every CTA of `mask`
-__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// CTA = 2 epilogue/MMA warpgroups + 1 loader warp.  A thread-block cluster of C CTAs (C window
-// tiles of the same launch) shares every weight block: each CTA fetches 1/C of the block and
-// multicasts it to all C shared memories, so the L2 -> SM weight traffic drops by C.
+constexpr int EPI_WG = 4;          // epilogue warpgroups = TMEM accumulator stages
+constexpr int B_STAGES = 4;        // weight ring in shared memory; one entry = the x rows OR the h rows of a block
+constexpr int STEP_THREADS = EPI_WG * WG + 64;
+
+// Warp-specialised pipeline, one CTA per 128-window tile:
+//   loader warp  : A operand once ([x_t | h_{t-1}], bulk copies), then the layer's weight blocks
+//                  through a 2-stage ring (b_full / b_empty);
+//   MMA warp     : per block K/16 tcgen05.mma into accumulator stage b%4, then two commits: one
+//                  frees the weight stage, one publishes the accumulator (t_full);
+//   4 epilogue warpgroups (TMEM lane = window): gates, cell update, h -> HBM in the A-operand
+//                  layout of the next launch; block b belongs to warpgroup b%4 (t_empty hands the
+//                  accumulator stage back).
+// Tensor pipe, weight streaming and the MUFU-heavy gate math of 4 different blocks overlap.
 template <int ACT>
-__global__ void __launch_bounds__(2 * WG + 32, 1)
+__global__ void __launch_bounds__(STEP_THREADS, 1)
 lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t a_bar[2];          // x part, h part of the A operand
-    __shared__ __align__(8) uint64_t b_bar[2];          // B block landed (per warpgroup buffer)
-    __shared__ __align__(8) uint64_t e_bar[2];          // B buffer free in EVERY CTA of the cluster
-    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ __align__(8) uint64_t a_bar[2];                 // x part, h part of the A operand
+    __shared__ __align__(8) uint64_t b_full[B_STAGES], b_empty[B_STAGES];
+    __shared__ __align__(8) uint64_t t_full[EPI_WG], t_empty[EPI_WG];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, wg = tid / WG, wtid = tid - wg * WG, warp = wtid >> 5;
-    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
-    const bool active = (int)blockIdx.x < a.tiles;               // padding CTAs of the last cluster only relay loads
-    const int tile = active ? blockIdx.x : a.tiles - 1;
+    const int tile = blockIdx.x;
     const int K = a.Kx + a.Kh;
     const bool has_h = a.t > 0;
     const uint32_t blk_bytes = (uint32_t)K * NB_COLS * 2;
+    const uint32_t stage_bytes = (uint32_t)(a.Kx > a.Kh ? a.Kx : a.Kh) * NB_COLS * 2;
     uint8_t* A = smem;                                           // [K/8][128][16 B]
     uint8_t* Bbase = smem + (size_t)TILE * K * 2;
+    // unit blocks are independent, so each tile walks them from a different start: at any moment the
+    // CTAs of a launch stream DIFFERENT weight blocks instead of hammering the same L2 lines
+    const int rot = tile % a.n_blocks;
 
     if (tid == 0) {
         mbar_init(&a_bar[0], 1); mbar_init(&a_bar[1], 1);
-        mbar_init(&b_bar[0], 1); mbar_init(&b_bar[1], 1);
-        mbar_init(&e_bar[0], csize); mbar_init(&e_bar[1], csize);
-        mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1);
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < EPI_WG; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) tmem_alloc(&s_tmem, 2 * NB_COLS);
+    if (tid < 32) tmem_alloc(&s_tmem, EPI_WG * NB_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (csize > 1) cluster_sync_all();            // every CTA's barriers exist before any multicast lands
 
-    if (wg == 2) {
-        // ===================== loader warp =====================
-        if (tid == 2 * WG) {
+    if (wg == EPI_WG) {
+        if (wtid == 0) {
+            // ===================== loader =====================
             const uint32_t xb = (uint32_t)a.Kx * 256;
             mbar_expect_tx(&a_bar[0], xb);
             if (a.layer == 0) {
@@ -234,55 +229,65 @@ lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
                 mbar_expect_tx(&a_bar[1], hb);
                 bulk_g2s(A + xb, a.h_prev + (size_t)tile * hb, hb, &a_bar[1]);
             }
-            const uint32_t slice = blk_bytes / csize;
-            const uint16_t mask = (uint16_t)((1u << csize) - 1);
-            uint32_t e_phase[2] = {0, 0};
+            // ring entries: (block, x rows) then (block, h rows): 4 smaller copies in flight hide the
+            // L2 latency that a 2-deep ring of whole blocks exposed
+            const int parts = has_h ? 2 : 1;
+            int it = 0;
             for (int b = 0; b < a.n_blocks; ++b) {
-                const int w = b & 1;
-                if (b >= 2) { mbar_wait(&e_bar[w], e_phase[w]); e_phase[w] ^= 1; }      // all C copies of buffer w are free
-                uint8_t* dst = Bbase + (size_t)w * blk_bytes + (size_t)crank * slice;
-                const uint8_t* src = a.wp + (size_t)b * blk_bytes + (size_t)crank * slice;
-                mbar_expect_tx(&b_bar[w], blk_bytes);
-                if (csize > 1) bulk_g2s_multicast(dst, src, slice, &b_bar[w], mask);
-                else bulk_g2s(dst, src, slice, &b_bar[w]);
+                const int blk = (b + rot) % a.n_blocks;
+                for (int part = 0; part < parts; ++part, ++it) {
+                    const int s = it % B_STAGES;
+                    if (it >= B_STAGES) mbar_wait(&b_empty[s], ((it / B_STAGES) - 1) & 1);
+                    const uint32_t bytes = (uint32_t)(part == 0 ? a.Kx : a.Kh) * NB_COLS * 2;
+                    mbar_expect_tx(&b_full[s], bytes);
+                    bulk_g2s(Bbase + (size_t)s * stage_bytes, a.wp + (size_t)blk * blk_bytes + (part ? (size_t)a.Kx * NB_COLS * 2 : 0),
+                             bytes, &b_full[s]);
+                }
+            }
+        } else if (wtid == 32) {
+            // ===================== MMA issuer =====================
+            mbar_wait(&a_bar[0], 0);
+            if (has_h) mbar_wait(&a_bar[1], 0);
+            const uint32_t idesc = make_idesc(TILE, NB_COLS);
+            const uint32_t a_addr = smem_u32(A);
+            const int parts = has_h ? 2 : 1;
+            int it = 0;
+            for (int b = 0; b < a.n_blocks; ++b) {
+                const int q = b % EPI_WG;
+                if (b >= EPI_WG) mbar_wait(&t_empty[q], ((b / EPI_WG) - 1) & 1);
+                const uint32_t d_tmem = s_tmem + (uint32_t)(q * NB_COLS);
+                for (int part = 0; part < parts; ++part, ++it) {
+                    const int s = it % B_STAGES;
+                    mbar_wait(&b_full[s], (it / B_STAGES) & 1);
+                    tc_fence_after();
+                    // descriptors advance by a constant in their start-address field: no per-step rebuild
+                    uint64_t da = make_desc(a_addr + (part ? (uint32_t)a.Kx * 256 : 0), 2048, 128);
+                    uint64_t db = make_desc(smem_u32(Bbase + (size_t)s * stage_bytes), 1024, 128);
+                    const int ksteps = (part ? a.Kh : a.Kx) / 16;
+                    umma_bf16(d_tmem, da, db, idesc, part ? 1u : 0u);
+                    #pragma unroll 4
+                    for (int ks = 1; ks < ksteps; ++ks) {
+                        da += (2 * 2048) >> 4; db += (2 * 1024) >> 4;
+                        umma_bf16(d_tmem, da, db, idesc, 1u);
+                    }
+                    umma_commit(&b_empty[s]);      // ring entry reusable once these MMAs retire
+                }
+                umma_commit(&t_full[q]);           // accumulator ready for warpgroup q
             }
         }
     } else {
-        // ===================== MMA + gate-epilogue warpgroups =====================
-        uint8_t* Bbuf = Bbase + (size_t)wg * blk_bytes;
-        const uint32_t tmem_acc = s_tmem + (uint32_t)(wg * NB_COLS);
-        const uint32_t tmem_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+        // ===================== gate epilogue, warpgroup q = wg =====================
+        const uint32_t tmem_lane = s_tmem + (uint32_t)(wg * NB_COLS) + ((uint32_t)(warp * 32) << 16);
         const int w = tile * TILE + wtid;                 // window index inside the chunk
-        uint32_t b_phase = 0, m_phase = 0;
-        bool a_ready = false;
-        for (int b = wg; b < a.n_blocks; b += 2) {
-            // cell state of this block's 16 units: 16 independent coalesced loads issued BEFORE the MMA
-            // wait, so their HBM/L2 latency hides behind the tensor-core work
+        for (int j = wg; j < a.n_blocks; j += EPI_WG) {
+            const int b = (j + rot) % a.n_blocks;            // the unit block this pipeline slot carries
+            // cell state of this block's 16 units: independent coalesced loads issued BEFORE the wait
             float cprev[UB];
             #pragma unroll
             for (int ul = 0; ul < UB; ++ul)
                 cprev[ul] = has_h ? __ldcg(a.c + (size_t)(b * UB + ul) * a.S + w) : 0.0f;
-            if (wtid == 0) {
-                mbar_wait(&b_bar[wg], b_phase);
-                if (!a_ready) { mbar_wait(&a_bar[0], 0); if (has_h) mbar_wait(&a_bar[1], 0); }
-                tc_fence_after();
-                const uint32_t idesc = make_idesc(TILE, NB_COLS);
-                const uint32_t a_addr = smem_u32(A), b_addr = smem_u32(Bbuf);
-                const int ksteps = (has_h ? K : a.Kx) / 16;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t da = make_desc(a_addr + ks * 2 * 2048, 2048, 128);
-                    const uint64_t db = make_desc(b_addr + ks * 2 * 1024, 1024, 128);
-                    umma_bf16(tmem_acc, da, db, idesc, ks > 0 ? 1u : 0u);
-                }
-                umma_commit(&mma_bar[wg]);
-            }
-            a_ready = true; b_phase ^= 1;
-            mbar_wait(&mma_bar[wg], m_phase); m_phase ^= 1;
+            mbar_wait(&t_full[wg], (j / EPI_WG) & 1);
             tc_fence_after();
-            // this CTA's copy of buffer `wg` is free: tell every loader in the cluster
-            if (wtid == 0 && b + 2 < a.n_blocks)
-                for (uint32_t r = 0; r < csize; ++r) mbar_arrive_remote(&e_bar[wg], r);
-            // ---- gate epilogue: 4 chunks of 16 columns = 4 units x (i,f,c~,o)
             const float* bias = a.bias + (size_t)b * NB_COLS;
             float hreg[8];
             #pragma unroll
@@ -296,7 +301,7 @@ lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
                     const float ig = sigmoid_fast(v[q * 4 + 0] + bb.x), fg = sigmoid_fast(v[q * 4 + 1] + bb.y);
                     const float gg = act_fast<ACT>(v[q * 4 + 2] + bb.z), og = sigmoid_fast(v[q * 4 + 3] + bb.w);
                     const float cn = fmaf(fg, cprev[ul], ig * gg);
-                    if (active) __stcg(a.c + (size_t)(b * UB + ul) * a.S + w, cn);
+                    __stcg(a.c + (size_t)(b * UB + ul) * a.S + w, cn);
                     hreg[(c4 & 1) * 4 + q] = og * act_fast<ACT>(cn);
                 }
                 if (c4 & 1) {
@@ -306,18 +311,17 @@ lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
                     pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
                     pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
                     const int chunk = b * 2 + (c4 >> 1);
-                    if (active)
-                        *reinterpret_cast<uint4*>(a.h_out + (size_t)tile * a.Kh * 256 + (size_t)chunk * 2048 + wtid * 16) = pk;
+                    *reinterpret_cast<uint4*>(a.h_out + (size_t)tile * a.Kh * 256 + (size_t)chunk * 2048 + wtid * 16) = pk;
                 }
             }
             tc_fence_before();
-            named_bar_sync(1 + wg, WG);          // every lane has drained TMEM before the next block's MMAs
+            named_bar_sync(1 + wg, WG);          // every lane has drained its TMEM reads
+            if (wtid == 0) mbar_arrive(&t_empty[wg]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (csize > 1) cluster_sync_all();            // no CTA leaves while peers may still multicast into it
-    if (tid < 32) tmem_dealloc(s_tmem, 2 * NB_COLS);
+    if (tid < 32) tmem_dealloc(s_tmem, EPI_WG * NB_COLS);
 }
 
 // yhat = out_act(h_last . Wd + bd) with h_last read from the canonical bf16 tiles
@@ -342,21 +346,7 @@ void launch_step(const StepTc& a, int tiles, size_t smem, cudaStream_t stream) {
         cudaFuncSetAttribute(lstm_step_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    // optional clusters of 2/4 window tiles share every weight block by multicast (GB200_LSTM_CLUSTER)
-    static int forced = -1;                        // debug knob: GB200_LSTM_CLUSTER=1|2|4
-    if (forced < 0) { const char* e = getenv("GB200_LSTM_CLUSTER"); forced = e ? atoi(e) : 0; }
-    int csize = 1;      // measured on B200 (c4 shape): 1 -> 971k, 2 -> 824k, 4 -> 731k windows/s: the cluster
-                        // lock-step costs more than the multicast saves while the per-block chain is latency-bound
-    if (forced == 1 || forced == 2 || forced == 4) csize = forced > tiles ? 1 : forced;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((tiles + csize - 1) / csize * csize);
-    cfg.blockDim = dim3(2 * WG + 32);
-    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, lstm_step_tc_kernel<ACT>, a);
+    lstm_step_tc_kernel<ACT><<<tiles, STEP_THREADS, smem, stream>>>(a);
 }
 
 }  // namespace
@@ -430,7 +420,7 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
                     a.h_out = base + y.h_off[t & 1];
                     a.c = (float*)(base + y.c_off);
                     a.wp = wp + y.wp_off; a.bias = bias + y.bias_off;
-                    const size_t smem = (size_t)TILE * (y.Kx + y.Kh) * 2 + 2 * (size_t)(y.Kx + y.Kh) * NB_COLS * 2;
+                    const size_t smem = (size_t)TILE * (y.Kx + y.Kh) * 2 + (size_t)B_STAGES_HOST * (y.Kx > y.Kh ? y.Kx : y.Kh) * NB_COLS * 2;
                     switch (y.act) {
                         case GB200_ACT_TANH: launch_step<GB200_ACT_TANH>(a, tiles, smem, stream); break;
                         case GB200_ACT_RELU: launch_step<GB200_ACT_RELU>(a, tiles, smem, stream); break;
