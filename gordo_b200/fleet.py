@@ -174,6 +174,35 @@ class FFFleet:
         return scale, mn
 
     @staticmethod
+    def score_outputs(model_out: torch.Tensor, y: torch.Tensor, out_row_off, y_row_off, *, err_scale=None,
+                      feat_thr=None, agg_thr=None):
+        """
+        DiffBasedAnomalyDetector columns (diff.py:350-444) for PRECOMPUTED model output whose rows are
+        offset against y (LSTM: the output is shorter than the input).  Machine m's output rows
+        [out_row_off[m], out_row_off[m+1]) align with rows of y starting at y_row_off[m].
+        """
+        _require_cuda(model_out, y, err_scale, feat_thr, agg_thr)
+        dev = model_out.device
+        M = len(y_row_off)
+        R, T = model_out.shape
+        oo = torch.as_tensor(np.asarray(out_row_off, np.int64), device=dev)
+        yo = torch.as_tensor(np.asarray(y_row_off, np.int64), device=dev)
+        res = {"tag-anomaly-scaled": torch.empty((R, T), dtype=torch.float32, device=dev),
+               "tag-anomaly-unscaled": torch.empty((R, T), dtype=torch.float32, device=dev),
+               "total-anomaly-scaled": torch.empty((R,), dtype=torch.float32, device=dev),
+               "total-anomaly-unscaled": torch.empty((R,), dtype=torch.float32, device=dev)}
+        if feat_thr is not None:
+            res["anomaly-confidence"] = torch.empty((R, T), dtype=torch.float32, device=dev)
+        if agg_thr is not None:
+            res["total-anomaly-confidence"] = torch.empty((R,), dtype=torch.float32, device=dev)
+        N.check(N.lib().gb200_score_outputs(
+            M, N.ptr(oo), N.ptr(yo), T, N.ptr(model_out), N.ptr(y), N.ptr(err_scale), N.ptr(feat_thr), N.ptr(agg_thr),
+            N.ptr(res["tag-anomaly-scaled"]), N.ptr(res["tag-anomaly-unscaled"]), N.ptr(res["total-anomaly-scaled"]),
+            N.ptr(res["total-anomaly-unscaled"]), N.ptr(res.get("anomaly-confidence")),
+            N.ptr(res.get("total-anomaly-confidence")), _stream_ptr()), "gb200_score_outputs")
+        return res
+
+    @staticmethod
     def rolling_min_max(v: torch.Tensor, rows_lo: torch.Tensor, rows_hi: torch.Tensor, window: int = 6):
         """pandas rolling(window).min().max() per column over row ranges -> [J, C]."""
         v2 = v if v.dim() == 2 else v.unsqueeze(1)

@@ -8,8 +8,9 @@ absent.
 ``anomaly()`` takes the fused GPU path -- MinMax input scaling, Dense stack, |yhat - y| columns and
 confidences in ONE launch of libgordo_b200.so -- whenever the detector is the standard
 ``Pipeline[MinMaxScaler, KerasAutoEncoder]`` (or a bare KerasAutoEncoder) with a MinMaxScaler error
-scaler; any other composition (RobustScaler, LSTM, extra transformers) predicts on the GPU through
-the base estimator and derives the columns on the host exactly as the reference does.
+scaler; for the LSTM estimators the GPU predict is followed by ``gb200_score_outputs`` on the offset
+output.  Any other composition (RobustScaler, extra transformers) predicts on the GPU through the
+base estimator and derives the columns on the host exactly as the reference does.
 """
 from datetime import timedelta
 from typing import Optional, Union
@@ -26,7 +27,7 @@ from sklearn.utils import shuffle
 from gordo_b200.machine.model import utils as model_utils
 from gordo_b200.machine.model.anomaly.base import AnomalyDetectorBase
 from gordo_b200.machine.model.base import GordoBase
-from gordo_b200.machine.model.models import KerasAutoEncoder
+from gordo_b200.machine.model.models import KerasAutoEncoder, KerasLSTMBaseEstimator
 
 
 def _rows(a, idx):
@@ -196,12 +197,13 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         if tuple(getattr(self.scaler, "feature_range", (0, 1))) != (0, 1):
             return None
         be = self.base_estimator
-        if isinstance(be, KerasAutoEncoder) and type(be) is KerasAutoEncoder:
-            return (None, be) if be.model is not None else None
+        ours = lambda e: (type(e) is KerasAutoEncoder or isinstance(e, KerasLSTMBaseEstimator)) and e.model is not None
+        if ours(be):
+            return (None, be)
         if isinstance(be, Pipeline) and len(be.steps) == 2:
             sc, est = be.steps[0][1], be.steps[1][1]
-            if (isinstance(sc, MinMaxScaler) and hasattr(sc, "scale_") and type(est) is KerasAutoEncoder
-                    and est.model is not None and tuple(sc.feature_range) == (0, 1) and not getattr(sc, "clip", False)):
+            if (isinstance(sc, MinMaxScaler) and hasattr(sc, "scale_") and ours(est)
+                    and tuple(sc.feature_range) == (0, 1) and not getattr(sc, "clip", False)):
                 return (sc, est)
         return None
 
@@ -211,6 +213,8 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         sc, est = plan
         topo = est.model.topology
         dev = torch.device("cuda", torch.cuda.current_device())
+        if isinstance(est, KerasLSTMBaseEstimator):
+            return self._fused_columns_lstm(sc, est, Xv, yv, dev)
         fleet = FFFleet(topo, 1, dev)
         fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
         f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)[None], device=dev)
@@ -226,6 +230,30 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
         prec = est._precision if fleet.tc_eligible() else "f32"
         res = fleet.score(Schedule([len(Xv)]), xd, yd, precision=prec)
+        return {k: v.cpu().numpy() for k, v in res.items()}
+
+    def _fused_columns_lstm(self, sc, est, Xv, yv, dev):
+        """LSTM base: predict on the GPU (windows never materialised), then score the offset output."""
+        import torch
+        from gordo_b200.fleet import FFFleet, Schedule
+        from gordo_b200.lstm import LSTMFleet
+        topo = est.model.topology
+        fleet = LSTMFleet(topo, 1, est.lookahead, dev)
+        fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)[None], device=dev)
+        if sc is not None:
+            fleet.in_scale, fleet.in_min = f32(sc.scale_), f32(sc.min_)
+        xd = torch.as_tensor(np.ascontiguousarray(Xv, np.float32), device=dev)
+        yd = torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
+        prec = est._precision if fleet.tc_eligible() else "f32"
+        out, off = fleet.predict(Schedule([len(Xv)]), xd, precision=prec)
+        n_out = int(off[-1])
+        feat = self.__dict__.get("feature_thresholds_"); agg = self.__dict__.get("aggregate_threshold_")
+        res = FFFleet.score_outputs(
+            out, yd, off, [len(yv) - n_out], err_scale=f32(self.scaler.scale_),
+            feat_thr=None if feat is None else f32(np.asarray(feat, np.float64)),
+            agg_thr=None if agg is None else torch.as_tensor(np.array([agg], np.float32), device=dev))
+        res["model-output"] = out
         return {k: v.cpu().numpy() for k, v in res.items()}
 
     def anomaly(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None) -> pd.DataFrame:
@@ -248,7 +276,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         x_tags = list(X.columns)
         y_tags = list(y.columns) if hasattr(y, "columns") else x_tags
         plan = self._fused_plan()
-        if plan is not None and Xv.shape[1] == plan[1].model.topology.n_in and yv.shape[1] == plan[1].model.topology.n_out:
+        if plan is not None and Xv.shape[1] == _n_in(plan[1]) and yv.shape[1] == _n_out(plan[1]):
             cols = self._fused_columns(plan, Xv, yv)
             out = cols["model-output"]
             d_scaled, tot_scaled = cols["tag-anomaly-scaled"], cols["total-anomaly-scaled"]
@@ -284,6 +312,16 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         if tconf is not None:
             groups.append(("total-anomaly-confidence", tconf, None))
         return model_utils.assemble_frame(groups, getattr(X, "index", None), frequency)
+
+
+def _n_in(est):
+    t = est.model.topology
+    return getattr(t, "n_in", None) or t.n_features
+
+
+def _n_out(est):
+    t = est.model.topology
+    return getattr(t, "n_out", None) or t.n_features_out
 
 
 def _as_like(y_pred, y_true):

@@ -368,7 +368,8 @@ class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin):
         fleet = LSTMFleet(self.model.topology, 1, self.lookahead, dev)
         fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
         xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
-        out, _ = fleet.predict(Schedule([len(X)]), xd)
+        prec = self._precision if fleet.tc_eligible() else "f32"       # "bf16": tcgen05 step kernel
+        out, _ = fleet.predict(Schedule([len(X)]), xd, precision=prec)
         return out.cpu().numpy()
 
     def transform(self, X, **kwargs):

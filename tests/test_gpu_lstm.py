@@ -173,3 +173,33 @@ def test_lstm_predict_tensor_core_path(T, L, units, funcs):
         np.testing.assert_allclose(got, want, atol=3e-2 * scale, err_msg=f"machine {m}")
         assert float(np.abs(got - want).mean()) < 5e-3 * scale
     assert float((out - ref).abs().max()) < 3e-2 * max(1.0, float(ref.abs().max()))
+
+
+def test_lstm_detector_fused_scoring_matches_generic_path():
+    """Pipeline[MinMaxScaler, KerasLSTMAutoEncoder]: GPU predict + gb200_score_outputs == host arithmetic."""
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import MinMaxScaler, RobustScaler
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_b200.machine.model.models import KerasLSTMAutoEncoder
+    rng = np.random.default_rng(8)
+    X = pd.DataFrame(rng.random((150, 4)) * [1, 10, 100, 0.1], columns=list("abcd"))
+    np.random.seed(1)
+    det = DiffBasedAnomalyDetector(base_estimator=Pipeline([("s", MinMaxScaler()), ("m", KerasLSTMAutoEncoder(
+        kind="lstm_hourglass", lookback_window=5))]))
+    det.cross_validate(X=X, y=X); det.fit(X, X)
+    assert det._fused_plan() is not None
+    f = det.anomaly(X, X)
+    assert len(f) == 146
+    out = det.predict(X)                                          # generic path pieces on the host
+    np.testing.assert_allclose(f["model-output"].to_numpy(), out, atol=1e-6)
+    d = np.abs(out.astype(np.float64) - X.to_numpy()[4:])
+    s = np.abs(det.scaler.transform(pd.DataFrame(out, columns=X.columns)) - det.scaler.transform(X)[4:])
+    np.testing.assert_allclose(f["tag-anomaly-unscaled"].to_numpy(), d, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(f["tag-anomaly-scaled"].to_numpy(), s, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(f["total-anomaly-scaled"].to_numpy().ravel(), (s ** 2).mean(1), rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(f["anomaly-confidence"].to_numpy(), d / det.feature_thresholds_.to_numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(f["total-anomaly-confidence"].to_numpy().ravel(), (s ** 2).mean(1) / det.aggregate_threshold_, rtol=1e-4, atol=1e-7)
+    # bf16 tensor-core inference selectable from the model kwargs
+    det.base_estimator.steps[1][1].kwargs["precision"] = "bf16"
+    fb = det.anomaly(X, X)
+    assert float(np.abs(fb["model-output"].to_numpy() - f["model-output"].to_numpy()).max()) < 3e-2
