@@ -198,11 +198,16 @@ class FleetModelBuilder:
             vfleet.in_min = in_min[sel].contiguous(); vfleet.err_scale = err_scale[sel].contiguous()
             vs = Schedule(rows_lo=te_lo, rows_hi=te_hi, rows_total=int(off[-1]))
             prec = self.cv_precision if vfleet.tc_eligible() else "f32"
-            res = vfleet.score(vs, xd, yd, precision=prec, columns=("tag-anomaly-unscaled", "total-anomaly-scaled"))
+            res = vfleet.score(vs, xd, yd, precision=prec,
+                               columns=("model-output", "tag-anomaly-unscaled", "total-anomaly-scaled"))
             tl = torch.as_tensor(np.asarray(te_lo, np.int64), device=dev)
             th = torch.as_tensor(np.asarray(te_hi, np.int64), device=dev)
             feat_pf = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], tl, th, 6).reshape(M, k, To)
             agg_pf = FFFleet.rolling_min_max(res["total-anomaly-scaled"], tl, th, 6).reshape(M, k)
+            # the builder's CV metrics (build_model.py:245-289): scoring scaler = MinMaxScaler fitted on the
+            # full y of each Machine = the final job's error scaler
+            full_scale = err_scale[torch.arange(M, device=dev) * per + k].double().cpu().numpy()
+            cv_metrics = FFFleet.cv_scores(ysrc, res["model-output"], tl, th, np.repeat(full_scale, k, axis=0))
         final = torch.arange(M, device=dev) * per + k
         fleet.set_params(params[final]); fleet.in_scale = in_scale[final].contiguous()
         fleet.in_min = in_min[final].contiguous(); fleet.err_scale = err_scale[final].contiguous()
@@ -244,12 +249,37 @@ class FleetModelBuilder:
                 model.aggregate_threshold_ = float(agg_h[m, -1])
                 model.smooth_aggregate_threshold_ = None
                 model.smooth_feature_thresholds_ = None
+            scores = _cv_score_dict({kk: v[m * k:(m + 1) * k] for kk, v in cv_metrics.items()}, tags) if k else {}
             meta = {"name": mc.name, "model_offset": 0, "model": model.get_metadata(),
+                    "cross_validation": {"scores": scores,
+                                         "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
+                                                    enumerate(time_series_split_bounds(int(rows[m]), k))} if k else {}},
                     "fleet": {"machines_in_launch": M, "fit_jobs": J, "fit_duration_sec": t_fit,
                               "build_duration_sec": t_total},
                     "cv_fold_history": {f"fold-{i}": {"loss": [float(v) for v in hl_h[m * per + i]]} for i in range(k)}}
             out.append((model, meta))
         return out
+
+
+def _cv_score_dict(metrics: Dict[str, np.ndarray], tags) -> Dict[str, Dict[str, float]]:
+    """
+    ``scores`` in the layout of build_model.py:274-289: per metric ``{metric}-{tag}`` and the uniform
+    average over tags ``{metric}``, each {fold-mean, fold-std, fold-max, fold-min, fold-1..k}.
+    """
+    out: Dict[str, Dict[str, float]] = {}
+
+    def entry(vals):
+        vals = np.asarray(vals, np.float64)
+        d = {"fold-mean": float(vals.mean()), "fold-std": float(vals.std()), "fold-max": float(vals.max()),
+             "fold-min": float(vals.min())}
+        d.update({f"fold-{i + 1}": float(v) for i, v in enumerate(vals)})
+        return d
+
+    for name, per_tag in metrics.items():               # per_tag: [k folds, T]
+        for j, tag in enumerate(tags):
+            out[f"{name}-{str(tag).replace(' ', '-')}"] = entry(per_tag[:, j])
+        out[name] = entry(per_tag.mean(axis=1))
+    return out
 
 
 def _set_minmax(scaler: MinMaxScaler, scale, min_, data, frame):

@@ -198,6 +198,13 @@ int gb200_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int32_t n_jo
                             hist_loss, hist_acc, (cudaStream_t)stream);
 }
 
+int gb200_cv_sums(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* y,
+                  const float* yhat, int32_t n_tags, double* sums, void* stream) {
+    GB_REQUIRE(n_jobs >= 0 && n_tags >= 1, "bad n_jobs / n_tags");
+    GB_REQUIRE(rows_lo && rows_hi && y && yhat && sums, "NULL argument");
+    return gb_launch_cv_sums(n_jobs, rows_lo, rows_hi, y, yhat, n_tags, sums, (cudaStream_t)stream);
+}
+
 int gb200_score_outputs(int32_t n_machines, const int64_t* out_row_off, const int64_t* y_row_off,
                         int32_t n_tags, const float* model_out, const float* y, const float* err_scale,
                         const float* feat_thr, const float* agg_thr,

@@ -150,6 +150,42 @@ score_outputs_kernel(int M, const int64_t* __restrict__ out_off, const int64_t* 
     }
 }
 
+// per (job, tag): sum y, sum y^2, sum e, sum e^2, sum |e| with e = y - yhat, in double (the variance
+// terms of r2 / explained variance cancel catastrophically in float32)
+__global__ void __launch_bounds__(RED_THREADS)
+cv_sums_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, const float* __restrict__ y,
+               const float* __restrict__ yhat, int T, double* __restrict__ out) {
+    const int job = blockIdx.y;
+    const int64_t r0 = lo[job] + (int64_t)blockIdx.x * ROWS_PER_CHUNK;
+    const int64_t r1 = min(r0 + (int64_t)ROWS_PER_CHUNK, hi[job]);
+    if (r0 >= r1) return;
+    extern __shared__ double smd[];          // [5][R][Tc]
+    for (int c0 = 0; c0 < T; c0 += RED_THREADS) {
+        const int Tc = min(T - c0, RED_THREADS);
+        const int R = RED_THREADS / Tc;
+        const int lane = threadIdx.x / Tc, tag = threadIdx.x - lane * Tc;
+        double acc[5] = {0, 0, 0, 0, 0};
+        if (lane < R) {
+            for (int64_t r = r0 + lane; r < r1; r += R) {
+                const double yv = y[r * T + c0 + tag], e = yv - (double)yhat[r * T + c0 + tag];
+                acc[0] += yv; acc[1] += yv * yv; acc[2] += e; acc[3] += e * e; acc[4] += fabs(e);
+            }
+            #pragma unroll
+            for (int q = 0; q < 5; ++q) smd[(q * R + lane) * Tc + tag] = acc[q];
+        }
+        __syncthreads();
+        if (threadIdx.x < Tc) {
+            #pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                double t = 0.0;
+                for (int l = 0; l < R; ++l) t += smd[(q * R + l) * Tc + threadIdx.x];
+                atomicAdd(out + ((size_t)job * 5 + q) * T + c0 + threadIdx.x, t);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 int max_chunks_host(int n_jobs, const int64_t* lo, const int64_t* hi, cudaStream_t stream, int64_t* out) {
     // row ranges live on the device; the grid must cover the longest job
     int64_t* hl = (int64_t*)malloc(sizeof(int64_t) * 2 * (size_t)n_jobs);
@@ -219,6 +255,22 @@ int gb_launch_score_outputs(int n_machines, const int64_t* out_row_off, const in
     score_outputs_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n_machines, out_row_off, y_row_off, n_tags,
         model_out, y, err_scale, feat_thr, agg_thr, tag_scaled, tag_unscaled, total_scaled, total_unscaled,
         conf, total_conf, rows_total);
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
+}
+
+int gb_launch_cv_sums(int n_jobs, const int64_t* lo, const int64_t* hi, const float* y, const float* yhat,
+                      int n_tags, double* out, cudaStream_t stream) {
+    if (n_jobs <= 0) return GB_OK;
+    int64_t max_rows = 0;
+    int rc = max_chunks_host(n_jobs, lo, hi, stream, &max_rows);
+    if (rc) return rc;
+    GB_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n_jobs * 5 * n_tags, stream));
+    const int chunks = (int)((max_rows + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK);
+    if (chunks > 0) {
+        dim3 grid(chunks, n_jobs);
+        cv_sums_kernel<<<grid, RED_THREADS, 5 * RED_THREADS * sizeof(double), stream>>>(lo, hi, y, yhat, n_tags, out);
+    }
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
 }

@@ -174,6 +174,33 @@ class FFFleet:
         return scale, mn
 
     @staticmethod
+    def cv_scores(y: torch.Tensor, yhat: torch.Tensor, rows_lo: torch.Tensor, rows_hi: torch.Tensor,
+                  scoring_scale: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+        """
+        The builder's cross-validation metrics (build_model.py:377-446) per row range and tag, from one
+        device pass (gb200_cv_sums): explained-variance-score, r2-score, mean-squared-error,
+        mean-absolute-error of MinMax-scaled y / yhat.  ``scoring_scale``: [J, T] scale_ of the
+        scoring scaler fitted on the full y (None = unscaled).  Returns {metric: float64 [J, T]}.
+        """
+        _require_cuda(y, yhat, rows_lo, rows_hi)
+        J, T = rows_lo.numel(), y.shape[1]
+        sums = torch.empty((J, 5, T), dtype=torch.float64, device=y.device)
+        N.check(N.lib().gb200_cv_sums(J, N.ptr(rows_lo), N.ptr(rows_hi), N.ptr(y), N.ptr(yhat), T, N.ptr(sums),
+                                      _stream_ptr()), "gb200_cv_sums")
+        s = sums.cpu().numpy()
+        n = (rows_hi - rows_lo).double().cpu().numpy()[:, None]
+        sy, syy, se, see, sae = s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 4]
+        var_y = syy / n - (sy / n) ** 2
+        var_e = see / n - (se / n) ** 2
+        sc = np.ones((J, T)) if scoring_scale is None else np.asarray(scoring_scale, np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            # sklearn semantics for a constant target: score 1 if the numerator is 0 too, else 0
+            r2 = np.where(var_y > 0, 1.0 - (see / n) / var_y, np.where(see > 0, 0.0, 1.0))
+            ev = np.where(var_y > 0, 1.0 - var_e / var_y, np.where(var_e > 0, 0.0, 1.0))
+        return {"explained-variance-score": ev, "r2-score": r2,
+                "mean-squared-error": (see / n) * sc ** 2, "mean-absolute-error": (sae / n) * np.abs(sc)}
+
+    @staticmethod
     def score_outputs(model_out: torch.Tensor, y: torch.Tensor, out_row_off, y_row_off, *, err_scale=None,
                       feat_thr=None, agg_thr=None):
         """

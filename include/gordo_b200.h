@@ -134,6 +134,17 @@ int gb200_rolling_min_max(int32_t n_jobs, const int64_t* rows_lo, const int64_t*
                           const float* v, int32_t n_cols, int32_t window, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Cross-validation scoring sums (gordo/builder/build_model.py:377-446 builds 4 x (T+1) sklearn
+ * scorers -- explained variance, r2, MSE, MAE per tag and averaged -- each a host pass over the
+ * fold): one pass per fold on the device.  sums: [n_jobs, 5, n_tags] float64 =
+ * sum y, sum y^2, sum e, sum e^2, sum |e| with e = y - yhat over rows [lo, hi) (absolute rows of
+ * both y and yhat); the four metrics of MinMax-scaled data follow on the host (r2 / explained
+ * variance are scale invariant, MSE scales with scale^2, MAE with |scale|).
+ */
+int gb200_cv_sums(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* y,
+                  const float* yhat, int32_t n_tags, double* sums, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Feed-forward training: Keras Model.fit (models.py:243-287 -> scikeras -> [3P] keras) for
  * n_jobs independent fits in one launch (CV folds and the final fit are separate jobs):
  * float32, mini-batches of `batch_size` in the order given by `perm` (NULL = natural order),
