@@ -40,7 +40,7 @@ SIGNATURES = {
     "gb200_fleet_create": (C.c_int, [C.POINTER(_P), _I32, C.POINTER(_I64)]),
     "gb200_fleet_create_ranges": (C.c_int, [C.POINTER(_P), _I32, C.POINTER(_I64), C.POINTER(_I64)]),
     "gb200_fleet_destroy": (None, [_P]),
-    "gb200_ff_score": (C.c_int, [_P, C.POINTER(FFArch), C.c_int] + [_P] * 17),
+    "gb200_ff_score": (C.c_int, [_P, C.POINTER(FFArch), C.c_int] + [_P] * 18),
     "gb200_ff_packed_bytes": (_I64, [C.POINTER(FFArch)]),
     "gb200_ff_pack_bf16": (C.c_int, [C.POINTER(FFArch), _I32, _P, _P, _P]),
     "gb200_ff_param_count": (_I64, [C.POINTER(FFArch)]),

@@ -139,7 +139,7 @@ int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
                    const float* x, const float* y,
                    float* model_out, float* tag_scaled, float* tag_unscaled,
                    float* total_scaled, float* total_unscaled,
-                   float* conf, float* total_conf, void* stream) {
+                   float* conf, float* total_conf, float* activity_l1, void* stream) {
     GB_REQUIRE(f != nullptr, "fleet is NULL");
     int rc = check_ff_arch(arch); if (rc) return rc;
     GB_REQUIRE(x != nullptr, "x is NULL");
@@ -150,9 +150,10 @@ int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
         GB_REQUIRE(params != nullptr, "params is NULL");
         return gb_launch_ff_score_f32(f, arch, params, in_scale, in_min, err_scale, feat_thr, agg_thr, x, y,
                                       model_out, tag_scaled, tag_unscaled, total_scaled, total_unscaled,
-                                      conf, total_conf, (cudaStream_t)stream);
+                                      conf, total_conf, activity_l1, (cudaStream_t)stream);
     }
     if (precision == GB200_PREC_BF16_TC) {
+        GB_REQUIRE(activity_l1 == nullptr, "activity_l1 is only produced by GB200_PREC_F32");
         GB_REQUIRE(packed_bf16 != nullptr, "packed_bf16 is NULL (call gb200_ff_pack_bf16 first)");
         GB_REQUIRE(gb_ff_packed_bytes(arch) > 0, "topology is not eligible for the tensor-core path");
         return gb_launch_ff_score_tc(f, arch, packed_bf16, in_scale, in_min, err_scale, feat_thr, agg_thr, x, y,

@@ -74,7 +74,7 @@ int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, cons
                            const float* feat_thr, const float* agg_thr, const float* x, const float* y,
                            float* model_out, float* tag_scaled, float* tag_unscaled,
                            float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
-                           cudaStream_t stream);
+                           float* activity, cudaStream_t stream);
 int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const void* packed,
                           const float* in_scale, const float* in_min, const float* err_scale,
                           const float* feat_thr, const float* agg_thr, const float* x, const float* y,

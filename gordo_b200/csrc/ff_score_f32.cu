@@ -24,6 +24,7 @@ struct ScoreArgs {
     const float* x; const float* y;
     float* model_out; float* tag_scaled; float* tag_unscaled;
     float* total_scaled; float* total_unscaled; float* conf; float* total_conf;
+    float* activity;      // optional [rows]: sum_l l1[l] * sum_j |h_l[j]| (the Keras activity-regulariser loss of the row)
     int max_w;            // max layer width
     int smem_w_floats;    // padded weight image size (0 = weights stay in global)
 };
@@ -94,9 +95,11 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
 
         float* hin = act0; float* hout = act1;
         int so = 0; int64_t go = 0;
+        float act_l1 = 0.0f;
         for (int l = 0; l < L; ++l) {
             const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
             const int code = a.arch.acts[l];
+            const float c1 = a.activity ? a.arch.l1[l] : 0.0f;
             const int ldw = (wout + 7) & ~7;
             const float* W; const float* B;
             if (SMEM_W) { W = wsm + so; B = W + win * ldw; so += win * ldw + ldw; }
@@ -131,7 +134,11 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
                 }
                 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (n0 + j < wout) hout[(n0 + j) * TILE + tid] = gb_act(code, acc[j]);
+                    if (n0 + j < wout) {
+                        const float h = gb_act(code, acc[j]);
+                        hout[(n0 + j) * TILE + tid] = h;
+                        if (c1 != 0.0f) act_l1 = fmaf(c1, fabsf(h), act_l1);
+                    }
             }
             float* t = hin; hin = hout; hout = t;     // each thread reads only its own column
         }
@@ -157,6 +164,7 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
             if (a.total_scaled) a.total_scaled[row] = ts;
             if (a.total_unscaled) a.total_unscaled[row] = tu;
             if (a.total_conf && a.agg_thr) a.total_conf[row] = ts / a.agg_thr[m];
+            if (a.activity) a.activity[row] = act_l1;
         }
         __syncthreads();            // act buffers / s_m reused by the next tile
     }
@@ -169,8 +177,9 @@ int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, cons
                            const float* feat_thr, const float* agg_thr, const float* x, const float* y,
                            float* model_out, float* tag_scaled, float* tag_unscaled,
                            float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
-                           cudaStream_t stream) {
+                           float* activity, cudaStream_t stream) {
     ScoreArgs a{};
+    a.activity = activity;
     a.arch = *arch;
     a.row_lo = f->d_row_lo; a.row_hi = f->d_row_hi; a.tile_off = f->d_tile_off;
     a.n_machines = f->n_machines; a.tiles_total = f->tiles_total;

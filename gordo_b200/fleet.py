@@ -275,6 +275,7 @@ class FFFleet:
         tu = buf("tag-anomaly-unscaled", (R, To)); tts = buf("total-anomaly-scaled", (R,))
         ttu = buf("total-anomaly-unscaled", (R,)); cf = buf("anomaly-confidence", (R, To))
         tcf = buf("total-anomaly-confidence", (R,))
+        act = buf("activity-l1", (R,)) if precision == "f32" else None
         if precision == "bf16":
             prec, packed = N.PREC_BF16_TC, self.packed()
         elif precision == "f32":
@@ -285,7 +286,7 @@ class FFFleet:
             sched.handle, C.byref(self.topo.arch), prec, N.ptr(self.params), N.ptr(packed),
             N.ptr(self.in_scale), N.ptr(self.in_min), N.ptr(self.err_scale),
             N.ptr(self.feat_thr), N.ptr(self.agg_thr), N.ptr(x), N.ptr(y),
-            N.ptr(mo), N.ptr(ts), N.ptr(tu), N.ptr(tts), N.ptr(ttu), N.ptr(cf), N.ptr(tcf),
+            N.ptr(mo), N.ptr(ts), N.ptr(tu), N.ptr(tts), N.ptr(ttu), N.ptr(cf), N.ptr(tcf), N.ptr(act),
             _stream_ptr()), "gb200_ff_score")
         return res
 

@@ -66,6 +66,71 @@ class History:
         self.epoch = epoch or []
 
 
+class EarlyStopping:
+    """
+    [3P] keras.callbacks.EarlyStopping (Keras 3.3.3 semantics) for the per-epoch loop of ``fit``:
+    monitor / min_delta / patience / mode / baseline / restore_best_weights / start_from_epoch.
+    The best weights are restored at the end of training whenever ``restore_best_weights`` is set.
+    """
+
+    def __init__(self, monitor="val_loss", min_delta=0, patience=0, verbose=0, mode="auto", baseline=None,
+                 restore_best_weights=False, start_from_epoch=0):
+        self.monitor, self.min_delta, self.patience = monitor, abs(float(min_delta)), int(patience)
+        self.baseline, self.restore_best_weights, self.start_from_epoch = baseline, bool(restore_best_weights), int(start_from_epoch)
+        if mode not in ("auto", "min", "max"):
+            mode = "auto"
+        if mode == "auto":
+            mode = "max" if (monitor.endswith("acc") or monitor.endswith("accuracy") or monitor.endswith("auc")) else "min"
+        self.mode = mode
+        self.wait, self.stopped_epoch, self.best_epoch, self.best_weights = 0, 0, 0, None
+        self.best = np.inf if mode == "min" else -np.inf
+
+    def _is_improvement(self, value, reference):
+        return value < reference - self.min_delta if self.mode == "min" else value > reference + self.min_delta
+
+    def on_epoch_end(self, epoch, logs, get_weights) -> bool:
+        """Returns True when training must stop."""
+        current = logs.get(self.monitor)
+        if current is None or epoch < self.start_from_epoch:
+            return False
+        if self.restore_best_weights and self.best_weights is None:
+            self.best_weights, self.best_epoch = get_weights(), epoch
+        self.wait += 1
+        if self._is_improvement(current, self.best):
+            self.best, self.best_epoch = current, epoch
+            if self.restore_best_weights:
+                self.best_weights = get_weights()
+            if self.baseline is None or self._is_improvement(current, self.baseline):
+                self.wait = 0
+            return False
+        if self.wait >= self.patience and epoch > 0:
+            self.stopped_epoch = epoch
+            return True
+        return False
+
+
+def build_callbacks(definitions):
+    """
+    Callback definitions of a Machine YAML (gordo/serializer/from_definition.py:352-373) -> callback
+    objects.  Supported: ``tensorflow.keras.callbacks.EarlyStopping`` (any ``...EarlyStopping`` path) or an
+    object exposing the same attributes; anything else fails loudly.
+    """
+    out = []
+    for cb in definitions or []:
+        if isinstance(cb, EarlyStopping):
+            out.append(cb)
+        elif isinstance(cb, dict) and len(cb) == 1 and str(next(iter(cb))).endswith("EarlyStopping"):
+            out.append(EarlyStopping(**(next(iter(cb.values())) or {})))
+        elif isinstance(cb, str) and cb.endswith("EarlyStopping"):
+            out.append(EarlyStopping())
+        elif type(cb).__name__ == "EarlyStopping":
+            out.append(EarlyStopping(**{k: getattr(cb, k) for k in ("monitor", "min_delta", "patience", "mode", "baseline",
+                                                                    "restore_best_weights", "start_from_epoch") if hasattr(cb, k)}))
+        else:
+            raise NotImplementedError(f"Keras callback {cb!r} is not supported by gordo_b200 (EarlyStopping only)")
+    return out
+
+
 class KerasBaseEstimator(BaseEstimator, GordoBase):
     supported_fit_args = ["batch_size", "epochs", "verbose", "callbacks", "validation_split", "shuffle",
                           "class_weight", "initial_epoch", "steps_per_epoch", "validation_batch_size",
@@ -216,8 +281,7 @@ class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
         self.kwargs.update({"n_features": self.get_n_features(X), "n_features_out": self.get_n_features_out(y)})
         same = y is X
         X = np.asarray(_values(X)); y = X if same else np.asarray(_values(y))
-        if self._fit_arg("callbacks", None, kwargs):
-            raise NotImplementedError("Keras callbacks (EarlyStopping ...) are not implemented in gordo_b200 yet")
+        callbacks = build_callbacks(self._fit_arg("callbacks", None, kwargs))
         epochs = int(self._fit_arg("epochs", 1, kwargs))
         batch_size = int(self._fit_arg("batch_size", None, kwargs) or 32)
         shuffle = bool(self._fit_arg("shuffle", True, kwargs))
@@ -246,9 +310,11 @@ class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
         hist = {"loss": [], "accuracy": []}
         if vsplit:
             hist["val_loss"] = []
-        # with a validation split Keras evaluates after every epoch, so train one epoch per launch
-        for e0 in range(0, epochs, 1 if vsplit else epochs):
-            ne = 1 if vsplit else epochs
+        # Keras evaluates the validation split and runs callbacks after every epoch: one epoch per launch then
+        per_epoch = bool(vsplit) or bool(callbacks)
+        epochs_run = 0
+        for e0 in range(0, epochs, 1 if per_epoch else epochs):
+            ne = 1 if per_epoch else epochs
             pool = poff = None
             if shuffle and n_train > 0:
                 pool = torch.stack([torch.randperm(n_train, generator=gen, device=dev) for _ in range(ne)]
@@ -258,17 +324,37 @@ class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
                                            perm_pool=pool, perm_off=poff, l1_mean=l1_mean, adam_mv=mv, adam_t=t)
             hist["loss"] += [float(v) for v in hl[0].cpu()]
             hist["accuracy"] += [float(v) for v in ha[0].cpu()]
+            epochs_run += ne
             if vsplit and n > n_train:
+                # val_loss = MSE + activity-regulariser loss, batch-size weighted like Keras' evaluate()
                 from gordo_b200.fleet import Schedule
                 fleet.set_params(params)
                 vs = Schedule(rows_lo=[n_train], rows_hi=[n], rows_total=n)
-                vp = fleet.score(vs, xd, yd, precision="f32", columns=("total-anomaly-unscaled",))
-                hist["val_loss"].append(float(vp["total-anomaly-unscaled"][n_train:n].mean()))
+                vp = fleet.score(vs, xd, yd, precision="f32", columns=("total-anomaly-unscaled", "activity-l1"))
+                mse = float(vp["total-anomaly-unscaled"][n_train:n].mean())
+                act = vp["activity-l1"][n_train:n].double()
+                nv = n - n_train
+                if l1_mean:
+                    reg = float(act.mean())
+                else:           # per batch the activity loss is SUMMED over its rows: weight by the batch sizes
+                    sizes = torch.full((-(-nv // batch_size),), batch_size, dtype=torch.float64, device=dev)
+                    sizes[-1] = nv - batch_size * (len(sizes) - 1)
+                    per_batch = torch.zeros_like(sizes).index_add_(0, torch.arange(nv, device=dev) // batch_size, act)
+                    reg = float((per_batch * sizes).sum() / nv)
+                hist["val_loss"].append(mse + reg)
+            if callbacks:
+                logs = {k: v[-1] for k, v in hist.items() if v}
+                get_w = lambda: (params.clone(), mv.clone(), t.clone())
+                if any(cb.on_epoch_end(epochs_run - 1, logs, get_w) for cb in callbacks):
+                    break
+        for cb in callbacks:
+            if cb.restore_best_weights and cb.best_weights is not None:
+                params = cb.best_weights[0].clone()
         self.model.params = params[0].cpu().numpy()
         self.model.adam_mv = mv[0].cpu().numpy()
         self.model.adam_t = int(t[0])
         steps = -(-n_train // batch_size)
-        self._history = History(hist, {"verbose": 0, "epochs": epochs, "steps": steps}, list(range(epochs)))
+        self._history = History(hist, {"verbose": 0, "epochs": epochs, "steps": steps}, list(range(epochs_run)))
         return self
 
     def predict(self, X, **kwargs) -> np.ndarray:

@@ -99,6 +99,8 @@ void gb200_fleet_destroy(gb200_fleet* f);
  * packed_bf16  : [M, gb200_ff_packed_bytes()] from gb200_ff_pack_bf16 (GB200_PREC_BF16_TC), else NULL
  * in_scale/in_min : [M, T_in] fp32 (NULL = identity); err_scale : [M, T_out] fp32 (NULL = 1)
  * feat_thr : [M, T_out] or NULL; agg_thr : [M] or NULL
+ * activity_l1 : optional [rows] (GB200_PREC_F32 only): sum_l l1[l]*sum_j|h_l[j]| per row -- the activity-
+ *   regulariser part of the Keras loss (feedforward_autoencoder.py:78-81), needed for val_loss
  */
 int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
                    const float* params, const void* packed_bf16,
@@ -107,7 +109,7 @@ int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
                    const float* x, const float* y,
                    float* model_out, float* tag_scaled, float* tag_unscaled,
                    float* total_scaled, float* total_unscaled,
-                   float* conf, float* total_conf, void* stream);
+                   float* conf, float* total_conf, float* activity_l1, void* stream);
 
 /* bytes per Machine of the tensor-core operand image (bf16 weights in the tcgen05 canonical
  * K-major shared-memory layout + fp32 biases); 0 if the topology is not eligible (a width > 256) */

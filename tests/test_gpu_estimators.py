@@ -236,3 +236,38 @@ def test_fleet_builder_cv_scores_match_sklearn_scorers():
     m = scores["mean-squared-error"]
     np.testing.assert_allclose(m["fold-mean"], np.mean([m["fold-1"], m["fold-2"], m["fold-3"]]))
     assert meta["cross_validation"]["splits"] == {"fold-1-n-train": 100, "fold-2-n-train": 200, "fold-3-n-train": 300}
+
+
+def test_validation_split_val_loss_and_early_stopping():
+    """val_loss (MSE + activity loss, batch-weighted) vs the oracle; Keras-3 EarlyStopping semantics."""
+    from gordo_b200.machine.model.models import KerasAutoEncoder, _Model, EarlyStopping
+    X = _data(9, 500, 6); Xs = OMinMax().fit(X).transform(X).astype(np.float32)
+    spec = factories.feedforward_hourglass(6)
+    init = dense.ff_flatten(dense.ff_init(spec, np.random.default_rng(2)))
+    est = KerasAutoEncoder(kind="feedforward_hourglass", epochs=3, shuffle=False, validation_split=0.2)
+    est.kwargs.update(n_features=6, n_features_out=6)
+    est.model = _Model(est._topology(), init.copy())
+    est.fit(Xs, Xs)
+    p = dense.ff_unflatten(init, spec["widths"])
+    hist, _ = dense.ff_fit(spec, p, Xs, Xs, epochs=3, batch_size=32, perms=None, validation_split=0.2)
+    h = est.get_metadata()["history"]
+    np.testing.assert_allclose(h["loss"], hist["loss"], rtol=3e-4)
+    np.testing.assert_allclose(h["val_loss"], hist["val_loss"], rtol=3e-4)
+    # EarlyStopping from a Machine-YAML style definition: a huge min_delta means "never an improvement"
+    # after the first epoch -> stop at epoch index `patience`, restore the first epoch's weights
+    cb = [{"tensorflow.keras.callbacks.EarlyStopping": {"monitor": "val_loss", "patience": 2, "min_delta": 10.0,
+                                                        "restore_best_weights": True}}]
+    es = KerasAutoEncoder(kind="feedforward_hourglass", epochs=50, shuffle=False, validation_split=0.2, callbacks=cb)
+    es.kwargs.update(n_features=6, n_features_out=6)
+    es.model = _Model(es._topology(), init.copy())
+    es.fit(Xs, Xs)
+    he = es.get_metadata()["history"]
+    assert len(he["loss"]) == 3 and len(he["val_loss"]) == 3          # epochs 0,1,2 then wait(2) >= patience
+    one = KerasAutoEncoder(kind="feedforward_hourglass", epochs=1, shuffle=False, validation_split=0.2)
+    one.kwargs.update(n_features=6, n_features_out=6)
+    one.model = _Model(one._topology(), init.copy())
+    one.fit(Xs, Xs)
+    np.testing.assert_allclose(es.model.params, one.model.params, atol=1e-7)     # best = epoch 0 restored
+    assert isinstance(EarlyStopping(monitor="val_accuracy").mode, str) and EarlyStopping(monitor="val_accuracy").mode == "max"
+    with pytest.raises(NotImplementedError):
+        KerasAutoEncoder(kind="feedforward_hourglass", callbacks=["keras.callbacks.TensorBoard"]).fit(Xs, Xs)
