@@ -1,7 +1,6 @@
 // lstm_tc: the stacked-LSTM forward (KerasLSTMBaseEstimator.predict, models.py:618-660) on tcgen05.
 //
-// One launch = one (layer, timestep) for a chunk of S windows (time-step-synchronous over the
-// stack, like lstm.cu).  Everything a tile needs is kept IN HBM IN THE UMMA CANONICAL LAYOUT, so
+// Everything a tile needs is kept IN HBM IN THE UMMA CANONICAL LAYOUT, so
 // every operand is a plain 1-D bulk async copy (no tensor maps, no repacking on the way in):
 //   * Xc   : bf16(x*scale+min) of the chunk's rows, K-chunk-major [Kx/8][rows][8]: the 128
 //            consecutive rows of a window tile at time t are one contiguous 2 KB run per K chunk
@@ -9,14 +8,16 @@
 //   * h_l  : bf16 hidden state, per 128-window tile [Kh/8][128][8] (ping-pong over t);
 //   * W|U  : per 16-unit block the B operand [K/8][8][8][8] with columns ordered unit*4+gate, so
 //            a 16-column tcgen05.ld delivers the i,f,c,o pre-activations of 4 units;
-//   * c_l  : fp32 cell state, unit-major [units][S] (coalesced over windows).
-// CTA = one 128-window tile (TMEM lane = window): loader warp + MMA warp + 4 gate-epilogue
-// warpgroups over a 2-stage weight ring and 4 accumulator stages (see lstm_step_tc_kernel).
+//   * c_l  : fp32 cell state, [tile][unit][128 windows] (coalesced, constant strides inside a tile).
+// One PERSISTENT CTA per 128-window tile walks all L x n_layers (timestep, layer) steps itself
+// (window tiles are independent sequences: no grid sync, no per-step launch) with two loader
+// warps, an MMA warp and 4 gate-epilogue warpgroups (see lstm_persist_tc_kernel).
 // (A cluster-multicast variant of the weight loads was measured slower -- 971k / 824k / 731k
 // windows/s at cluster size 1 / 2 / 4 on the c4 shape -- and dropped.)
 // bf16 operands / fp32 accumulate / fp32 cell state; gates via tanh.approx (sigmoid = .5*tanh(.5z)+.5).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 using namespace gbptx;
 
@@ -51,7 +52,7 @@ TcPlan make_tc_plan(const gb200_lstm_arch* a) {
     p.n_layers = a->n_layers; p.T_in = a->n_features; p.T_out = a->n_features_out;
     p.L = a->lookback_window; p.lookahead = a->lookahead; p.out_act = a->out_act;
     int64_t off = 0; int in = a->n_features;
-    size_t wp = 0, bf = 0, smem = 0;
+    size_t wp = 0, bf = 0, smem = 0, max_a = 0, max_s = 0;
     for (int l = 0; l < a->n_layers; ++l) {
         TcLayer& y = p.ly[l];
         y.in = in; y.u = a->units[l]; y.act = a->acts[l];
@@ -63,8 +64,10 @@ TcPlan make_tc_plan(const gb200_lstm_arch* a) {
         y.b_off = off; off += 4 * y.u;
         y.wp_off = wp; wp += (size_t)y.n_blocks * (y.Kx + y.Kh) * NB_COLS * 2;
         y.bias_off = bf; bf += (size_t)y.n_blocks * NB_COLS;
-        const size_t s = (size_t)TILE * (y.Kx + y.Kh) * 2 + (size_t)B_STAGES_HOST * (y.Kx > y.Kh ? y.Kx : y.Kh) * NB_COLS * 2;
-        if (s > smem) smem = s;
+        const size_t ab = (size_t)TILE * (y.Kx + y.Kh) * 2, sb = (size_t)(y.Kx > y.Kh ? y.Kx : y.Kh) * NB_COLS * 2;
+        if (ab > max_a) max_a = ab;
+        if (sb > max_s) max_s = sb;
+        smem = max_a + (size_t)B_STAGES_HOST * max_s;
         in = y.u;
     }
     p.dense_w_off = off; off += (int64_t)in * a->n_features_out;
@@ -105,11 +108,12 @@ __global__ void lstm_pack_w_kernel(TcLayer y, const float* __restrict__ P, uint8
             if (k < y.Kx) { if (k < y.in) w = P[y.w_off + (int64_t)k * 4 * y.u + gate * y.u + unit]; }
             else { const int kh = k - y.Kx; if (kh < y.u) w = P[y.u_off + (int64_t)kh * 4 * y.u + gate * y.u + unit]; }
         }
+        if (gate != 2) w *= 0.5f;              // sigmoid(z) = 0.5*tanh(0.5 z) + 0.5: the inner 0.5 lives in the weights
         B[(k >> 3) * (8 * 64) + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
     }
     for (int n = threadIdx.x; n < NB_COLS; n += blockDim.x) {
         const int unit = b * UB + (n >> 2), gate = n & 3;
-        bias[y.bias_off + (size_t)b * NB_COLS + n] = unit < y.u ? P[y.b_off + gate * y.u + unit] : 0.0f;
+        bias[y.bias_off + (size_t)b * NB_COLS + n] = unit < y.u ? P[y.b_off + gate * y.u + unit] * (gate != 2 ? 0.5f : 1.0f) : 0.0f;
     }
 }
 
@@ -149,61 +153,94 @@ __device__ __forceinline__ float act_fast(float z) {
     if (ACT == GB200_ACT_SOFTPLUS) return z > 15.0f ? z : __logf(1.0f + __expf(z));
     return z;
 }
-__device__ __forceinline__ float sigmoid_fast(float z) {
-    float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(0.5f * z));
+// z_half = 0.5 * z (the 0.5 is folded into the packed weights / bias of the i, f, o gates)
+__device__ __forceinline__ float sigmoid_from_half(float z_half) {
+    float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z_half));
     return fmaf(0.5f, r, 0.5f);
 }
 
-struct StepTc {
-    int Kx, Kh, n_blocks, t, layer, S, tiles;
-    int64_t xc_rows;                       // rows of Xc (layer 0)
-    const uint8_t* x_src;                  // layer 0: Xc; else h_{l-1} (current t) tiles
-    const uint8_t* h_prev;                 // this layer's h at t-1 (tiles)
-    uint8_t* h_out;                        // this layer's h at t
-    float* c;                              // [n_blocks*UB][S]
-    const uint8_t* wp; const float* bias;  // this layer's packed blocks / biases
+struct PLayer {
+    int Kx, Kh, n_blocks, act;
+    uint32_t wp_off, bias_off;             // byte / float offsets of this layer's packed blocks / biases
+    uint64_t h_off[2], c_off;              // byte offsets (from `base`) of the two h buffers and the cell state
+};
+struct PersistTc {
+    int n_layers, L, tiles, dbg;
+    int64_t xc_rows;                       // rows of Xc
+    const uint8_t* xc;                     // bf16 scaled samples, K-chunk-major
+    uint8_t* base;                         // state scratch
+    const uint8_t* wp; const float* bias;
+    uint32_t stage_bytes;                  // weight-ring entry size (max over layers)
+    uint32_t a_bytes;                      // A operand region (max over layers)
+    PLayer ly[GB200_MAX_LAYERS];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 constexpr int EPI_WG = 4;          // epilogue warpgroups = TMEM accumulator stages
-constexpr int B_STAGES = 4;        // weight ring in shared memory; one entry = the x rows OR the h rows of a block
-constexpr int STEP_THREADS = EPI_WG * WG + 64;
+constexpr int B_STAGES = 4;        // weight ring; one entry = the x rows OR the h rows of a 16-unit block
+constexpr int PERSIST_THREADS = EPI_WG * WG + 96;
 
-// Warp-specialised pipeline, one CTA per 128-window tile:
-//   loader warp  : A operand once ([x_t | h_{t-1}], bulk copies), then the layer's weight blocks
-//                  through a 2-stage ring (b_full / b_empty);
-//   MMA warp     : per block K/16 tcgen05.mma into accumulator stage b%4, then two commits: one
-//                  frees the weight stage, one publishes the accumulator (t_full);
-//   4 epilogue warpgroups (TMEM lane = window): gates, cell update, h -> HBM in the A-operand
-//                  layout of the next launch; block b belongs to warpgroup b%4 (t_empty hands the
-//                  accumulator stage back).
-// Tensor pipe, weight streaming and the MUFU-heavy gate math of 4 different blocks overlap.
+// gates + cell update + h for one 16-unit block of one step (thread = window = TMEM lane)
 template <int ACT>
-__global__ void __launch_bounds__(STEP_THREADS, 1)
-lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
+__device__ __forceinline__ void gate_block(uint32_t tmem_lane, const float* __restrict__ bias, float* __restrict__ cblk,
+                                           uint8_t* __restrict__ hdst, bool has_h) {
+    #pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float cprev[8];
+        #pragma unroll
+        for (int u8 = 0; u8 < 8; ++u8) cprev[u8] = has_h ? __ldcg(cblk + (half * 8 + u8) * TILE) : 0.0f;
+        float hreg[8];
+        #pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+            float v[16];
+            tmem_ld16(tmem_lane + (half * 2 + c2) * 16, v);
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int u8 = c2 * 4 + q, ul = half * 8 + u8;
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ul * 4));
+                const float ig = sigmoid_from_half(v[q * 4 + 0] + bb.x), fg = sigmoid_from_half(v[q * 4 + 1] + bb.y);
+                const float gg = act_fast<ACT>(v[q * 4 + 2] + bb.z), og = sigmoid_from_half(v[q * 4 + 3] + bb.w);
+                const float cn = fmaf(fg, cprev[u8], ig * gg);
+                __stcg(cblk + ul * TILE, cn);
+                hreg[u8] = og * act_fast<ACT>(cn);
+            }
+        }
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(hreg[0], hreg[1]), t1 = __floats2bfloat162_rn(hreg[2], hreg[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(hreg[4], hreg[5]), t3 = __floats2bfloat162_rn(hreg[6], hreg[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(hdst + (size_t)half * 2048) = pk;
+    }
+}
+
+// PERSISTENT kernel: one CTA owns one 128-window tile for ALL L x n_layers (timestep, layer) steps.
+// Window tiles are independent sequences, so there is no grid-wide synchronisation and no
+// per-step launch: the CTA walks the steps itself, its h / c state round-trips through L2 only.
+//   loader A : per step the A operand [x_t | h_{t-1}] (bulk copies; waits for the producing step)
+//   loader B : the weight ring, free-running across steps (prefetches the next step's blocks)
+//   MMA warp : per block K/16 tcgen05.mma into accumulator stage g%4 (g = global block counter)
+//   4 epilogue warpgroups : gates / cell update / h -> HBM in next-step A-operand layout; at the
+//              end of a step each publishes its stores to the async proxy and arrives on step_done.
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t a_bar[2];                 // x part, h part of the A operand
+    __shared__ __align__(8) uint64_t a_full[2], a_empty, step_done;
     __shared__ __align__(8) uint64_t b_full[B_STAGES], b_empty[B_STAGES];
     __shared__ __align__(8) uint64_t t_full[EPI_WG], t_empty[EPI_WG];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, wg = tid / WG, wtid = tid - wg * WG, warp = wtid >> 5;
     const int tile = blockIdx.x;
-    const int K = a.Kx + a.Kh;
-    const bool has_h = a.t > 0;
-    const uint32_t blk_bytes = (uint32_t)K * NB_COLS * 2;
-    const uint32_t stage_bytes = (uint32_t)(a.Kx > a.Kh ? a.Kx : a.Kh) * NB_COLS * 2;
     uint8_t* A = smem;                                           // [K/8][128][16 B]
-    uint8_t* Bbase = smem + (size_t)TILE * K * 2;
-    // unit blocks are independent, so each tile walks them from a different start: at any moment the
-    // CTAs of a launch stream DIFFERENT weight blocks instead of hammering the same L2 lines
-    const int rot = tile % a.n_blocks;
+    uint8_t* Bbase = smem + a.a_bytes;
 
     if (tid == 0) {
-        mbar_init(&a_bar[0], 1); mbar_init(&a_bar[1], 1);
+        mbar_init(&a_full[0], 1); mbar_init(&a_full[1], 1); mbar_init(&a_empty, 1); mbar_init(&step_done, EPI_WG);
         for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < EPI_WG; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -215,108 +252,133 @@ lstm_step_tc_kernel(const __grid_constant__ StepTc a) {
 
     if (wg == EPI_WG) {
         if (wtid == 0) {
-            // ===================== loader =====================
-            const uint32_t xb = (uint32_t)a.Kx * 256;
-            mbar_expect_tx(&a_bar[0], xb);
-            if (a.layer == 0) {
-                for (int c = 0; c < a.Kx / 8; ++c)
-                    bulk_g2s(A + c * 2048, a.x_src + ((size_t)c * a.xc_rows + (size_t)tile * TILE + a.t) * 16, 2048, &a_bar[0]);
-            } else {
-                bulk_g2s(A, a.x_src + (size_t)tile * xb, xb, &a_bar[0]);
-            }
-            if (has_h) {
-                const uint32_t hb = (uint32_t)a.Kh * 256;
-                mbar_expect_tx(&a_bar[1], hb);
-                bulk_g2s(A + xb, a.h_prev + (size_t)tile * hb, hb, &a_bar[1]);
-            }
-            // ring entries: (block, x rows) then (block, h rows): 4 smaller copies in flight hide the
-            // L2 latency that a 2-deep ring of whole blocks exposed
-            const int parts = has_h ? 2 : 1;
-            int it = 0;
-            for (int b = 0; b < a.n_blocks; ++b) {
-                const int blk = (b + rot) % a.n_blocks;
-                for (int part = 0; part < parts; ++part, ++it) {
-                    const int s = it % B_STAGES;
-                    if (it >= B_STAGES) mbar_wait(&b_empty[s], ((it / B_STAGES) - 1) & 1);
-                    const uint32_t bytes = (uint32_t)(part == 0 ? a.Kx : a.Kh) * NB_COLS * 2;
-                    mbar_expect_tx(&b_full[s], bytes);
-                    bulk_g2s(Bbase + (size_t)s * stage_bytes, a.wp + (size_t)blk * blk_bytes + (part ? (size_t)a.Kx * NB_COLS * 2 : 0),
-                             bytes, &b_full[s]);
+            // ===================== loader A: the per-step A operand =====================
+            int s = 0, hs = 0;
+            for (int t = 0; t < a.L; ++t) {
+                for (int l = 0; l < a.n_layers; ++l, ++s) {
+                    const PLayer& y = a.ly[l];
+                    const uint32_t xb = (uint32_t)y.Kx * 256, hb = (uint32_t)y.Kh * 256;
+                    if (s > 0) mbar_wait(&a_empty, (s - 1) & 1);           // previous step's MMAs have read A
+                    if (t > 0) {                                           // h_{l,t-1}: produced n_layers steps ago
+                        mbar_expect_tx(&a_full[1], hb);
+                        bulk_g2s(A + xb, a.base + y.h_off[(t + 1) & 1] + (size_t)tile * hb, hb, &a_full[1]);
+                        ++hs;
+                    }
+                    if (s > 0) mbar_wait(&step_done, (s - 1) & 1);         // h_{l-1,t} of the previous step is in L2
+                    mbar_expect_tx(&a_full[0], xb);
+                    if (l == 0) {
+                        for (int c = 0; c < y.Kx / 8; ++c)
+                            bulk_g2s(A + c * 2048, a.xc + ((size_t)c * a.xc_rows + (size_t)tile * TILE + t) * 16, 2048, &a_full[0]);
+                    } else {
+                        bulk_g2s(A, a.base + a.ly[l - 1].h_off[t & 1] + (size_t)tile * xb, xb, &a_full[0]);
+                    }
                 }
             }
         } else if (wtid == 32) {
+            // ===================== loader B: free-running weight ring =====================
+            int it = 0;
+            for (int t = 0; t < a.L; ++t) {
+                const int parts = t > 0 ? 2 : 1;
+                for (int l = 0; l < a.n_layers; ++l) {
+                    const PLayer& y = a.ly[l];
+                    const uint32_t blk_bytes = (uint32_t)(y.Kx + y.Kh) * NB_COLS * 2;
+                    const int rot = tile % y.n_blocks;
+                    for (int b = 0; b < y.n_blocks; ++b) {
+                        const int blk = (b + rot) % y.n_blocks;
+                        for (int part = 0; part < parts; ++part, ++it) {
+                            const int st = it % B_STAGES;
+                            if (it >= B_STAGES) mbar_wait(&b_empty[st], ((it / B_STAGES) - 1) & 1);
+                            const uint32_t bytes = (a.dbg & 4) ? 128u : (uint32_t)(part == 0 ? y.Kx : y.Kh) * NB_COLS * 2;
+                            mbar_expect_tx(&b_full[st], bytes);
+                            bulk_g2s(Bbase + (size_t)st * a.stage_bytes,
+                                     a.wp + y.wp_off + (size_t)blk * blk_bytes + (part ? (size_t)y.Kx * NB_COLS * 2 : 0), bytes, &b_full[st]);
+                        }
+                    }
+                }
+            }
+        } else if (wtid == 64) {
             // ===================== MMA issuer =====================
-            mbar_wait(&a_bar[0], 0);
-            if (has_h) mbar_wait(&a_bar[1], 0);
             const uint32_t idesc = make_idesc(TILE, NB_COLS);
             const uint32_t a_addr = smem_u32(A);
-            const int parts = has_h ? 2 : 1;
-            int it = 0;
-            for (int b = 0; b < a.n_blocks; ++b) {
-                const int q = b % EPI_WG;
-                if (b >= EPI_WG) mbar_wait(&t_empty[q], ((b / EPI_WG) - 1) & 1);
-                const uint32_t d_tmem = s_tmem + (uint32_t)(q * NB_COLS);
-                for (int part = 0; part < parts; ++part, ++it) {
-                    const int s = it % B_STAGES;
-                    mbar_wait(&b_full[s], (it / B_STAGES) & 1);
-                    tc_fence_after();
-                    // descriptors advance by a constant in their start-address field: no per-step rebuild
-                    uint64_t da = make_desc(a_addr + (part ? (uint32_t)a.Kx * 256 : 0), 2048, 128);
-                    uint64_t db = make_desc(smem_u32(Bbase + (size_t)s * stage_bytes), 1024, 128);
-                    const int ksteps = (part ? a.Kh : a.Kx) / 16;
-                    umma_bf16(d_tmem, da, db, idesc, part ? 1u : 0u);
-                    #pragma unroll 4
-                    for (int ks = 1; ks < ksteps; ++ks) {
-                        da += (2 * 2048) >> 4; db += (2 * 1024) >> 4;
-                        umma_bf16(d_tmem, da, db, idesc, 1u);
+            int it = 0, g = 0, s = 0, hs = 0;
+            for (int t = 0; t < a.L; ++t) {
+                const int parts = t > 0 ? 2 : 1;
+                for (int l = 0; l < a.n_layers; ++l, ++s) {
+                    const PLayer& y = a.ly[l];
+                    mbar_wait(&a_full[0], s & 1);
+                    if (t > 0) { mbar_wait(&a_full[1], hs & 1); ++hs; }
+                    for (int b = 0; b < y.n_blocks; ++b, ++g) {
+                        const int q = g % EPI_WG;
+                        if (g >= EPI_WG) mbar_wait(&t_empty[q], ((g / EPI_WG) - 1) & 1);
+                        const uint32_t d_tmem = s_tmem + (uint32_t)(q * NB_COLS);
+                        for (int part = 0; part < parts; ++part, ++it) {
+                            const int st = it % B_STAGES;
+                            mbar_wait(&b_full[st], (it / B_STAGES) & 1);
+                            tc_fence_after();
+                            uint64_t da = make_desc(a_addr + (part ? (uint32_t)y.Kx * 256 : 0), 2048, 128);
+                            uint64_t db = make_desc(smem_u32(Bbase + (size_t)st * a.stage_bytes), 1024, 128);
+                            const int ksteps = (a.dbg & 2) ? 1 : (part ? y.Kh : y.Kx) / 16;
+                            umma_bf16(d_tmem, da, db, idesc, part ? 1u : 0u);
+                            #pragma unroll 4
+                            for (int ks = 1; ks < ksteps; ++ks) {
+                                da += (2 * 2048) >> 4; db += (2 * 1024) >> 4;
+                                umma_bf16(d_tmem, da, db, idesc, 1u);
+                            }
+                            umma_commit(&b_empty[st]);     // ring entry reusable once these MMAs retire
+                        }
+                        umma_commit(&t_full[q]);           // accumulator ready for warpgroup q
                     }
-                    umma_commit(&b_empty[s]);      // ring entry reusable once these MMAs retire
+                    umma_commit(&a_empty);                 // the A operand may be overwritten
                 }
-                umma_commit(&t_full[q]);           // accumulator ready for warpgroup q
             }
         }
     } else {
         // ===================== gate epilogue, warpgroup q = wg =====================
         const uint32_t tmem_lane = s_tmem + (uint32_t)(wg * NB_COLS) + ((uint32_t)(warp * 32) << 16);
-        const int w = tile * TILE + wtid;                 // window index inside the chunk
-        for (int j = wg; j < a.n_blocks; j += EPI_WG) {
-            const int b = (j + rot) % a.n_blocks;            // the unit block this pipeline slot carries
-            // cell state of this block's 16 units: independent coalesced loads issued BEFORE the wait
-            float cprev[UB];
-            #pragma unroll
-            for (int ul = 0; ul < UB; ++ul)
-                cprev[ul] = has_h ? __ldcg(a.c + (size_t)(b * UB + ul) * a.S + w) : 0.0f;
-            mbar_wait(&t_full[wg], (j / EPI_WG) & 1);
-            tc_fence_after();
-            const float* bias = a.bias + (size_t)b * NB_COLS;
-            float hreg[8];
-            #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                float v[16];
-                tmem_ld16(tmem_lane + c4 * 16, v);
-                #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int ul = c4 * 4 + q;
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + ul * 4));
-                    const float ig = sigmoid_fast(v[q * 4 + 0] + bb.x), fg = sigmoid_fast(v[q * 4 + 1] + bb.y);
-                    const float gg = act_fast<ACT>(v[q * 4 + 2] + bb.z), og = sigmoid_fast(v[q * 4 + 3] + bb.w);
-                    const float cn = fmaf(fg, cprev[ul], ig * gg);
-                    __stcg(a.c + (size_t)(b * UB + ul) * a.S + w, cn);
-                    hreg[(c4 & 1) * 4 + q] = og * act_fast<ACT>(cn);
+        int g0 = 0, es = 0;
+        for (int t = 0; t < a.L; ++t) {
+            for (int l = 0; l < a.n_layers; ++l) {
+                const PLayer& y = a.ly[l];
+                const int rot = tile % y.n_blocks;
+                float* ctile = reinterpret_cast<float*>(a.base + y.c_off) + (size_t)tile * y.n_blocks * UB * TILE + wtid;
+                uint8_t* htile = a.base + y.h_off[t & 1] + (size_t)tile * y.Kh * 256 + wtid * 16;
+                const float* lbias = a.bias + y.bias_off;
+                for (int j = 0; j < y.n_blocks; ++j) {
+                    const int g = g0 + j;
+                    if (g % EPI_WG != wg) continue;
+                    const int b = (j + rot) % y.n_blocks;
+                    // only warp 0 polls the accumulator barrier; the other three park on a hardware barrier
+                    if (warp == 0) mbar_wait(&t_full[wg], (g / EPI_WG) & 1);
+                    named_bar_sync(1 + wg, WG);
+                    tc_fence_after();
+                    if (!(a.dbg & 1)) {
+                        const float* bias = lbias + (size_t)b * NB_COLS;
+                        float* cblk = ctile + b * UB * TILE;
+                        uint8_t* hdst = htile + (size_t)(b * 2) * 2048;
+                        switch (y.act) {
+                            case GB200_ACT_TANH:     gate_block<GB200_ACT_TANH>(tmem_lane, bias, cblk, hdst, t > 0); break;
+                            case GB200_ACT_RELU:     gate_block<GB200_ACT_RELU>(tmem_lane, bias, cblk, hdst, t > 0); break;
+                            case GB200_ACT_SIGMOID:  gate_block<GB200_ACT_SIGMOID>(tmem_lane, bias, cblk, hdst, t > 0); break;
+                            case GB200_ACT_ELU:      gate_block<GB200_ACT_ELU>(tmem_lane, bias, cblk, hdst, t > 0); break;
+                            case GB200_ACT_SOFTPLUS: gate_block<GB200_ACT_SOFTPLUS>(tmem_lane, bias, cblk, hdst, t > 0); break;
+                            default:                 gate_block<GB200_ACT_LINEAR>(tmem_lane, bias, cblk, hdst, t > 0); break;
+                        }
+                    }
+                    tc_fence_before();
+                    named_bar_sync(1 + wg, WG);          // every lane has drained its TMEM reads
+                    if (wtid == 0) mbar_arrive(&t_empty[wg]);
                 }
-                if (c4 & 1) {
-                    uint4 pk;
-                    __nv_bfloat162 t0 = __floats2bfloat162_rn(hreg[0], hreg[1]), t1 = __floats2bfloat162_rn(hreg[2], hreg[3]);
-                    __nv_bfloat162 t2 = __floats2bfloat162_rn(hreg[4], hreg[5]), t3 = __floats2bfloat162_rn(hreg[6], hreg[7]);
-                    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                    const int chunk = b * 2 + (c4 >> 1);
-                    *reinterpret_cast<uint4*>(a.h_out + (size_t)tile * a.Kh * 256 + (size_t)chunk * 2048 + wtid * 16) = pk;
-                }
+                g0 += y.n_blocks;
+                // publish this step's h stores to the async proxy (the next step's bulk copies read them)
+                fence_proxy_async_all();
+                named_bar_sync(1 + wg, WG);
+                if (wtid == 0) mbar_arrive(&step_done);
+                // a warpgroup without a block in this step must not run ahead and arrive for a later step
+                // while a busy warpgroup is still inside this one: everybody waits for the step to close
+                if (warp == 0) mbar_wait(&step_done, es & 1);
+                named_bar_sync(1 + wg, WG);
+                ++es;
             }
-            tc_fence_before();
-            named_bar_sync(1 + wg, WG);          // every lane has drained its TMEM reads
-            if (wtid == 0) mbar_arrive(&t_empty[wg]);
         }
     }
     tc_fence_before();
@@ -337,16 +399,6 @@ __global__ void lstm_dense_tc_kernel(const uint8_t* __restrict__ h, int Kh, int 
             acc = fmaf(__bfloat162float(tile[(k >> 3) * 1024 + r * 8 + (k & 7)]), Wd[(size_t)k * T_out + n], acc);
         out[(size_t)s * T_out + n] = gb_act(act, acc);
     }
-}
-
-template <int ACT>
-void launch_step(const StepTc& a, int tiles, size_t smem, cudaStream_t stream) {
-    static size_t configured = 0;                 // per instantiation
-    if (smem > configured) {
-        cudaFuncSetAttribute(lstm_step_tc_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
-    lstm_step_tc_kernel<ACT><<<tiles, STEP_THREADS, smem, stream>>>(a);
 }
 
 }  // namespace
@@ -378,6 +430,8 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
         while ((int64_t)tc_state_bytes(q, S + TILE, false) <= scratch_bytes && S + TILE <= (1 << 20)) S += TILE;
     }
     tc_state_bytes(p, S, true);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GB200_LSTM_DBG"); dbg = e ? atoi(e) : 0; }
     uint8_t* base = (uint8_t*)scratch;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~(size_t)255; return r; };
@@ -409,27 +463,29 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
             const int64_t row0 = f->h_row_lo[m] + k0;
             const int64_t rows_avail = f->h_row_hi[m] - row0;
             lstm_pack_x_kernel<<<148 * 4, 256, 0, stream>>>(x, row0, rows_avail, rows_chunk, p.T_in, p.ly[0].Kx, sc, mn, xc);
-            for (int t = 0; t < p.L; ++t) {
+            {
+                PersistTc a{};
+                a.n_layers = p.n_layers; a.L = p.L; a.tiles = tiles; a.dbg = dbg; a.xc_rows = rows_chunk;
+                a.xc = (const uint8_t*)xc; a.base = base; a.wp = wp; a.bias = bias;
+                uint32_t stage = 0, abytes = 0;
                 for (int l = 0; l < p.n_layers; ++l) {
                     const TcLayer& y = p.ly[l];
-                    StepTc a{};
-                    a.Kx = y.Kx; a.Kh = y.Kh; a.n_blocks = y.n_blocks; a.t = t; a.layer = l; a.S = (int)S; a.tiles = tiles;
-                    a.xc_rows = rows_chunk;
-                    a.x_src = l == 0 ? (const uint8_t*)xc : base + p.ly[l - 1].h_off[t & 1];
-                    a.h_prev = base + y.h_off[(t + 1) & 1];
-                    a.h_out = base + y.h_off[t & 1];
-                    a.c = (float*)(base + y.c_off);
-                    a.wp = wp + y.wp_off; a.bias = bias + y.bias_off;
-                    const size_t smem = (size_t)TILE * (y.Kx + y.Kh) * 2 + (size_t)B_STAGES_HOST * (y.Kx > y.Kh ? y.Kx : y.Kh) * NB_COLS * 2;
-                    switch (y.act) {
-                        case GB200_ACT_TANH: launch_step<GB200_ACT_TANH>(a, tiles, smem, stream); break;
-                        case GB200_ACT_RELU: launch_step<GB200_ACT_RELU>(a, tiles, smem, stream); break;
-                        case GB200_ACT_SIGMOID: launch_step<GB200_ACT_SIGMOID>(a, tiles, smem, stream); break;
-                        case GB200_ACT_ELU: launch_step<GB200_ACT_ELU>(a, tiles, smem, stream); break;
-                        case GB200_ACT_SOFTPLUS: launch_step<GB200_ACT_SOFTPLUS>(a, tiles, smem, stream); break;
-                        default: launch_step<GB200_ACT_LINEAR>(a, tiles, smem, stream); break;
-                    }
+                    a.ly[l].Kx = y.Kx; a.ly[l].Kh = y.Kh; a.ly[l].n_blocks = y.n_blocks; a.ly[l].act = y.act;
+                    a.ly[l].wp_off = (uint32_t)y.wp_off; a.ly[l].bias_off = (uint32_t)y.bias_off;
+                    a.ly[l].h_off[0] = y.h_off[0]; a.ly[l].h_off[1] = y.h_off[1]; a.ly[l].c_off = y.c_off;
+                    const uint32_t sb = (uint32_t)(y.Kx > y.Kh ? y.Kx : y.Kh) * NB_COLS * 2;
+                    if (sb > stage) stage = sb;
+                    const uint32_t ab = (uint32_t)TILE * (y.Kx + y.Kh) * 2;
+                    if (ab > abytes) abytes = ab;
                 }
+                a.stage_bytes = stage; a.a_bytes = abytes;
+                const size_t smem = (size_t)abytes + (size_t)B_STAGES_HOST * stage;
+                static size_t configured = 0;
+                if (smem > configured) {
+                    GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_persist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    configured = smem;
+                }
+                lstm_persist_tc_kernel<<<tiles, PERSIST_THREADS, smem, stream>>>(a);
             }
             const TcLayer& yl = p.ly[p.n_layers - 1];
             int blocks = (nb * p.T_out + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;

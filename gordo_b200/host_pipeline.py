@@ -16,14 +16,15 @@ from .fleet import FFFleet, Schedule, SCORE_COLUMNS
 
 class HostPipeline:
     def __init__(self, fleet: FFFleet, sched: Schedule, n_chunks: int = 8, precision: str = "bf16",
-                 columns=SCORE_COLUMNS):
+                 columns=SCORE_COLUMNS, machines: int = None):
         if getattr(sched, "row_off", None) is None:
             raise ValueError("HostPipeline needs a contiguous Schedule (row counts)")
         self.fleet, self.sched, self.precision = fleet, sched, precision
         self.columns = [c for c in columns
                         if not (c == "anomaly-confidence" and fleet.feat_thr is None)
                         and not (c == "total-anomaly-confidence" and fleet.agg_thr is None)]
-        M = fleet.M
+        M = fleet.M if machines is None else max(1, min(int(machines), fleet.M))   # first M Machines only
+        self.machines = M
         n_chunks = max(1, min(n_chunks, M))
         bounds = np.linspace(0, M, n_chunks + 1).astype(int)
         self.chunks = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
@@ -36,7 +37,8 @@ class HostPipeline:
                                                                 "tag-anomaly-unscaled", "anomaly-confidence")
                                      else (max_rows,), dtype=torch.float32, device=dev)
                       for c in self.columns} for _ in range(2)]
-        R = sched.rows_total
+        R = int(sched.row_off[M])
+        self.rows = R
         self.host_out: Dict[str, torch.Tensor] = {
             c: torch.empty((R, To) if self.dout[0][c].dim() == 2 else (R,), dtype=torch.float32, pin_memory=True)
             for c in self.columns}
