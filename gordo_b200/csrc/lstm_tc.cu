@@ -221,7 +221,9 @@ __device__ __forceinline__ void gate_block(uint32_t tmem_lane, const float* __re
 // PERSISTENT kernel: one CTA owns one 128-window tile for ALL L x n_layers (timestep, layer) steps.
 // Window tiles are independent sequences, so there is no grid-wide synchronisation and no
 // per-step launch: the CTA walks the steps itself, its h / c state round-trips through L2 only.
-//   loader A : per step the A operand [x_t | h_{t-1}] (bulk copies; waits for the producing step)
+//   steps are walked along ANTI-DIAGONALS (l + t = d, l descending): the steps of a diagonal are mutually
+//   independent, so while one step's gates finish the next step's operands and MMAs proceed;
+//   loader A : per step the A operand [x_t | h_{t-1}] (bulk copies; waits for the two producing steps)
 //   loader B : the weight ring, free-running across steps (prefetches the next step's blocks)
 //   MMA warp : per block K/16 tcgen05.mma into accumulator stage g%4 (g = global block counter)
 //   4 epilogue warpgroups : gates / cell update / h -> HBM in next-step A-operand layout; at the
@@ -229,7 +231,9 @@ __device__ __forceinline__ void gate_block(uint32_t tmem_lane, const float* __re
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t a_full[2], a_empty, step_done;
+    __shared__ __align__(8) uint64_t a_full[2], a_empty;
+    // completion of step (l, t), published twice: done_t[l] is consumed by step (l, t+1), done_l[l] by step (l+1, t)
+    __shared__ __align__(8) uint64_t done_t[GB200_MAX_LAYERS], done_l[GB200_MAX_LAYERS];
     __shared__ __align__(8) uint64_t b_full[B_STAGES], b_empty[B_STAGES];
     __shared__ __align__(8) uint64_t t_full[EPI_WG], t_empty[EPI_WG];
     __shared__ uint32_t s_tmem;
@@ -240,7 +244,8 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
     uint8_t* Bbase = smem + a.a_bytes;
 
     if (tid == 0) {
-        mbar_init(&a_full[0], 1); mbar_init(&a_full[1], 1); mbar_init(&a_empty, 1); mbar_init(&step_done, EPI_WG);
+        mbar_init(&a_full[0], 1); mbar_init(&a_full[1], 1); mbar_init(&a_empty, 1);
+        for (int i = 0; i < a.n_layers; ++i) { mbar_init(&done_t[i], EPI_WG); mbar_init(&done_l[i], EPI_WG); }
         for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < EPI_WG; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,23 +258,25 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
     if (wg == EPI_WG) {
         if (wtid == 0) {
             // ===================== loader A: the per-step A operand =====================
-            int s = 0, hs = 0;
-            for (int t = 0; t < a.L; ++t) {
-                for (int l = 0; l < a.n_layers; ++l, ++s) {
+            int s = 0;
+            for (int d = 0; d < a.L + a.n_layers - 1; ++d) {
+                const int l_hi = min(a.n_layers - 1, d), l_lo = max(0, d - (a.L - 1));
+                for (int l = l_hi; l >= l_lo; --l, ++s) {
+                    const int t = d - l;
                     const PLayer& y = a.ly[l];
                     const uint32_t xb = (uint32_t)y.Kx * 256, hb = (uint32_t)y.Kh * 256;
                     if (s > 0) mbar_wait(&a_empty, (s - 1) & 1);           // previous step's MMAs have read A
-                    if (t > 0) {                                           // h_{l,t-1}: produced n_layers steps ago
+                    if (t > 0) {                                           // h_{l,t-1}
+                        mbar_wait(&done_t[l], (t - 1) & 1);
                         mbar_expect_tx(&a_full[1], hb);
                         bulk_g2s(A + xb, a.base + y.h_off[(t + 1) & 1] + (size_t)tile * hb, hb, &a_full[1]);
-                        ++hs;
                     }
-                    if (s > 0) mbar_wait(&step_done, (s - 1) & 1);         // h_{l-1,t} of the previous step is in L2
                     mbar_expect_tx(&a_full[0], xb);
                     if (l == 0) {
                         for (int c = 0; c < y.Kx / 8; ++c)
                             bulk_g2s(A + c * 2048, a.xc + ((size_t)c * a.xc_rows + (size_t)tile * TILE + t) * 16, 2048, &a_full[0]);
                     } else {
+                        mbar_wait(&done_l[l - 1], t & 1);                  // h_{l-1,t}
                         bulk_g2s(A, a.base + a.ly[l - 1].h_off[t & 1] + (size_t)tile * xb, xb, &a_full[0]);
                     }
                 }
@@ -277,9 +284,10 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
         } else if (wtid == 32) {
             // ===================== loader B: free-running weight ring =====================
             int it = 0;
-            for (int t = 0; t < a.L; ++t) {
-                const int parts = t > 0 ? 2 : 1;
-                for (int l = 0; l < a.n_layers; ++l) {
+            for (int d = 0; d < a.L + a.n_layers - 1; ++d) {
+                const int l_hi = min(a.n_layers - 1, d), l_lo = max(0, d - (a.L - 1));
+                for (int l = l_hi; l >= l_lo; --l) {
+                    const int parts = (d - l) > 0 ? 2 : 1;
                     const PLayer& y = a.ly[l];
                     const uint32_t blk_bytes = (uint32_t)(y.Kx + y.Kh) * NB_COLS * 2;
                     const int rot = tile % y.n_blocks;
@@ -301,9 +309,11 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
             const uint32_t idesc = make_idesc(TILE, NB_COLS);
             const uint32_t a_addr = smem_u32(A);
             int it = 0, g = 0, s = 0, hs = 0;
-            for (int t = 0; t < a.L; ++t) {
-                const int parts = t > 0 ? 2 : 1;
-                for (int l = 0; l < a.n_layers; ++l, ++s) {
+            for (int d = 0; d < a.L + a.n_layers - 1; ++d) {
+                const int l_hi = min(a.n_layers - 1, d), l_lo = max(0, d - (a.L - 1));
+                for (int l = l_hi; l >= l_lo; --l, ++s) {
+                    const int t = d - l;
+                    const int parts = t > 0 ? 2 : 1;
                     const PLayer& y = a.ly[l];
                     mbar_wait(&a_full[0], s & 1);
                     if (t > 0) { mbar_wait(&a_full[1], hs & 1); ++hs; }
@@ -335,9 +345,11 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
     } else {
         // ===================== gate epilogue, warpgroup q = wg =====================
         const uint32_t tmem_lane = s_tmem + (uint32_t)(wg * NB_COLS) + ((uint32_t)(warp * 32) << 16);
-        int g0 = 0, es = 0;
-        for (int t = 0; t < a.L; ++t) {
-            for (int l = 0; l < a.n_layers; ++l) {
+        int g0 = 0;
+        for (int d = 0; d < a.L + a.n_layers - 1; ++d) {
+            const int l_hi = min(a.n_layers - 1, d), l_lo = max(0, d - (a.L - 1));
+            for (int l = l_hi; l >= l_lo; --l) {
+                const int t = d - l;
                 const PLayer& y = a.ly[l];
                 const int rot = tile % y.n_blocks;
                 float* ctile = reinterpret_cast<float*>(a.base + y.c_off) + (size_t)tile * y.n_blocks * UB * TILE + wtid;
@@ -371,13 +383,12 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
                 g0 += y.n_blocks;
                 // publish this step's h stores to the async proxy (the next step's bulk copies read them)
                 fence_proxy_async_all();
+                // a warpgroup without a block in some step must not arrive for (l, t) before (l, t-1) has
+                // closed, or its early arrival would complete the older phase without a busy warpgroup
+                if (t > 0 && warp == 0) mbar_wait(&done_t[l], (t - 1) & 1);
                 named_bar_sync(1 + wg, WG);
-                if (wtid == 0) mbar_arrive(&step_done);
-                // a warpgroup without a block in this step must not run ahead and arrive for a later step
-                // while a busy warpgroup is still inside this one: everybody waits for the step to close
-                if (warp == 0) mbar_wait(&step_done, es & 1);
-                named_bar_sync(1 + wg, WG);
-                ++es;
+                // done_l first: once done_t's phase t is complete every warpgroup has also arrived on done_l
+                if (wtid == 0) { mbar_arrive(&done_l[l]); mbar_arrive(&done_t[l]); }
             }
         }
     }
