@@ -26,7 +26,7 @@ from sklearn.preprocessing import MinMaxScaler
 from gordo_b200 import serializer
 from gordo_b200.fleet import FFFleet, FFTopology, Schedule, time_series_split_bounds
 from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
-from gordo_b200.machine.model.models import KerasAutoEncoder, History, _Model
+from gordo_b200.machine.model.models import KerasAutoEncoder, KerasLSTMBaseEstimator, History, _Model
 
 
 @dataclass
@@ -100,7 +100,7 @@ class FleetModelBuilder:
             return None
         be = model.base_estimator
         if isinstance(be, Pipeline) and len(be.steps) == 2 and isinstance(be.steps[0][1], MinMaxScaler) \
-                and type(be.steps[1][1]) is KerasAutoEncoder:
+                and (type(be.steps[1][1]) is KerasAutoEncoder or isinstance(be.steps[1][1], KerasLSTMBaseEstimator)):
             return be.steps[1][1]
         return None
 
@@ -114,6 +114,10 @@ class FleetModelBuilder:
         y = X if mc.y is None else np.asarray(getattr(mc.y, "values", mc.y))
         est.kwargs.update({"n_features": X.shape[1], "n_features_out": y.shape[1]})
         topo = est._topology()
+        if isinstance(est, KerasLSTMBaseEstimator):
+            return ("lstm", type(est).__name__, topo.key(), int(est.kwargs.get("epochs", 1)), int(est.batch_size),
+                    mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
+                    tuple(sorted(topo.adam.items())), est.kwargs.get("precision", "f32"))
         fit = (int(est.kwargs.get("epochs", 1)), int(est.kwargs.get("batch_size") or 32),
                bool(est.kwargs.get("shuffle", True)), est.kwargs.get("l1_batch_norm", "sum"),
                mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
@@ -142,6 +146,8 @@ class FleetModelBuilder:
     def _build_bucket(self, mcs: List[FleetMachine], protos: List[Any], dev):
         import torch
         est0 = self._standard_parts(protos[0])
+        if isinstance(est0, KerasLSTMBaseEstimator):
+            return self._build_bucket_lstm(mcs, protos, dev)
         topo: FFTopology = est0._topology()
         epochs = int(est0.kwargs.get("epochs", 1)); batch = int(est0.kwargs.get("batch_size") or 32)
         do_shuffle = bool(est0.kwargs.get("shuffle", True))
@@ -259,6 +265,92 @@ class FleetModelBuilder:
                     "cv_fold_history": {f"fold-{i}": {"loss": [float(v) for v in hl_h[m * per + i]]} for i in range(k)}}
             out.append((model, meta))
         return out
+
+
+def _build_bucket_lstm_impl(self, mcs, protos, dev):
+    """
+    Batched build of a bucket of LSTM Machines: every CV fold + final fit is a job of ONE
+    gb200_lstm_fit call (lock-step batches, grid.z = jobs), the fold predictions one
+    gb200_lstm_predict over the test ranges as virtual Machines, scored by gb200_score_outputs.
+    """
+    import torch
+    from gordo_b200.lstm import LSTMFleet
+    est0 = self._standard_parts(protos[0])
+    topo = est0._topology()
+    lookahead, L = est0.lookahead, topo.lookback_window
+    epochs = int(est0.kwargs.get("epochs", 1)); batch = int(est0.batch_size)
+    cv_mode = mcs[0].evaluation.get("cv_mode", "full_build")
+    k = int(mcs[0].evaluation.get("n_splits", 3)) if cv_mode == "full_build" else 0
+    M, T, To, per = len(mcs), topo.n_features, topo.n_features_out, k + 1
+    Xs = [np.asarray(getattr(m.X, "values", m.X)) for m in mcs]
+    Ys = [X if (m.y is None or m.y is m.X) else np.asarray(getattr(m.y, "values", m.y)) for m, X in zip(mcs, Xs)]
+    rows = np.array([len(x) for x in Xs], np.int64)
+    off = np.concatenate([[0], np.cumsum(rows)])
+    xd = torch.as_tensor(np.ascontiguousarray(np.concatenate(Xs), np.float32), device=dev)
+    yd = torch.as_tensor(np.ascontiguousarray(np.concatenate(Ys), np.float32), device=dev)
+    lo, hi, te_lo, te_hi = [], [], [], []
+    for m in range(M):
+        for (s_, e_) in (time_series_split_bounds(int(rows[m]), k) if k else []):
+            lo.append(off[m]); hi.append(off[m] + s_); te_lo.append(off[m] + s_); te_hi.append(off[m] + e_)
+        lo.append(off[m]); hi.append(off[m] + rows[m])
+    lo = np.asarray(lo, np.int64); hi = np.asarray(hi, np.int64)
+    J = len(lo)
+    lo_t = torch.as_tensor(lo, device=dev); hi_t = torch.as_tensor(hi, device=dev)
+    t0 = time.time()
+    in_scale, in_min = FFFleet.minmax_fit(xd, lo_t, hi_t)
+    err_scale, _ = FFFleet.minmax_fit(yd, lo_t, hi_t)
+    gen = torch.Generator(device=dev); gen.manual_seed(int(mcs[0].evaluation.get("seed", 0)))
+    params = topo.init_params(J, gen, dev)
+    trainer = LSTMFleet(topo, J, lookahead, dev)
+    hl, pl = trainer.fit_jobs(xd, yd, lo, hi, params, in_scale=in_scale, in_min=in_min, epochs=epochs, batch_size=batch)
+    feat_h = agg_h = None
+    if k:
+        fold_jobs = np.array([m * per + i for m in range(M) for i in range(k)])
+        sel = torch.as_tensor(fold_jobs, device=dev)
+        vf = LSTMFleet(topo, M * k, lookahead, dev)
+        vf.set_params(params[sel]); vf.in_scale = in_scale[sel].contiguous(); vf.in_min = in_min[sel].contiguous()
+        vs = Schedule(rows_lo=te_lo, rows_hi=te_hi, rows_total=int(off[-1]))
+        prec = est0.kwargs.get("precision", "f32") if vf.tc_eligible() else "f32"
+        out, out_off = vf.predict(vs, xd, precision=prec)
+        n_out = np.diff(out_off)
+        y_off = np.asarray(te_hi, np.int64) - n_out                     # align to the LAST len(output) rows
+        res = FFFleet.score_outputs(out, yd, out_off, y_off, err_scale=err_scale[sel].contiguous())
+        ol = torch.as_tensor(out_off[:-1].copy(), device=dev); oh = torch.as_tensor(out_off[1:].copy(), device=dev)
+        feat_h = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], ol, oh, 6).reshape(M, k, To).double().cpu().numpy()
+        agg_h = FFFleet.rolling_min_max(res["total-anomaly-scaled"], ol, oh, 6).reshape(M, k).double().cpu().numpy()
+    torch.cuda.synchronize()
+    t_total = time.time() - t0
+    P_host = params.cpu().numpy(); hl_h = hl.cpu().numpy(); pl_h = pl.cpu().numpy()
+    in_scale_h = in_scale.double().cpu().numpy(); in_min_h = in_min.double().cpu().numpy(); es_h = err_scale.double().cpu().numpy()
+    out_models = []
+    for m, (mc, model) in enumerate(zip(mcs, protos)):
+        j = m * per + k
+        est = self._standard_parts(model)
+        est.kwargs.update({"n_features": T, "n_features_out": To})
+        est.model = _Model(topo, P_host[j])
+        est._history = History({"loss": [float(pl_h[j])]}, {"verbose": 0, "epochs": 1, "steps": 1}, [0])     # primer (models.py:285)
+        est.history_main_ = {"loss": [float(v) for v in hl_h[j]]}
+        _set_minmax(model.base_estimator.steps[0][1], in_scale_h[j], in_min_h[j], Xs[m], mc.X)
+        ymin = Ys[m].min(axis=0)
+        _set_minmax(model.scaler, es_h[j], -ymin * es_h[j], Ys[m], mc.y if mc.y is not None else mc.X)
+        tags = list(mc.y.columns) if isinstance(mc.y, pd.DataFrame) else (
+            list(mc.X.columns) if isinstance(mc.X, pd.DataFrame) and To == T else list(range(To)))
+        if k:
+            model.feature_thresholds_per_fold_ = pd.DataFrame(feat_h[m], index=[f"fold-{i}" for i in range(k)], columns=tags)
+            model.aggregate_thresholds_per_fold_ = {f"fold-{i}": float(agg_h[m, i]) for i in range(k)}
+            model.smooth_feature_thresholds_per_fold_ = pd.DataFrame()
+            model.smooth_aggregate_thresholds_per_fold_ = {}
+            model.feature_thresholds_ = pd.Series(feat_h[m, -1], index=tags, name=f"fold-{k - 1}")
+            model.aggregate_threshold_ = float(agg_h[m, -1])
+            model.smooth_aggregate_threshold_ = None
+            model.smooth_feature_thresholds_ = None
+        meta = {"name": mc.name, "model_offset": L - 1 + lookahead, "model": model.get_metadata(),
+                "fleet": {"machines_in_launch": M, "fit_jobs": J, "build_duration_sec": t_total}}
+        out_models.append((model, meta))
+    return out_models
+
+
+FleetModelBuilder._build_bucket_lstm = _build_bucket_lstm_impl
 
 
 def _cv_score_dict(metrics: Dict[str, np.ndarray], tags) -> Dict[str, Dict[str, float]]:

@@ -203,3 +203,37 @@ def test_lstm_detector_fused_scoring_matches_generic_path():
     det.base_estimator.steps[1][1].kwargs["precision"] = "bf16"
     fb = det.anomaly(X, X)
     assert float(np.abs(fb["model-output"].to_numpy() - f["model-output"].to_numpy()).max()) < 3e-2
+
+
+def test_fleet_builder_lstm_bucket_matches_oracle():
+    """Batched LSTM build (all folds + final fits in one gb200_lstm_fit, fold scoring on the device) vs the oracle."""
+    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.lstm import LSTMTopology
+    from oracle.anomaly import DiffDetector, LSTMBase
+    T, L, rows = 3, 4, [120, 96]
+    rng = np.random.default_rng(50)
+    Xs = [rng.random((n, T)).astype(np.float32) * [1, 5, 0.2] for n in rows]
+    defn = {"gordo_b200.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {
+        "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler",
+            {"gordo_b200.machine.model.models.KerasLSTMAutoEncoder": {
+                "kind": "lstm_symmetric", "lookback_window": L, "batch_size": 16, "dims": [4], "funcs": ["tanh"]}}]}}}}
+    mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=list("abc")), model=defn, evaluation={"seed": 9}) for i, X in enumerate(Xs)]
+    built = FleetModelBuilder(mcs).build()
+    spec = factories.lstm_symmetric(T, lookback_window=L, dims=(4,), funcs=("tanh",))
+    topo = LSTMTopology(T, T, spec["units"], spec["acts"], "linear", L)
+    gen = torch.Generator(device=DEV); gen.manual_seed(9)
+    init = topo.init_params(len(rows) * 4, gen, torch.device(DEV)).cpu().numpy()
+    for m, ((model, meta), X) in enumerate(zip(built, Xs)):
+        Xd = X.astype(np.float64)
+        det = DiffDetector(lambda tag, m=m: LSTMBase(spec, olstm.lstm_unflatten(
+            init[m * 4 + (3 if tag == "final" else int(tag[-1]))], spec), lookback_window=L, batch_size=16))
+        det.cross_validate(Xd, Xd); det.fit(Xd, Xd)
+        est = model.base_estimator.steps[1][1]
+        np.testing.assert_allclose(est.model.params, olstm.lstm_flatten(det.base.params), atol=3e-4)
+        np.testing.assert_allclose(model.feature_thresholds_.to_numpy(), det.feature_thresholds_, rtol=5e-3, atol=1e-5)
+        np.testing.assert_allclose(model.aggregate_threshold_, det.aggregate_threshold_, rtol=5e-3)
+        assert meta["model_offset"] == L - 1 and meta["fleet"]["fit_jobs"] == 8
+        f = model.anomaly(mcs[m].X, mcs[m].X)
+        want = det.anomaly(Xd, Xd)
+        assert len(f) == rows[m] - L + 1
+        np.testing.assert_allclose(f["total-anomaly-confidence"].to_numpy().ravel(), want["total-anomaly-confidence"], rtol=2e-2, atol=1e-4)
