@@ -17,7 +17,6 @@
 // bf16 operands / fp32 accumulate / fp32 cell state; gates via tanh.approx (sigmoid = .5*tanh(.5z)+.5).
 #include "common.cuh"
 #include "ptx.cuh"
-#include <stdlib.h>
 
 using namespace gbptx;
 
@@ -165,7 +164,7 @@ struct PLayer {
     uint64_t h_off[2], c_off;              // byte offsets (from `base`) of the two h buffers and the cell state
 };
 struct PersistTc {
-    int n_layers, L, tiles, dbg;
+    int n_layers, L, tiles;
     int64_t xc_rows;                       // rows of Xc
     const uint8_t* xc;                     // bf16 scaled samples, K-chunk-major
     uint8_t* base;                         // state scratch
@@ -296,7 +295,7 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
                         for (int part = 0; part < parts; ++part, ++it) {
                             const int st = it % B_STAGES;
                             if (it >= B_STAGES) mbar_wait(&b_empty[st], ((it / B_STAGES) - 1) & 1);
-                            const uint32_t bytes = (a.dbg & 4) ? 128u : (uint32_t)(part == 0 ? y.Kx : y.Kh) * NB_COLS * 2;
+                            const uint32_t bytes = (uint32_t)(part == 0 ? y.Kx : y.Kh) * NB_COLS * 2;
                             mbar_expect_tx(&b_full[st], bytes);
                             bulk_g2s(Bbase + (size_t)st * a.stage_bytes,
                                      a.wp + y.wp_off + (size_t)blk * blk_bytes + (part ? (size_t)y.Kx * NB_COLS * 2 : 0), bytes, &b_full[st]);
@@ -327,7 +326,7 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
                             tc_fence_after();
                             uint64_t da = make_desc(a_addr + (part ? (uint32_t)y.Kx * 256 : 0), 2048, 128);
                             uint64_t db = make_desc(smem_u32(Bbase + (size_t)st * a.stage_bytes), 1024, 128);
-                            const int ksteps = (a.dbg & 2) ? 1 : (part ? y.Kh : y.Kx) / 16;
+                            const int ksteps = (part ? y.Kh : y.Kx) / 16;
                             umma_bf16(d_tmem, da, db, idesc, part ? 1u : 0u);
                             #pragma unroll 4
                             for (int ks = 1; ks < ksteps; ++ks) {
@@ -363,7 +362,7 @@ lstm_persist_tc_kernel(const __grid_constant__ PersistTc a) {
                     if (warp == 0) mbar_wait(&t_full[wg], (g / EPI_WG) & 1);
                     named_bar_sync(1 + wg, WG);
                     tc_fence_after();
-                    if (!(a.dbg & 1)) {
+                    {
                         const float* bias = lbias + (size_t)b * NB_COLS;
                         float* cblk = ctile + b * UB * TILE;
                         uint8_t* hdst = htile + (size_t)(b * 2) * 2048;
@@ -441,8 +440,6 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
         while ((int64_t)tc_state_bytes(q, S + TILE, false) <= scratch_bytes && S + TILE <= (1 << 20)) S += TILE;
     }
     tc_state_bytes(p, S, true);
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("GB200_LSTM_DBG"); dbg = e ? atoi(e) : 0; }
     uint8_t* base = (uint8_t*)scratch;
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 255) & ~(size_t)255; return r; };
@@ -476,7 +473,7 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
             lstm_pack_x_kernel<<<148 * 4, 256, 0, stream>>>(x, row0, rows_avail, rows_chunk, p.T_in, p.ly[0].Kx, sc, mn, xc);
             {
                 PersistTc a{};
-                a.n_layers = p.n_layers; a.L = p.L; a.tiles = tiles; a.dbg = dbg; a.xc_rows = rows_chunk;
+                a.n_layers = p.n_layers; a.L = p.L; a.tiles = tiles; a.xc_rows = rows_chunk;
                 a.xc = (const uint8_t*)xc; a.base = base; a.wp = wp; a.bias = bias;
                 uint32_t stage = 0, abytes = 0;
                 for (int l = 0; l < p.n_layers; ++l) {
@@ -491,11 +488,7 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
                 }
                 a.stage_bytes = stage; a.a_bytes = abytes;
                 const size_t smem = (size_t)abytes + (size_t)B_STAGES_HOST * stage;
-                static size_t configured = 0;
-                if (smem > configured) {
-                    GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_persist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    configured = smem;
-                }
+                GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_persist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 lstm_persist_tc_kernel<<<tiles, PERSIST_THREADS, smem, stream>>>(a);
             }
             const TcLayer& yl = p.ly[p.n_layers - 1];
