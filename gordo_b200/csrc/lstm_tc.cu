@@ -174,9 +174,6 @@ struct PersistTc {
     PLayer ly[GB200_MAX_LAYERS];
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 constexpr int EPI_WG = 4;          // epilogue warpgroups = TMEM accumulator stages
