@@ -46,6 +46,8 @@ SIGNATURES = {
     "gb200_ff_param_count": (_I64, [C.POINTER(FFArch)]),
     "gb200_minmax_fit": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _P, _P]),
     "gb200_rolling_min_max": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _P, _P]),
+    "gb200_smooth": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "gb200_quantile": (C.c_int, [_I32, _P, _P, _P, _I32, C.c_double, _P, _P]),
     "gb200_cv_sums": (C.c_int, [_I32, _P, _P, _P, _P, _I32, _P, _P]),
     "gb200_ff_fit": (C.c_int, [C.POINTER(FFArch), C.POINTER(Adam), _I32] + [_P] * 9 + [_I32] * 3 + [_P] * 6),
     "gb200_lstm_param_count": (_I64, [C.POINTER(LSTMArch)]),

@@ -199,6 +199,20 @@ int gb200_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int32_t n_jo
                             hist_loss, hist_acc, (cudaStream_t)stream);
 }
 
+int gb200_smooth(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* v,
+                 int32_t n_cols, int32_t method, int32_t window, float* out, void* stream) {
+    GB_REQUIRE(n_jobs >= 0 && n_cols >= 1, "bad n_jobs / n_cols");
+    GB_REQUIRE(rows_lo && rows_hi && v && out, "NULL argument");
+    return gb_launch_smooth(n_jobs, rows_lo, rows_hi, v, n_cols, method, window, out, (cudaStream_t)stream);
+}
+
+int gb200_quantile(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* v,
+                   int32_t n_cols, double q, double* out, void* stream) {
+    GB_REQUIRE(n_jobs >= 0 && n_cols >= 1, "bad n_jobs / n_cols");
+    GB_REQUIRE(rows_lo && rows_hi && v && out, "NULL argument");
+    return gb_launch_quantile(n_jobs, rows_lo, rows_hi, v, n_cols, q, out, (cudaStream_t)stream);
+}
+
 int gb200_cv_sums(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* y,
                   const float* yhat, int32_t n_tags, double* sums, void* stream) {
     GB_REQUIRE(n_jobs >= 0 && n_tags >= 1, "bad n_jobs / n_tags");

@@ -94,6 +94,10 @@ int gb_launch_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int n_jo
                      const int64_t* perm_off, const int32_t* perm_pool, int epochs, int batch_size,
                      int l1_mean, float* params, float* adam_mv, int64_t* adam_t, float* hist_loss,
                      float* hist_acc, cudaStream_t stream);
+int gb_launch_smooth(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v, int n_cols,
+                     int method, int window, float* out, cudaStream_t stream);
+int gb_launch_quantile(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v, int n_cols,
+                       double q, double* out, cudaStream_t stream);
 int gb_launch_cv_sums(int n_jobs, const int64_t* lo, const int64_t* hi, const float* y, const float* yhat,
                       int n_tags, double* out, cudaStream_t stream);
 int64_t gb_lstm_tc_scratch_bytes(const gb200_lstm_arch* arch, int64_t max_windows);

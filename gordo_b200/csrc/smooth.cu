@@ -1,0 +1,282 @@
+// Smoothing and percentile thresholds of the anomaly scores.
+//
+//   gb200_smooth   : pandas `rolling(w).median()` / `rolling(w).mean()` / `ewm(span=w).mean()` of every
+//                    column of a row-major [rows, C] matrix, restarted at each job's first row
+//                    (diff.py:302-308; the smooth-* columns of .anomaly(), diff.py:387-415).
+//   gb200_quantile : pandas `DataFrame.quantile(q)` (linear interpolation, NaN skipped) per column
+//                    over each job's rows (diff.py:631-635: the KFCV thresholds).
+//
+// Smoothing: one thread owns (column, run of S consecutive output rows) and slides its window over
+// the run after warming up on the w-1 rows in front of it; threads of a warp sit on adjacent columns,
+// so a row step of a warp is one contiguous read and one contiguous write.  The moving median keeps
+// the window SORTED in shared memory ([w][threads], conflict-free) and replaces the outgoing value
+// by the incoming one with a single shift pass.  Mean / EWMA carry their state in float64 registers,
+// in the recurrences pandas uses.  Quantile: one CTA per (job, column), three-pass radix select
+// (11+11+10 bits of the order-preserving integer image of the float) per order statistic.
+#include "common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace {
+
+struct SmoothArgs {
+    const int64_t* lo; const int64_t* hi;
+    const float* v; float* out;
+    int C, window, method;
+    int S;              // output rows per thread
+    int halo;           // rows of warm-up in front of a run (window-1, or the EWMA truncation length)
+    double alpha;       // EWMA: 2 / (span + 1)
+};
+
+// sorted window of thread `tid`: element i lives at s[i * nt + tid]
+struct SortedWin {
+    float* s; int nt; int n;
+    __device__ __forceinline__ float& at(int i) { return s[i * nt]; }
+    __device__ __forceinline__ int lower_bound(float x) {        // first i with s[i] >= x
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (at(mid) < x) lo = mid + 1; else hi = mid; }
+        return lo;
+    }
+    __device__ __forceinline__ void insert(float x) {
+        int i = n;
+        while (i > 0 && at(i - 1) > x) { at(i) = at(i - 1); --i; }
+        at(i) = x; ++n;
+    }
+    __device__ __forceinline__ void remove(float x) {
+        int i = lower_bound(x);
+        for (; i + 1 < n; ++i) at(i) = at(i + 1);
+        --n;
+    }
+    // the outgoing value's slot is refilled by shifting towards the incoming value's position
+    __device__ __forceinline__ void replace(float x_old, float x_new) {
+        int i = lower_bound(x_old);
+        if (x_new >= x_old) { while (i + 1 < n && at(i + 1) < x_new) { at(i) = at(i + 1); ++i; } }
+        else                { while (i > 0 && at(i - 1) > x_new) { at(i) = at(i - 1); --i; } }
+        at(i) = x_new;
+    }
+};
+
+__global__ void smooth_kernel(const __grid_constant__ SmoothArgs a) {
+    extern __shared__ float s_win[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    const int job = blockIdx.y;
+    const int c0 = blockIdx.z * nt;
+    const int Cc = min(a.C - c0, nt);
+    const int nsub = nt / Cc;
+    const int sub = tid / Cc, col = c0 + tid - sub * Cc;
+    if (sub >= nsub) return;
+    const int64_t j0 = a.lo[job], j1 = a.hi[job];
+    const int64_t o0 = j0 + ((int64_t)blockIdx.x * nsub + sub) * a.S;
+    const int64_t o1 = min(o0 + (int64_t)a.S, j1);
+    if (o0 >= o1) return;
+    const int64_t h0 = max(j0, o0 - (int64_t)a.halo);
+    const int C = a.C, w = a.window;
+    const float* v = a.v + col;
+    float* out = a.out + col;
+
+    if (a.method == GB200_SMOOTH_SMM) {
+        SortedWin sw{s_win + tid, nt, 0};
+        const bool odd = (w & 1) != 0;
+        for (int64_t r = h0; r < o1; ++r) {
+            const float x_new = v[r * C];
+            const bool has_old = r - w >= h0;
+            const float x_old = has_old ? v[(r - w) * C] : NAN;
+            const bool vo = x_old == x_old, vn = x_new == x_new;
+            if (vo && vn) sw.replace(x_old, x_new);
+            else { if (vo) sw.remove(x_old); if (vn) sw.insert(x_new); }
+            if (r >= o0) {
+                float m = NAN;
+                if (sw.n == w)          // w non-NaN observations (min_periods = window)
+                    m = odd ? sw.at(w >> 1) : (float)(0.5 * ((double)sw.at((w >> 1) - 1) + (double)sw.at(w >> 1)));
+                out[r * C] = m;
+            }
+        }
+    } else if (a.method == GB200_SMOOTH_SMA) {
+        double sum = 0.0; int nobs = 0;
+        const double inv_w = 1.0 / (double)w;
+        for (int64_t r = h0; r < o1; ++r) {
+            const float x_new = v[r * C];
+            if (x_new == x_new) { sum += (double)x_new; ++nobs; }
+            if (r - w >= h0) { const float x_old = v[(r - w) * C]; if (x_old == x_old) { sum -= (double)x_old; --nobs; } }
+            if (r >= o0) out[r * C] = nobs == w ? (float)(sum * inv_w) : NAN;
+        }
+    } else {
+        // pandas ewm(span=w, adjust=True, ignore_na=False).mean(): avg <- (old_wt*avg + x)/(old_wt + 1)
+        // with old_wt decayed by (1 - alpha) at every row; the history before h0 carries a relative
+        // weight below 2^-64 and is dropped
+        const double decay = 1.0 - a.alpha;
+        double avg = NAN, old_wt = 1.0;
+        for (int64_t r = h0; r < o1; ++r) {
+            const float x = v[r * C];
+            const bool obs = x == x;
+            if (r > h0) {
+                if (avg == avg) {
+                    old_wt *= decay;
+                    if (obs) {
+                        if (avg != (double)x) avg = (old_wt * avg + (double)x) / (old_wt + 1.0);
+                        old_wt += 1.0;
+                    }
+                } else if (obs) avg = (double)x;
+            } else if (obs) avg = (double)x;
+            if (r >= o0) out[r * C] = (float)avg;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- quantile
+constexpr int Q_THREADS = 256;
+constexpr int Q_BINS = 2048;
+
+__device__ __forceinline__ uint32_t f2key(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// value of 0-based ascending rank `rank` among the non-NaN elements of the column (all threads call)
+__device__ float radix_select(const float* __restrict__ v, int64_t n_rows, int C, int64_t rank,
+                              int* hist, int* scan, int* s_pick) {
+    uint32_t prefix = 0, mask = 0;
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+        const int nb = 1 << bits[p];
+        for (int i = threadIdx.x; i < Q_BINS; i += Q_THREADS) hist[i] = 0;
+        __syncthreads();
+        for (int64_t r = threadIdx.x; r < n_rows; r += Q_THREADS) {
+            const float x = v[r * C];
+            if (x == x) {
+                const uint32_t k = f2key(x);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shifts[p]) & (nb - 1)], 1);
+            }
+        }
+        __syncthreads();
+        // each thread owns Q_BINS / Q_THREADS consecutive bins; inclusive scan of the per-thread sums
+        constexpr int PER = Q_BINS / Q_THREADS;
+        int local = 0;
+        for (int i = 0; i < PER; ++i) local += hist[threadIdx.x * PER + i];
+        scan[threadIdx.x] = local;
+        __syncthreads();
+        for (int off = 1; off < Q_THREADS; off <<= 1) {
+            const int t = threadIdx.x >= off ? scan[threadIdx.x - off] : 0;
+            __syncthreads();
+            scan[threadIdx.x] += t;
+            __syncthreads();
+        }
+        const int64_t before = (int64_t)scan[threadIdx.x] - local;           // elements in lower bins
+        if (rank >= before && rank < before + local) {
+            int64_t acc = before; int b = threadIdx.x * PER;
+            for (;; ++b) { const int h = hist[b]; if (rank < acc + h) break; acc += h; }
+            s_pick[0] = b; s_pick[1] = (int)(rank - acc);
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_pick[0] << shifts[p];
+        mask |= (uint32_t)(nb - 1) << shifts[p];
+        rank = s_pick[1];
+        __syncthreads();
+    }
+    return key2f(prefix);
+}
+
+__global__ void __launch_bounds__(Q_THREADS)
+quantile_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, const float* __restrict__ v,
+                int C, double q, double* __restrict__ out) {
+    __shared__ int hist[Q_BINS];
+    __shared__ int scan[Q_THREADS];
+    __shared__ int s_pick[2];
+    __shared__ int64_t s_n;
+    const int job = blockIdx.y, col = blockIdx.x;
+    const int64_t j0 = lo[job], n_rows = hi[job] - j0;
+    const float* base = v + j0 * C + col;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int64_t cnt = 0;
+    for (int64_t r = threadIdx.x; r < n_rows; r += Q_THREADS) { const float x = base[r * C]; cnt += (x == x); }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)&s_n, (unsigned long long)cnt);
+    __syncthreads();
+    const int64_t n = s_n;
+    double res = NAN;
+    if (n > 0) {
+        const double h = (double)(n - 1) * q;
+        const int64_t k = (int64_t)floor(h);
+        const double frac = h - (double)k;
+        const float va = radix_select(base, n_rows, C, k, hist, scan, s_pick);
+        float vb = va;
+        if (frac > 0.0 && k + 1 < n) vb = radix_select(base, n_rows, C, k + 1, hist, scan, s_pick);
+        res = (double)va + ((double)vb - (double)va) * frac;
+    }
+    if (threadIdx.x == 0) out[(size_t)job * C + col] = res;
+}
+
+int max_rows_host(int n_jobs, const int64_t* lo, const int64_t* hi, cudaStream_t stream, int64_t* out) {
+    int64_t* h = (int64_t*)malloc(sizeof(int64_t) * 2 * n_jobs);
+    if (!h) { gb_set_error("out of host memory"); return GB_ERR_ARG; }
+    cudaError_t e = cudaMemcpyAsync(h, lo, sizeof(int64_t) * n_jobs, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h + n_jobs, hi, sizeof(int64_t) * n_jobs, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { free(h); gb_set_error("row range copy: %s", cudaGetErrorString(e)); return GB_ERR_CUDA; }
+    int64_t mx = 0;
+    for (int i = 0; i < n_jobs; ++i) { const int64_t n = h[n_jobs + i] - h[i]; if (n > mx) mx = n; }
+    free(h);
+    *out = mx;
+    return GB_OK;
+}
+
+}  // namespace
+
+int gb_launch_smooth(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v, int n_cols,
+                     int method, int window, float* out, cudaStream_t stream) {
+    if (n_jobs <= 0) return GB_OK;
+    GB_REQUIRE(window >= 1, "smooth: window must be >= 1");
+    GB_REQUIRE(method == GB200_SMOOTH_SMM || method == GB200_SMOOTH_SMA || method == GB200_SMOOTH_EWMA,
+               "smooth: method must be GB200_SMOOTH_SMM / _SMA / _EWMA");
+    int64_t max_rows = 0;
+    int rc = max_rows_host(n_jobs, lo, hi, stream, &max_rows);
+    if (rc) return rc;
+    if (max_rows == 0) return GB_OK;
+    SmoothArgs a{};
+    a.lo = lo; a.hi = hi; a.v = v; a.out = out; a.C = n_cols; a.window = window; a.method = method;
+    int nt = 256;
+    size_t smem = 0;
+    if (method == GB200_SMOOTH_SMM) {
+        // the sorted windows of a block live in shared memory: fewer threads for long windows
+        const size_t cap = 200 * 1024;
+        while (nt > 32 && (size_t)nt * window * sizeof(float) > cap) nt >>= 1;
+        GB_REQUIRE((size_t)nt * window * sizeof(float) <= cap, "smooth: moving-median window %d too long (max %d)",
+                   window, (int)(cap / (32 * sizeof(float))));
+        smem = (size_t)nt * window * sizeof(float);
+        a.halo = window - 1;
+    } else if (method == GB200_SMOOTH_SMA) {
+        a.halo = window - 1;
+    } else {
+        a.alpha = 2.0 / ((double)window + 1.0);
+        // (1 - alpha)^halo < 2^-64
+        const double need = ceil(64.0 * log(2.0) / -log1p(-a.alpha));
+        a.halo = need > 1e9 ? 1000000000 : (int)need;
+    }
+    // rows per thread: long enough to amortise the warm-up, short enough to fill the GPU
+    int S = a.halo > 512 ? a.halo : 512;
+    const int Cc = n_cols < nt ? n_cols : nt;
+    const int nsub = nt / Cc;
+    while (S > 64 && S / 2 >= a.halo && ((max_rows + S - 1) / S) * (int64_t)n_jobs * n_cols < 148LL * 2048) S >>= 1;
+    a.S = S;
+    const int64_t rows_per_block = (int64_t)nsub * S;
+    dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), n_jobs, (n_cols + nt - 1) / nt);
+    if (smem > 48 * 1024)
+        GB_CUDA_CHECK(cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smooth_kernel<<<grid, nt, smem, stream>>>(a);
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
+}
+
+int gb_launch_quantile(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v, int n_cols,
+                       double q, double* out, cudaStream_t stream) {
+    if (n_jobs <= 0) return GB_OK;
+    GB_REQUIRE(q >= 0.0 && q <= 1.0, "quantile: q must be in [0, 1]");
+    dim3 grid(n_cols, n_jobs);
+    quantile_kernel<<<grid, Q_THREADS, 0, stream>>>(lo, hi, v, n_cols, q, out);
+    GB_CUDA_CHECK(cudaGetLastError());
+    return GB_OK;
+}

@@ -240,6 +240,40 @@ class FFFleet:
                                               N.ptr(out), _stream_ptr()), "gb200_rolling_min_max")
         return out
 
+    SMOOTH_METHODS = {"smm": 0, "sma": 1, "ewma": 2}
+
+    @staticmethod
+    def smooth(v: torch.Tensor, rows_lo: torch.Tensor, rows_hi: torch.Tensor, method: str, window: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """
+        pandas rolling(window).median() / .mean() / ewm(span=window).mean() of every column over row
+        ranges (diff.py:302-308).  v: [R] or [R, C] float32 CUDA -> same shape.
+        """
+        if method not in FFFleet.SMOOTH_METHODS:
+            raise ValueError(f"smoothing_method must be one of {sorted(FFFleet.SMOOTH_METHODS)}, got {method!r}")
+        v2 = v if v.dim() == 2 else v.unsqueeze(1)
+        _require_cuda(v2, rows_lo, rows_hi)
+        if v2.dtype != torch.float32 or not v2.is_contiguous():
+            raise ValueError("smooth: v must be contiguous float32")
+        res = torch.full_like(v2, float("nan")) if out is None else (out if out.dim() == 2 else out.unsqueeze(1))
+        N.check(N.lib().gb200_smooth(rows_lo.numel(), N.ptr(rows_lo), N.ptr(rows_hi), N.ptr(v2), v2.shape[1],
+                                     FFFleet.SMOOTH_METHODS[method], int(window), N.ptr(res), _stream_ptr()),
+                "gb200_smooth")
+        return res if v.dim() == 2 else res[:, 0]
+
+    @staticmethod
+    def quantile(v: torch.Tensor, rows_lo: torch.Tensor, rows_hi: torch.Tensor, q: float) -> torch.Tensor:
+        """pandas DataFrame.quantile(q) (linear, NaN skipped) per column over row ranges -> [J, C] float64."""
+        v2 = v if v.dim() == 2 else v.unsqueeze(1)
+        _require_cuda(v2, rows_lo, rows_hi)
+        if v2.dtype != torch.float32 or not v2.is_contiguous():
+            raise ValueError("quantile: v must be contiguous float32")
+        J, Cc = rows_lo.numel(), v2.shape[1]
+        out = torch.empty((J, Cc), dtype=torch.float64, device=v.device)
+        N.check(N.lib().gb200_quantile(J, N.ptr(rows_lo), N.ptr(rows_hi), N.ptr(v2), Cc, float(q), N.ptr(out),
+                                       _stream_ptr()), "gb200_quantile")
+        return out
+
     # ------------------------------------------------------------------ inference + scoring
     def score(self, sched: Schedule, x: torch.Tensor, y: Optional[torch.Tensor] = None, *,
               precision: str = "bf16", columns: Sequence[str] = SCORE_COLUMNS,

@@ -182,12 +182,32 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         return pd.DataFrame(np.abs(np.asarray(y_true, np.float64) - np.asarray(y_pred, np.float64)))
 
     def _smoothing(self, metric: Union[pd.DataFrame, pd.Series]):
-        if self.smoothing_method == "smm":
-            return metric.rolling(self.window).median()
-        elif self.smoothing_method == "sma":
-            return metric.rolling(self.window).mean()
-        elif self.smoothing_method == "ewma":
-            return metric.ewm(span=self.window).mean()
+        """'smm' / 'sma' / 'ewma' of every column (diff.py:302-308), one ``gb200_smooth`` launch."""
+        if self.smoothing_method not in ("smm", "sma", "ewma"):
+            # the reference falls through its if-chain, returns None and dies on `None.columns`
+            raise AttributeError(f"smoothing_method must be 'smm', 'sma' or 'ewma', got {self.smoothing_method!r}")
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        v = torch.as_tensor(np.ascontiguousarray(np.asarray(metric, np.float32)), device=dev)
+        sm = self._smooth_device(v).cpu().numpy().astype(np.float64)
+        if isinstance(metric, pd.Series):
+            return pd.Series(sm, index=metric.index, name=metric.name)
+        return pd.DataFrame(sm, index=metric.index, columns=metric.columns)
+
+    def _smooth_device(self, v):
+        """v: [n] or [n, C] float32 CUDA, one series per column, all rows one range."""
+        import torch
+        from gordo_b200.fleet import FFFleet
+        lo = torch.zeros(1, dtype=torch.int64, device=v.device)
+        hi = torch.full((1,), v.shape[0], dtype=torch.int64, device=v.device)
+        return FFFleet.smooth(v.contiguous(), lo, hi, self.smoothing_method, self.window)
+
+    def _add_smooth_columns(self, res):
+        """smooth-* columns of .anomaly() (diff.py:387-415) from the device-resident score columns."""
+        if self.window is not None and self.smoothing_method in ("smm", "sma", "ewma"):
+            for k in ("tag-anomaly-scaled", "total-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-unscaled"):
+                res["smooth-" + k] = self._smooth_device(res[k])
+        return res
 
     # ------------------------------------------------------------------ anomaly
     def _fused_plan(self):
@@ -229,7 +249,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         yd = None if (Xv.shape == yv.shape and np.array_equal(Xv, yv)) else \
             torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
         prec = est._precision if fleet.tc_eligible() else "f32"
-        res = fleet.score(Schedule([len(Xv)]), xd, yd, precision=prec)
+        res = self._add_smooth_columns(fleet.score(Schedule([len(Xv)]), xd, yd, precision=prec))
         return {k: v.cpu().numpy() for k, v in res.items()}
 
     def _fused_columns_lstm(self, sc, est, Xv, yv, dev):
@@ -254,7 +274,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             feat_thr=None if feat is None else f32(np.asarray(feat, np.float64)),
             agg_thr=None if agg is None else torch.as_tensor(np.array([agg], np.float32), device=dev))
         res["model-output"] = out
-        return {k: v.cpu().numpy() for k, v in res.items()}
+        return {k: v.cpu().numpy() for k, v in self._add_smooth_columns(res).items()}
 
     def anomaly(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None) -> pd.DataFrame:
         """
@@ -282,7 +302,9 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             d_scaled, tot_scaled = cols["tag-anomaly-scaled"], cols["total-anomaly-scaled"]
             d_un, tot_un = cols["tag-anomaly-unscaled"], cols["total-anomaly-unscaled"]
             conf, tconf = cols.get("anomaly-confidence"), cols.get("total-anomaly-confidence")
+            smooth = {k: v for k, v in cols.items() if k.startswith("smooth-")}
         else:
+            smooth = None
             out = np.asarray(self.predict(X) if hasattr(self, "predict") else self.transform(X))
             n = len(out)
             out_names = y_tags if out.shape[1] == len(y_tags) else [str(i) for i in range(out.shape[1])]
@@ -302,11 +324,15 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
                   ("tag-anomaly-unscaled", d_un, [model_utils._tag_name(t) for t in y_tags]),
                   ("total-anomaly-unscaled", tot_un, None)]
         if self.window is not None and self.smoothing_method is not None:
-            sm = lambda a: np.asarray(self._smoothing(pd.DataFrame(np.asarray(a, np.float64))))
-            groups += [("smooth-tag-anomaly-scaled", sm(d_scaled), out_names),
-                       ("smooth-total-anomaly-scaled", sm(tot_scaled)[:, 0], None),
-                       ("smooth-tag-anomaly-unscaled", sm(d_un), [model_utils._tag_name(t) for t in y_tags]),
-                       ("smooth-total-anomaly-unscaled", sm(tot_un)[:, 0], None)]
+            if not smooth:
+                sm = lambda a: np.asarray(self._smoothing(pd.DataFrame(np.asarray(a, np.float64))))
+                smooth = {"smooth-tag-anomaly-scaled": sm(d_scaled), "smooth-total-anomaly-scaled": sm(tot_scaled)[:, 0],
+                          "smooth-tag-anomaly-unscaled": sm(d_un), "smooth-total-anomaly-unscaled": sm(tot_un)[:, 0]}
+            groups += [("smooth-tag-anomaly-scaled", smooth["smooth-tag-anomaly-scaled"], out_names),
+                       ("smooth-total-anomaly-scaled", smooth["smooth-total-anomaly-scaled"], None),
+                       ("smooth-tag-anomaly-unscaled", smooth["smooth-tag-anomaly-unscaled"],
+                        [model_utils._tag_name(t) for t in y_tags]),
+                       ("smooth-total-anomaly-unscaled", smooth["smooth-total-anomaly-unscaled"], None)]
         if conf is not None:
             groups.append(("anomaly-confidence", conf, out_names))
         if tconf is not None:
@@ -387,5 +413,15 @@ class DiffBasedKFCVAnomalyDetector(DiffBasedAnomalyDetector):
         return self._calculate_threshold(absolute_error)
 
     def _calculate_threshold(self, validation_metric):
-        val_metric = self._smoothing(validation_metric)
-        return val_metric.quantile(self.threshold_percentile)
+        """percentile of the smoothed validation metric (diff.py:631-635): gb200_smooth -> gb200_quantile."""
+        import torch
+        from gordo_b200.fleet import FFFleet
+        dev = torch.device("cuda", torch.cuda.current_device())
+        v = torch.as_tensor(np.ascontiguousarray(np.asarray(validation_metric, np.float32)), device=dev)
+        sm = self._smooth_device(v)
+        lo = torch.zeros(1, dtype=torch.int64, device=dev)
+        hi = torch.full((1,), v.shape[0], dtype=torch.int64, device=dev)
+        q = FFFleet.quantile(sm, lo, hi, self.threshold_percentile)[0].cpu().numpy()
+        if isinstance(validation_metric, pd.DataFrame):
+            return pd.Series(q, index=validation_metric.columns, name=self.threshold_percentile)
+        return float(q[0])

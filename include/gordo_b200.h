@@ -136,6 +136,28 @@ int gb200_rolling_min_max(int32_t n_jobs, const int64_t* rows_lo, const int64_t*
                           const float* v, int32_t n_cols, int32_t window, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Smoothing of the anomaly scores (diff.py:302-308 `_smoothing`; the smooth-* columns of
+ * .anomaly(), diff.py:387-415; the validation metric of DiffBasedKFCVAnomalyDetector, diff.py:631-635):
+ *   GB200_SMOOTH_SMM  pandas rolling(window).median()     (NaN for the first window-1 rows of a job)
+ *   GB200_SMOOTH_SMA  pandas rolling(window).mean()       (same)
+ *   GB200_SMOOTH_EWMA pandas ewm(span=window).mean()      (adjust=True, ignore_na=False)
+ * applied to every column of v [rows_total, n_cols] over each job's rows [lo, hi), restarted at lo.
+ * out: [rows_total, n_cols]; rows outside every job are left untouched.  NaN inputs follow pandas
+ * (a window holding a NaN yields NaN; EWMA carries the last mean over a NaN).
+ */
+enum { GB200_SMOOTH_SMM = 0, GB200_SMOOTH_SMA = 1, GB200_SMOOTH_EWMA = 2 };
+int gb200_smooth(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* v,
+                 int32_t n_cols, int32_t method, int32_t window, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Percentile thresholds: pandas DataFrame.quantile(q) (linear interpolation, NaN skipped) of every
+ * column of v [rows_total, n_cols] over each job's rows (diff.py:631-635 `_calculate_threshold`).
+ * out: [n_jobs, n_cols] float64 (NaN when a column has no finite row in the range).
+ */
+int gb200_quantile(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const float* v,
+                   int32_t n_cols, double q, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Cross-validation scoring sums (gordo/builder/build_model.py:377-446 builds 4 x (T+1) sklearn
  * scorers -- explained variance, r2, MSE, MAE per tag and averaged -- each a host pass over the
  * fold): one pass per fold on the device.  sums: [n_jobs, 5, n_tags] float64 =

@@ -10,7 +10,7 @@ this file against those outputs.
 import numpy as np
 import pandas as pd
 
-from .scaler import MinMaxScaler, time_series_split
+from .scaler import MinMaxScaler, time_series_split, kfold_split, shuffle_rows
 from . import dense as _dense
 from . import lstm as _lstm
 
@@ -188,6 +188,54 @@ class DiffDetector:
             raise AttributeError("`require_thresholds=True` however `.cross_validate` needs to be "
                                  "called in order to calculate these thresholds before calling `.anomaly`")
         return res
+
+
+class KFCVDetector(DiffDetector):
+    """
+    DiffBasedKFCVAnomalyDetector (diff.py:461-635): KFold(5, shuffle, seed 0) out-of-fold predictions
+    for every row, thresholds = ``threshold_percentile`` quantile of the smoothed validation errors.
+    ``shuffle`` mirrors the detector's fit-time row shuffle (diff.py:166-174; on by default here as
+    in the reference's constructor).  PINNED by tests/golden/kfcv_golden.npz (real reference run).
+    """
+
+    def __init__(self, make_base, *, require_thresholds=True, window=144, smoothing_method="smm",
+                 threshold_percentile=0.99, shuffle=True):
+        super().__init__(make_base, require_thresholds=require_thresholds, window=window,
+                         smoothing_method=smoothing_method)
+        self.threshold_percentile = threshold_percentile
+        self.shuffle = shuffle
+
+    def _fit_base(self, tag, X, y):
+        if self.shuffle:
+            order = shuffle_rows(len(X), 0)
+            return self.make_base(tag).fit(X[order], y[order])
+        return self.make_base(tag).fit(X, y)
+
+    def fit(self, X, y):
+        X = np.asarray(X); y = np.asarray(y)
+        self.base = self._fit_base("final", X, y)
+        self.scaler = MinMaxScaler().fit(y)
+        return self
+
+    def _threshold(self, metric):
+        # diff.py:631-635: smoothing, then pandas quantile (linear interpolation, NaN skipped)
+        sm = smoothing(metric, self.smoothing_method, self.window)
+        q = pd.DataFrame(sm).quantile(self.threshold_percentile).to_numpy()
+        return float(q[0]) if np.asarray(metric).ndim == 1 else q
+
+    def cross_validate(self, X, y, n_splits=5, seed=0):
+        X = np.asarray(X); y = np.asarray(y)
+        y_pred = np.zeros_like(np.asarray(y, np.float64))
+        y_val_mse = np.full(len(y), np.nan)
+        for i, (tr, te) in enumerate(kfold_split(len(X), n_splits, seed)):
+            base = self._fit_base(f"fold-{i}", X[tr], y[tr])
+            fold_scaler = MinMaxScaler().fit(y[tr])
+            y_pred[te] = base.predict(X[te])
+            y_val_mse[te] = scaled_mse_per_timestep(fold_scaler, y[te], y_pred[te])
+        self.cv_predictions_ = y_pred
+        self.aggregate_threshold_ = self._threshold(y_val_mse)
+        self.feature_thresholds_ = self._threshold(np.abs(np.asarray(y, np.float64) - y_pred))
+        return self
 
 
 COLUMN_ORDER = ("model-input", "model-output", "tag-anomaly-scaled", "total-anomaly-scaled",

@@ -38,3 +38,29 @@ def time_series_split(n_samples, n_splits=3):
     idx = np.arange(n_samples)
     for test_start in range(n_samples - n_splits * test_size, n_samples, test_size):
         yield idx[:test_start], idx[test_start:test_start + test_size]
+
+
+def kfold_split(n_samples, n_splits=5, seed=0):
+    """
+    Yield (train_idx, test_idx) as sklearn ``KFold(n_splits, shuffle=True, random_state=seed)`` does
+    (the default cv of DiffBasedKFCVAnomalyDetector.cross_validate, diff.py:568): one Mersenne
+    shuffle of arange(n), cut into folds of size n//k (+1 for the first n%k), each side returned in
+    ascending order.
+    """
+    idx = np.arange(n_samples)
+    np.random.RandomState(seed).shuffle(idx)
+    sizes = np.full(n_splits, n_samples // n_splits, dtype=int)
+    sizes[: n_samples % n_splits] += 1
+    start = 0
+    for s in sizes:
+        mask = np.zeros(n_samples, dtype=bool)
+        mask[idx[start:start + s]] = True
+        yield np.where(~mask)[0], np.where(mask)[0]
+        start += s
+
+
+def shuffle_rows(n_samples, seed=0):
+    """Row order of ``sklearn.utils.shuffle(X, y, random_state=seed)`` (diff.py:168-170)."""
+    idx = np.arange(n_samples)
+    np.random.RandomState(seed).shuffle(idx)
+    return idx

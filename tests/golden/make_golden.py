@@ -193,9 +193,41 @@ def main():
     except AttributeError:
         raised = True
 
+    # ---- DiffBasedKFCVAnomalyDetector (diff.py:461-635): KFold(5, shuffle, seed 0) predictions, smoothed
+    # validation errors, percentile thresholds, and the anomaly frame with its smooth-* columns
+    kf_out, kf_cases = {}, []
+    for ci, (n, t, window, method, pct) in enumerate([
+            (1000, 4, 144, "smm", 0.99),
+            (600, 3, 24, "sma", 0.95),
+            (500, 5, 12, "ewma", 0.99),
+            (400, 2, 7, "smm", 0.9)]):
+        r = np.random.default_rng(200 + ci)
+        Xa = r.random((n, t)); ya = Xa * r.random(t) + 0.1 * r.random((n, t))
+        tags = [f"tag-{j}" for j in range(t)]
+        X = pd.DataFrame(Xa, columns=tags); y = pd.DataFrame(ya, columns=tags)
+        model = diff.DiffBasedKFCVAnomalyDetector(base_estimator=OffsetLinear(0), scaler=MinMaxScaler(),
+                                                  window=window, smoothing_method=method,
+                                                  threshold_percentile=pct)
+        model.cross_validate(X=X, y=y)
+        model.fit(X, y)
+        frame = model.anomaly(X, y, frequency=timedelta(minutes=10))
+        pre = f"k{ci}_"
+        kf_out[pre + "X"] = Xa; kf_out[pre + "y"] = ya
+        kf_out[pre + "feature_thresholds"] = np.asarray(model.feature_thresholds_, float)
+        kf_out[pre + "aggregate_threshold"] = float(model.aggregate_threshold_)
+        groups = []
+        for top in dict.fromkeys(c[0] for c in frame.columns):
+            if top in ("start", "end"):
+                continue
+            kf_out[pre + "col_" + top] = frame[top].to_numpy(float)
+            groups.append(top)
+        kf_cases.append({"n": n, "t": t, "window": window, "method": method, "percentile": pct,
+                         "groups": groups, "metadata_keys": sorted(model.get_metadata().keys())})
+    np.savez_compressed(os.path.join(HERE, "kfcv_golden.npz"), **kf_out)
+
     np.savez_compressed(os.path.join(HERE, "detector_golden.npz"), **out)
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
-        json.dump({"hourglass": hg, "time_series_split": tss, "cases": cases,
+        json.dump({"hourglass": hg, "time_series_split": tss, "cases": cases, "kfcv_cases": kf_cases,
                    "require_thresholds_raises": raised,
                    "versions": {"numpy": np.__version__, "pandas": pd.__version__,
                                 "sklearn": __import__("sklearn").__version__},

@@ -159,3 +159,45 @@ def test_rolling_min_max_matches_pandas():
         w1 = pd.Series(x[:, 0]).rolling(6).min().max()
         got = rolling_min_max(x[:, 0], 6)
         assert (np.isnan(w1) and np.isnan(got)) or np.isclose(w1, got)
+
+
+def test_kfold_and_shuffle_against_sklearn():
+    from sklearn.model_selection import KFold
+    from sklearn.utils import shuffle
+    from oracle.scaler import kfold_split, shuffle_rows
+    for n in (10, 11, 503, 1000):
+        for k in (2, 5, 7):
+            want = list(KFold(n_splits=k, shuffle=True, random_state=0).split(np.zeros((n, 1))))
+            got = list(kfold_split(n, k, 0))
+            assert len(want) == len(got) == k
+            for (wtr, wte), (gtr, gte) in zip(want, got):
+                np.testing.assert_array_equal(wtr, gtr)
+                np.testing.assert_array_equal(wte, gte)
+        np.testing.assert_array_equal(shuffle(np.arange(n), random_state=0), shuffle_rows(n, 0))
+
+
+KNPZ = np.load(os.path.join(G, "kfcv_golden.npz"))
+
+
+@pytest.mark.parametrize("ci", range(len(META["kfcv_cases"])))
+def test_kfcv_detector_against_real_reference(ci):
+    """DiffBasedKFCVAnomalyDetector of the real reference (diff.py:461-635) vs oracle.KFCVDetector."""
+    from oracle.anomaly import KFCVDetector
+    case = META["kfcv_cases"][ci]
+    pre = f"k{ci}_"
+    X, y = KNPZ[pre + "X"], KNPZ[pre + "y"]
+    det = KFCVDetector(lambda tag: _OffsetLinear(0), window=case["window"], smoothing_method=case["method"],
+                       threshold_percentile=case["percentile"])
+    det.cross_validate(X, y)
+    det.fit(X, y)
+    res = det.anomaly(X, y)
+    tol = dict(rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(det.feature_thresholds_, KNPZ[pre + "feature_thresholds"], **tol)
+    np.testing.assert_allclose(det.aggregate_threshold_, KNPZ[pre + "aggregate_threshold"], **tol)
+    assert set(case["groups"]) == set(res)
+    for grp in case["groups"]:
+        want = KNPZ[pre + "col_" + grp]
+        got = np.asarray(res[grp], float)
+        if want.ndim == 2 and want.shape[1] == 1 and got.ndim == 1:
+            want = want[:, 0]
+        np.testing.assert_allclose(got, want, equal_nan=True, **tol)
