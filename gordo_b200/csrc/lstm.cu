@@ -16,6 +16,7 @@
 // The tensor-core (tcgen05) recurrent kernel is the next step for this path.
 #include "common.cuh"
 #include <vector>
+#include <stdlib.h>
 
 namespace {
 
@@ -83,6 +84,9 @@ struct StepArgs {
     // optional caches for BPTT ([seq] x stride): gates i,f,g,o (4u) and act(c) (u)
     float* gates; int64_t gates_seq_stride, gates_grp_stride;
     float* actc; int64_t actc_seq_stride, actc_grp_stride;
+    // training: `gates` already holds x_t.W + b for this (layer, t) (batched over all t by
+    // lstm_bgemm_kernel); only the recurrent product h_{t-1}.U is left for this kernel
+    int pre;
 };
 
 __global__ void __launch_bounds__(ST_THREADS)
@@ -92,7 +96,7 @@ lstm_step_fwd_kernel(const __grid_constant__ StepArgs a) {
     const int s0 = blockIdx.x * ST_SEQ;
     if (s0 >= nb) return;
     const int u0 = blockIdx.y * ST_UNITS;
-    const int u = a.u, in = a.in, K = in + u;
+    const int u = a.u, in = a.pre ? 0 : a.in, K = (a.pre && !a.h_prev) ? 0 : in + u;
     const float* P = a.params + (size_t)grp * a.n_params;
     const float* W = P + a.w_off; const float* U = P + a.u_off; const float* bias = P + a.b_off;
 
@@ -108,7 +112,13 @@ lstm_step_fwd_kernel(const __grid_constant__ StepArgs a) {
         #pragma unroll
         for (int gte = 0; gte < 4; ++gte) {
             const int uu = u0 + uj + q;
-            acc[q][gte] = uu < u ? bias[gte * u + uu] : 0.0f;
+            float b0 = 0.0f;
+            if (uu < u) {
+                if (!a.pre) b0 = bias[gte * u + uu];
+                else if (s0 + s_l < nb)
+                    b0 = a.gates[(size_t)grp * a.gates_grp_stride + (size_t)(s0 + s_l) * a.gates_seq_stride + gte * u + uu];
+            }
+            acc[q][gte] = b0;
         }
     const int64_t row0 = a.layer == 0 ? a.g.rows_lo[grp] + a.g.seq_base + a.t : 0;
     const float* sc = (a.layer == 0 && a.in_scale) ? a.in_scale + (size_t)grp * a.T_in : nullptr;
@@ -366,6 +376,387 @@ __global__ void lstm_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched fp32 GEMM over the (t, seq) composite dimension of a training step.  Sequence buffers are
+// dense [t][seq][width] (row r = t*cap + seq), so everything that is not the recurrence itself is
+// one GEMM per layer instead of one launch per time step:
+//   comp == 0:  C[r][j]  = sum_k A(r,k) * B(k,j) (+ bias[j])      rows r composite, masked by seq < nb
+//               (x.W for all t: NN;  dz.W^T -> dLoss/dx for all t: NT)
+//   comp == 1:  C[i][j]  = sum_r A(r,i) * B(r,j)                   K composite: the weight gradients
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile; operands may be "k-contiguous" (element (m,k)
+// at P[m*ld + k]) or "m-contiguous" (P[k*ld + m]); one grid.z slice per fit job.
+struct GemmArgs {
+    GroupCtx g;
+    int seq_dim;             // sequences per time step in the buffers (the fit's batch size)
+    int M, N, K, comp;
+    const float* A; int64_t a_grp; int lda, a_kcontig;
+    const float* B; int64_t b_grp; int ldb, b_kcontig;
+    float* C; int64_t c_grp; int ldc;
+    const float* bias; int64_t bias_grp;
+};
+constexpr int GK = 16;
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256)
+lstm_bgemm_kernel(const __grid_constant__ GemmArgs a) {
+    constexpr int RM = BM / 64, RN = BN / 64;        // 4-wide chunks of the micro-tile (rows / cols)
+    constexpr int EA = BM * GK / 256, EB = BN * GK / 256;
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    if (nb == 0) return;
+    const int sd = a.seq_dim;
+    const bool full = nb == sd;                      // no masking needed (every step but a job's last)
+    const float* __restrict__ A = a.A + (size_t)grp * a.a_grp;
+    const float* __restrict__ B = a.B + (size_t)grp * a.b_grp;
+    float* C = a.C + (size_t)grp * a.c_grp;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    __shared__ __align__(16) float As[GK][BM + 4];
+    __shared__ __align__(16) float Bs[GK][BN + 4];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;          // 16 x 16 threads
+    float acc[RM * 4][RN * 4] = {};
+    float ra[EA], rb[EB];
+    // global -> registers for the K slab at k0: consecutive threads walk the operand's contiguous dimension
+    auto fetch = [&](int k0) {
+        #pragma unroll
+        for (int e = 0; e < EA; ++e) {
+            const int i = tid + e * 256;
+            int mm, kk;
+            if (a.a_kcontig) { kk = i & (GK - 1); mm = i / GK; } else { mm = i & (BM - 1); kk = i / BM; }
+            const int m = m0 + mm, k = k0 + kk;
+            float v = 0.0f;
+            if (m < a.M && k < a.K && (full || ((a.comp ? k : m) % sd) < nb))
+                v = a.a_kcontig ? A[(size_t)m * a.lda + k] : A[(size_t)k * a.lda + m];
+            ra[e] = v;
+        }
+        #pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const int i = tid + e * 256;
+            int nn, kk;
+            if (a.b_kcontig) { kk = i & (GK - 1); nn = i / GK; } else { nn = i & (BN - 1); kk = i / BN; }
+            const int n = n0 + nn, k = k0 + kk;
+            float v = 0.0f;
+            if (n < a.N && k < a.K && (full || !a.comp || (k % sd) < nb))
+                v = a.b_kcontig ? B[(size_t)n * a.ldb + k] : B[(size_t)k * a.ldb + n];
+            rb[e] = v;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < a.K; k0 += GK) {
+        #pragma unroll
+        for (int e = 0; e < EA; ++e) {
+            const int i = tid + e * 256;
+            if (a.a_kcontig) As[i & (GK - 1)][i / GK] = ra[e]; else As[i / BM][i & (BM - 1)] = ra[e];
+        }
+        #pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const int i = tid + e * 256;
+            if (a.b_kcontig) Bs[i & (GK - 1)][i / GK] = rb[e]; else Bs[i / BN][i & (BN - 1)] = rb[e];
+        }
+        __syncthreads();
+        if (k0 + GK < a.K) fetch(k0 + GK);          // next slab's loads fly while this one is multiplied
+        #pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            float ar[RM * 4], br[RN * 4];
+            #pragma unroll
+            for (int c = 0; c < RM; ++c) {
+                const float4 t = *reinterpret_cast<const float4*>(&As[kk][c * 64 + ty * 4]);
+                ar[c * 4] = t.x; ar[c * 4 + 1] = t.y; ar[c * 4 + 2] = t.z; ar[c * 4 + 3] = t.w;
+            }
+            #pragma unroll
+            for (int c = 0; c < RN; ++c) {
+                const float4 t = *reinterpret_cast<const float4*>(&Bs[kk][c * 64 + tx * 4]);
+                br[c * 4] = t.x; br[c * 4 + 1] = t.y; br[c * 4 + 2] = t.z; br[c * 4 + 3] = t.w;
+            }
+            #pragma unroll
+            for (int i = 0; i < RM * 4; ++i)
+                #pragma unroll
+                for (int j = 0; j < RN * 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const float* bias = a.bias ? a.bias + (size_t)grp * a.bias_grp : nullptr;
+    #pragma unroll
+    for (int i = 0; i < RM * 4; ++i) {
+        const int m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+        if (m >= a.M || (!a.comp && !full && (m % sd) >= nb)) continue;
+        #pragma unroll
+        for (int j = 0; j < RN * 4; ++j) {
+            const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+            if (n < a.N) C[(size_t)m * a.ldc + n] = acc[i][j] + (bias ? bias[n] : 0.0f);
+        }
+    }
+}
+
+// layer-0 operand of a training step, dense: xs[t][seq][k] = scale(x[rows_lo + seq_base + seq + t][k])
+__global__ void lstm_gather_x_kernel(GroupCtx g, int B, int L, int T_in, const float* __restrict__ x,
+                                     const float* __restrict__ in_scale, const float* __restrict__ in_min,
+                                     float* __restrict__ xs, int64_t xs_grp) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(g, grp);
+    const int64_t total = (int64_t)L * B * T_in;
+    const float* sc = in_scale ? in_scale + (size_t)grp * T_in : nullptr;
+    const float* mn = in_min ? in_min + (size_t)grp * T_in : nullptr;
+    const int64_t row0 = g.rows_lo[grp] + g.seq_base;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % T_in);
+        const int64_t r = i / T_in;
+        const int s = (int)(r % B), t = (int)(r / B);
+        float v = 0.0f;
+        if (s < nb) { v = x[(row0 + s + t) * T_in + k]; if (sc) v = fmaf(v, sc[k], mn[k]); }
+        xs[(size_t)grp * xs_grp + i] = v;
+    }
+}
+
+// bias gradients: out[grp][n] = sum over rows r = (t, seq < nb) of dz[r][n]
+__global__ void lstm_colsum_kernel(GroupCtx g, int B, int rows, int N, const float* __restrict__ dz, int64_t dz_grp,
+                                   float* __restrict__ out, int64_t out_grp, int64_t out_off) {
+    const int grp = blockIdx.z;
+    const int nb = group_nb(g, grp);
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int lane_r = threadIdx.x >> 5;                 // 8 row lanes
+    __shared__ float part[8][33];
+    float acc = 0.0f;
+    if (n < N)
+        for (int r = lane_r; r < rows; r += 8)
+            if ((r % B) < nb) acc += dz[(size_t)grp * dz_grp + (size_t)r * N + n];
+    part[lane_r][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (lane_r == 0 && n < N) {
+        for (int q = 1; q < 8; ++q) acc += part[q][threadIdx.x & 31];
+        out[(size_t)grp * out_grp + out_off + n] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The recurrence of a training step, persistent: ONE launch per layer walks all L time steps.
+// A fit job is a thread-block cluster of CL CTAs; CTA c keeps the recurrent weights of its slice of
+// units (all four gate columns) in shared memory for the whole sequence, so U is read once per layer
+// per step instead of once per time step, and time steps are separated by a cluster barrier instead
+// of a kernel launch.
+//   forward : z_t = (x_t.W + b)  [already in `gates`, from lstm_bgemm_kernel]  + h_{t-1}.U[:, own columns];
+//             gates, c_t, h_t for the own units; h_t is broadcast into every CTA's next h buffer (DSMEM).
+//   backward: dz_t for the own units from dLoss/dh_t (from above + recurrent) and the cached gates;
+//             partial dh_rec[s][j] = sum over OWN columns n of dz_t[s][n].U[j][n] for all units j, sent to
+//             the CTA owning unit j, which adds the CL partials in rank order (deterministic).
+struct RecArgs {
+    GroupCtx g;
+    int B, BP, L, u, act, us, nc, CL, width, NG, top;
+    const float* params; int64_t n_params, u_off;
+    float* gates; float* hs; float* cs; float* ac;      // [t][seq][4u] / [t][seq][u] caches, group stride gs
+    const float* dH; float* dz;                         // backward: dLoss/dh from above [t][seq][u]; dz out [t][seq][4u]
+    int64_t gs;
+};
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_peer(const float* local, uint32_t rank, float v) {
+    uint32_t addr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+constexpr int REC_SG = 16;          // sequences per thread per pass of the small GEMMs
+
+__global__ void lstm_rec_fwd_kernel(const __grid_constant__ RecArgs a) {
+    extern __shared__ __align__(16) float rsm[];
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    if (nb == 0) return;                              // the whole cluster leaves together
+    const int rank = (int)cluster_rank();
+    const int u = a.u, us = a.us, nc = a.nc, B = a.B, BP = a.BP, CL = a.CL;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    float* Us = rsm;                                  // [u][nc]     own columns of U, column = gate*us + unit
+    float* hb = Us + (size_t)u * nc;                  // [2][u][BP]  h_{t-1} / h_t, transposed (seq contiguous)
+    float* zb = hb + (size_t)2 * u * BP;              // [nc][BP+1]  pre-activations of the own columns
+    float* cst = zb + (size_t)nc * (BP + 1);          // [us][BP]    cell state
+    const int j0 = rank * us, nu = max(0, min(us, u - j0));
+    const float* U = a.params + (size_t)grp * a.n_params + a.u_off;
+    for (int i = tid; i < u * nc; i += nthr) {
+        const int k = i / nc, c = i - k * nc, gte = c / us, j = c - gte * us;
+        Us[i] = j < nu ? U[(size_t)k * 4 * u + gte * u + j0 + j] : 0.0f;
+    }
+    for (int i = tid; i < 2 * u * BP; i += nthr) hb[i] = 0.0f;
+    for (int i = tid; i < us * BP; i += nthr) cst[i] = 0.0f;
+    __syncthreads();
+    cluster_sync_all();                               // every CTA initialised before any peer writes into it
+    float* gates = a.gates + (size_t)grp * a.gs;
+    float* hs = a.hs + (size_t)grp * a.gs; float* cs = a.cs + (size_t)grp * a.gs; float* ac = a.ac + (size_t)grp * a.gs;
+    const int col = tid % a.width, sg = tid / a.width;
+    const int cg = col / us, cj = col - cg * us;
+    for (int t = 0; t < a.L; ++t) {
+        const float* hcur = hb + (size_t)(t & 1) * u * BP;
+        float* hnext = hb + (size_t)((t + 1) & 1) * u * BP;
+        // ---- phase A: z[col][s] = (x.W + b)[s][col] + sum_k h_{t-1}[s][k] * U[k][col]
+        if (col < nc) {
+            for (int sb = sg * REC_SG; sb < BP; sb += a.NG * REC_SG) {
+                float acc[REC_SG];
+                #pragma unroll
+                for (int i = 0; i < REC_SG; ++i) {
+                    const int sq = sb + i;
+                    acc[i] = (sq < nb && cj < nu) ? gates[((size_t)t * B + sq) * 4 * u + cg * u + j0 + cj] : 0.0f;
+                }
+                if (t > 0) {
+                    for (int k = 0; k < u; ++k) {
+                        const float uv = Us[k * nc + col];
+                        const float4* h4 = reinterpret_cast<const float4*>(hcur + (size_t)k * BP + sb);
+                        #pragma unroll
+                        for (int q = 0; q < REC_SG / 4; ++q) {
+                            const float4 hv = h4[q];
+                            acc[4 * q] = fmaf(hv.x, uv, acc[4 * q]); acc[4 * q + 1] = fmaf(hv.y, uv, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(hv.z, uv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(hv.w, uv, acc[4 * q + 3]);
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int i = 0; i < REC_SG; ++i) zb[col * (BP + 1) + sb + i] = acc[i];
+            }
+        }
+        __syncthreads();
+        // ---- phase B: gates, cell update, h_t for the own units; h_t goes to every CTA of the cluster
+        for (int e = tid; e < us * BP; e += nthr) {
+            const int j = e / BP, sq = e - j * BP;
+            if (j >= nu) continue;
+            float hval = 0.0f;
+            if (sq < nb) {
+                const float ig = sigmoidf_(zb[(0 * us + j) * (BP + 1) + sq]), fg = sigmoidf_(zb[(1 * us + j) * (BP + 1) + sq]);
+                const float gg = gb_act(a.act, zb[(2 * us + j) * (BP + 1) + sq]), og = sigmoidf_(zb[(3 * us + j) * (BP + 1) + sq]);
+                const float cn = fmaf(fg, cst[e], ig * gg);
+                const float acv = gb_act(a.act, cn);
+                cst[e] = cn;
+                hval = og * acv;
+                const size_t r = (size_t)t * B + sq;
+                float* gp = gates + r * 4 * u + j0 + j;
+                gp[0] = ig; gp[u] = fg; gp[2 * u] = gg; gp[3 * u] = og;
+                cs[r * u + j0 + j] = cn; ac[r * u + j0 + j] = acv; hs[r * u + j0 + j] = hval;
+            }
+            const float* dst = hnext + (size_t)(j0 + j) * BP + sq;
+            for (int r = 0; r < CL; ++r) st_peer(dst, (uint32_t)r, hval);
+        }
+        cluster_sync_all();
+    }
+}
+
+__global__ void lstm_rec_bwd_kernel(const __grid_constant__ RecArgs a) {
+    extern __shared__ __align__(16) float rsm[];
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    if (nb == 0) return;
+    const int rank = (int)cluster_rank();
+    const int u = a.u, us = a.us, nc = a.nc, B = a.B, BP = a.BP, CL = a.CL;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    float* UT = rsm;                                  // [nc][u]          U[j][own column n], n-major
+    float* dzT = UT + (size_t)nc * u;                 // [nc][BP]         dz_t of the own columns, transposed
+    float* recv = dzT + (size_t)nc * BP;              // [2][CL][us][BP]  partial dh_rec from every CTA
+    float* dcs = recv + (size_t)2 * CL * us * BP;     // [us][BP]         running dLoss/dc
+    const int j0 = rank * us, nu = max(0, min(us, u - j0));
+    const float* U = a.params + (size_t)grp * a.n_params + a.u_off;
+    for (int i = tid; i < nc * u; i += nthr) {
+        const int n = i / u, j = i - n * u, gte = n / us, jl = n - gte * us;
+        UT[i] = jl < nu ? U[(size_t)j * 4 * u + gte * u + j0 + jl] : 0.0f;
+    }
+    for (int i = tid; i < 2 * CL * us * BP; i += nthr) recv[i] = 0.0f;
+    for (int i = tid; i < us * BP; i += nthr) dcs[i] = 0.0f;
+    __syncthreads();
+    cluster_sync_all();
+    const float* gates = a.gates + (size_t)grp * a.gs;
+    const float* cs = a.cs + (size_t)grp * a.gs; const float* ac = a.ac + (size_t)grp * a.gs;
+    const float* dH = a.dH ? a.dH + (size_t)grp * a.gs : nullptr;
+    float* dz = a.dz + (size_t)grp * a.gs;
+    const int jc = tid % a.width, sg = tid / a.width;
+    for (int it = 0; it < a.L; ++it) {
+        const int t = a.L - 1 - it;
+        // ---- phase E: dz_t of the own units
+        for (int e = tid; e < us * BP; e += nthr) {
+            const int jl = e / BP, sq = e - jl * BP;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            if (jl < nu && sq < nb) {
+                const size_t r = (size_t)t * B + sq;
+                float dh = 0.0f;
+                if (dH && (!a.top || t == a.L - 1)) dh += dH[r * u + j0 + jl];
+                if (it > 0) {
+                    const float* rp = recv + (size_t)((it - 1) & 1) * CL * us * BP + (size_t)jl * BP + sq;
+                    float rec = 0.0f;
+                    for (int q = 0; q < CL; ++q) rec += rp[(size_t)q * us * BP];
+                    dh += rec;
+                }
+                const float* gp = gates + r * 4 * u + j0 + jl;
+                const float ig = gp[0], fg = gp[u], gg = gp[2 * u], og = gp[3 * u];
+                const float acv = ac[r * u + j0 + jl];
+                const float cp = t > 0 ? cs[(r - B) * u + j0 + jl] : 0.0f;
+                const float dc_in = it == 0 ? 0.0f : dcs[e];
+                const float d_o = dh * acv;
+                const float dc = dc_in + dh * og * act_grad_h(a.act, acv);
+                dcs[e] = dc * fg;
+                d0 = dc * gg * ig * (1.0f - ig);
+                d1 = dc * cp * fg * (1.0f - fg);
+                d2 = dc * ig * act_grad_h(a.act, gg);
+                d3 = d_o * og * (1.0f - og);
+                float* dp = dz + r * 4 * u + j0 + jl;
+                dp[0] = d0; dp[u] = d1; dp[2 * u] = d2; dp[3 * u] = d3;
+            }
+            dzT[(0 * us + jl) * BP + sq] = d0; dzT[(1 * us + jl) * BP + sq] = d1;
+            dzT[(2 * us + jl) * BP + sq] = d2; dzT[(3 * us + jl) * BP + sq] = d3;
+        }
+        __syncthreads();
+        // ---- phase G: partial dh_rec[s][j] over the own columns, sent to the owner of unit j
+        if (t > 0 && jc < u) {
+            const int owner = jc / us, jl = jc - owner * us;
+            for (int sb = sg * REC_SG; sb < BP; sb += a.NG * REC_SG) {
+                float acc[REC_SG] = {};
+                for (int n = 0; n < nc; ++n) {
+                    const float uv = UT[n * u + jc];
+                    const float4* d4 = reinterpret_cast<const float4*>(dzT + (size_t)n * BP + sb);
+                    #pragma unroll
+                    for (int q = 0; q < REC_SG / 4; ++q) {
+                        const float4 dv = d4[q];
+                        acc[4 * q] = fmaf(dv.x, uv, acc[4 * q]); acc[4 * q + 1] = fmaf(dv.y, uv, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(dv.z, uv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(dv.w, uv, acc[4 * q + 3]);
+                    }
+                }
+                const float* dst = recv + ((size_t)(it & 1) * CL + rank) * us * BP + (size_t)jl * BP + sb;
+                #pragma unroll
+                for (int i = 0; i < REC_SG; ++i) st_peer(dst + i, (uint32_t)owner, acc[i]);
+            }
+        }
+        cluster_sync_all();
+    }
+}
+
+struct RecPlan { bool ok; int CL, us, nc, BP, width_f, ng_f, width_b, ng_b; size_t smem_f, smem_b; };
+static RecPlan make_rec_plan(int u, int B) {
+    RecPlan r{};
+    r.BP = (B + REC_SG - 1) / REC_SG * REC_SG;
+    r.CL = u > 64 ? 8 : (u > 32 ? 4 : (u > 16 ? 2 : 1));
+    r.us = (u + r.CL - 1) / r.CL;
+    r.nc = 4 * r.us;
+    r.width_f = (r.nc + 31) / 32 * 32;
+    r.width_b = (u + 31) / 32 * 32;
+    const int passes = r.BP / REC_SG;
+    r.ng_f = 512 / r.width_f < passes ? 512 / r.width_f : passes;
+    r.ng_b = 512 / r.width_b < passes ? 512 / r.width_b : passes;
+    r.smem_f = sizeof(float) * ((size_t)u * r.nc + (size_t)2 * u * r.BP + (size_t)r.nc * (r.BP + 1) + (size_t)r.us * r.BP);
+    r.smem_b = sizeof(float) * ((size_t)r.nc * u + (size_t)r.nc * r.BP + (size_t)2 * r.CL * r.us * r.BP + (size_t)r.us * r.BP);
+    r.ok = u <= 256 && r.ng_f >= 1 && r.ng_b >= 1 && r.smem_f <= 200 * 1024 && r.smem_b <= 200 * 1024;
+    return r;
+}
+static int launch_rec(bool fwd, const RecPlan& rp, RecArgs& a, int J, cudaStream_t stream) {
+    a.BP = rp.BP; a.us = rp.us; a.nc = rp.nc; a.CL = rp.CL;
+    a.width = fwd ? rp.width_f : rp.width_b; a.NG = fwd ? rp.ng_f : rp.ng_b;
+    const size_t smem = fwd ? rp.smem_f : rp.smem_b;
+    auto* kern = fwd ? lstm_rec_fwd_kernel : lstm_rec_bwd_kernel;
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(rp.CL, 1, J); cfg.blockDim = dim3(a.width * a.NG, 1, 1);
+    cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = rp.CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    GB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+    return GB_OK;
+}
+
 struct AdamArgs {
     GroupCtx g; gb200_adam adam; int64_t n_params;
     float* params; const float* grad; float* mv; int64_t* tcount;
@@ -528,6 +919,7 @@ static size_t fit_floats_per_job(const LstmPlan& p, int B) {
         n += (size_t)B * u * 2;     // dh_rec, dc
     }
     n += (size_t)B * p.T_out * 2;   // yhat, dzd
+    n += BL * p.T_in;               // dense scaled layer-0 input [t][seq][T_in]
     n += (size_t)p.n_params * 3;    // grad, m, v
     return n + 64;
 }
@@ -592,26 +984,62 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
     }
     const size_t yh_o = o; o += (size_t)B * p.T_out;
     const size_t dzd_o = o; o += (size_t)B * p.T_out;
+    const size_t x0_o = o; o += BL * p.T_in;
     const size_t grad_o = o; o += p.n_params;
     const size_t mv_o = o; o += 2 * (size_t)p.n_params;
     for (int j = 0; j < J; ++j)
         GB_CUDA_CHECK(cudaMemsetAsync(S + (size_t)j * per_job + mv_o, 0, sizeof(float) * 2 * p.n_params, stream));
     const int64_t gs = (int64_t)per_job;            // group stride of everything in the scratch
 
+    // the per-time-step launch path stays as the fallback for very wide layers (GB200_LSTM_REC=0 forces it)
+    bool use_rec = true;
+    { const char* e = getenv("GB200_LSTM_REC"); if (e && atoi(e) == 0) use_rec = false; }
     // sequence buffers are [t][seq][width]: t stride = B*width, seq stride = width
     auto run_step = [&](int seq_base, int cap, float* primer_out) -> int {
         GroupCtx g{d_rows_lo, d_nwin, seq_base, cap};
         GB_CUDA_CHECK(cudaMemsetAsync(d_loss, 0, sizeof(float) * J, stream));
-        // ---------------- forward with caches
-        for (int t = 0; t < L; ++t) {
-            for (int l = 0; l < p.n_layers; ++l) {
-                const int u = p.ld[l].u;
+        // ---------------- forward with caches, layer by layer: the input projection x_t.W + b of ALL
+        // time steps is one GEMM, the recurrence adds h_{t-1}.U step by step
+        auto gemm = [&](int comp, int M, int N, int K, const float* A, int64_t a_grp, int lda, int a_kc,
+                        const float* Bm, int64_t b_grp, int ldb, int b_kc, float* Cm, int64_t c_grp, int ldc,
+                        const float* bias, int64_t bias_grp) {
+            GemmArgs ga{};
+            ga.g = g; ga.seq_dim = B; ga.M = M; ga.N = N; ga.K = K; ga.comp = comp;
+            ga.A = A; ga.a_grp = a_grp; ga.lda = lda; ga.a_kcontig = a_kc;
+            ga.B = Bm; ga.b_grp = b_grp; ga.ldb = ldb; ga.b_kcontig = b_kc;
+            ga.C = Cm; ga.c_grp = c_grp; ga.ldc = ldc; ga.bias = bias; ga.bias_grp = bias_grp;
+            // big tiles once they fill the GPU, small ones for a handful of jobs
+            if ((int64_t)cdiv(N, 128) * cdiv(M, 128) * J >= 148)
+                lstm_bgemm_kernel<128, 128><<<dim3(cdiv(N, 128), cdiv(M, 128), J), 256, 0, stream>>>(ga);
+            else
+                lstm_bgemm_kernel<64, 64><<<dim3(cdiv(N, 64), cdiv(M, 64), J), 256, 0, stream>>>(ga);
+        };
+        {
+            const int64_t tot = (int64_t)L * B * p.T_in;
+            int blocks = (int)((tot + 255) / 256); if (blocks > 2048) blocks = 2048;
+            lstm_gather_x_kernel<<<dim3(blocks, 1, J), 256, 0, stream>>>(g, B, L, p.T_in, x, in_scale, in_min, S + x0_o, gs);
+        }
+        for (int l = 0; l < p.n_layers; ++l) {
+            const int u = p.ld[l].u, in = p.ld[l].in;
+            const float* Ain = l == 0 ? S + x0_o : S + hs_o[l - 1];
+            gemm(0, L * B, 4 * u, in, Ain, gs, in, 1, params + p.ld[l].w_off, p.n_params, 4 * u, 0,
+                 S + gt_o[l], gs, 4 * u, params + p.ld[l].b_off, p.n_params);
+            const RecPlan rp = make_rec_plan(u, B);
+            if (rp.ok && use_rec) {
+                RecArgs ra{};
+                ra.g = g; ra.B = B; ra.L = L; ra.u = u; ra.act = p.acts[l];
+                ra.params = params; ra.n_params = p.n_params; ra.u_off = p.ld[l].u_off;
+                ra.gates = S + gt_o[l]; ra.hs = S + hs_o[l]; ra.cs = S + cs_o[l]; ra.ac = S + ac_o[l]; ra.gs = gs;
+                rc = launch_rec(true, rp, ra, J, stream);
+                if (rc) return rc;
+                continue;
+            }
+            for (int t = 0; t < L; ++t) {
                 StepArgs a{};
-                a.g = g; a.in = p.ld[l].in; a.u = u; a.act = p.acts[l]; a.t = t; a.layer = l;
+                a.g = g; a.in = in; a.u = u; a.act = p.acts[l]; a.t = t; a.layer = l; a.pre = 1;
                 a.params = params; a.n_params = p.n_params;
                 a.w_off = p.ld[l].w_off; a.u_off = p.ld[l].u_off; a.b_off = p.ld[l].b_off;
-                a.x = x; a.T_in = p.T_in; a.in_scale = in_scale; a.in_min = in_min;
-                if (l > 0) { a.xin = S + hs_o[l - 1] + (size_t)t * B * p.ld[l - 1].u; a.xin_seq_stride = p.ld[l - 1].u; a.xin_grp_stride = gs; }
+                a.T_in = p.T_in;
                 a.h_prev = t > 0 ? S + hs_o[l] + (size_t)(t - 1) * B * u : nullptr; a.hprev_seq_stride = u; a.hprev_grp_stride = gs;
                 a.h_out = S + hs_o[l] + (size_t)t * B * u; a.hout_seq_stride = u; a.hout_grp_stride = gs;
                 a.c_prev = t > 0 ? S + cs_o[l] + (size_t)(t - 1) * B * u : nullptr; a.cprev_seq_stride = u; a.cprev_grp_stride = gs;
@@ -656,11 +1084,22 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
             n.out = S + dH_o[p.n_layers - 1] + (size_t)(L - 1) * B * ul; n.o_seq_stride = ul; n.o_grp_stride = gs;
             lstm_nt_kernel<<<dim3(cdiv(cap * ul * 32, 256), 1, J), 256, 0, stream>>>(n);
         }
-        // ---------------- backward: BPTT, top layer first
+        // ---------------- backward: BPTT, top layer first.  Per time step only the recurrence
+        // (gate derivatives, dh_rec = dz.U^T); dLoss/dx and the weight gradients are one GEMM per layer
         for (int l = p.n_layers - 1; l >= 0; --l) {
             const int u = p.ld[l].u, in = p.ld[l].in;
             const bool top = (l == p.n_layers - 1);
-            for (int t = L - 1; t >= 0; --t) {
+            const RecPlan rp = make_rec_plan(u, B);
+            if (rp.ok && use_rec) {
+                RecArgs ra{};
+                ra.g = g; ra.B = B; ra.L = L; ra.u = u; ra.act = p.acts[l]; ra.top = top ? 1 : 0;
+                ra.params = params; ra.n_params = p.n_params; ra.u_off = p.ld[l].u_off;
+                ra.gates = S + gt_o[l]; ra.hs = S + hs_o[l]; ra.cs = S + cs_o[l]; ra.ac = S + ac_o[l]; ra.gs = gs;
+                ra.dH = S + dH_o[l]; ra.dz = S + dz_o[l];
+                rc = launch_rec(false, rp, ra, J, stream);
+                if (rc) return rc;
+            }
+            for (int t = L - 1; t >= 0 && !(rp.ok && use_rec); --t) {
                 BwdGateArgs b{};
                 b.g = g; b.u = u; b.act = p.acts[l]; b.t = t; b.L = L;
                 // the top layer only receives a gradient at t = L-1 (return_sequences=False)
@@ -673,8 +1112,7 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
                 b.c_prev = t > 0 ? S + cs_o[l] + (size_t)(t - 1) * B * u : nullptr; b.cp_seq_stride = u; b.cp_grp_stride = gs;
                 b.dz = S + dz_o[l] + (size_t)t * B * 4 * u; b.dz_seq_stride = 4 * u; b.dz_grp_stride = gs;
                 lstm_bwd_gates_kernel<<<dim3(cdiv(cap * u, 256), 1, J), 256, 0, stream>>>(b);
-                // dh_rec = dz . U^T (needed by t-1); dX_t = dz . W^T -> dH of the layer below
-                if (t > 0) {
+                if (t > 0) {    // dh_rec[seq][j] = sum_n dz_t[seq][n] * U[j][n]  (needed by t-1): one warp per output
                     NTArgs n{};
                     n.g = g; n.N = 4 * u; n.Kout = u;
                     n.A = b.dz; n.a_seq_stride = 4 * u; n.a_grp_stride = gs;
@@ -682,30 +1120,23 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
                     n.out = S + dr_o[l]; n.o_seq_stride = u; n.o_grp_stride = gs;
                     lstm_nt_kernel<<<dim3(cdiv(cap * u * 32, 256), 1, J), 256, 0, stream>>>(n);
                 }
-                if (l > 0) {
-                    NTArgs n{};
-                    n.g = g; n.N = 4 * u; n.Kout = in;
-                    n.A = b.dz; n.a_seq_stride = 4 * u; n.a_grp_stride = gs;
-                    n.B = params + p.ld[l].w_off; n.b_row_stride = 4 * u; n.b_grp_stride = p.n_params;
-                    n.out = S + dH_o[l - 1] + (size_t)t * B * in; n.o_seq_stride = in; n.o_grp_stride = gs;
-                    lstm_nt_kernel<<<dim3(cdiv(cap * in * 32, 256), 1, J), 256, 0, stream>>>(n);
-                }
             }
-            // weight gradients of this layer: one reduction over (t, seq) per weight
-            WgradArgs w{};
-            w.g = g; w.Kdim = in; w.N = 4 * u; w.L = L; w.layer = l; w.T_in = p.T_in; w.shift = 0;
-            if (l == 0) { w.x = x; w.in_scale = in_scale; w.in_min = in_min; }
-            else { w.aseq = S + hs_o[l - 1]; w.a_t_stride = (int64_t)B * in; w.a_seq_stride = in; w.a_grp_stride = gs; }
-            w.dz = S + dz_o[l]; w.dz_t_stride = (int64_t)B * 4 * u; w.dz_seq_stride = 4 * u; w.dz_grp_stride = gs;
-            w.grad = S + grad_o; w.grad_grp_stride = gs; w.grad_off = p.ld[l].w_off;
-            w.gbias = S + grad_o; w.gbias_off = p.ld[l].b_off;
-            lstm_wgrad_kernel<<<dim3(cdiv(in * 4 * u + 4 * u, 256), 1, J), 256, 0, stream>>>(w);
-            WgradArgs r{};
-            r.g = g; r.Kdim = u; r.N = 4 * u; r.L = L; r.layer = 1; r.shift = 1;
-            r.aseq = S + hs_o[l]; r.a_t_stride = (int64_t)B * u; r.a_seq_stride = u; r.a_grp_stride = gs;
-            r.dz = w.dz; r.dz_t_stride = w.dz_t_stride; r.dz_seq_stride = w.dz_seq_stride; r.dz_grp_stride = gs;
-            r.grad = S + grad_o; r.grad_grp_stride = gs; r.grad_off = p.ld[l].u_off;
-            lstm_wgrad_kernel<<<dim3(cdiv(u * 4 * u, 256), 1, J), 256, 0, stream>>>(r);
+            const float* Ain = l == 0 ? S + x0_o : S + hs_o[l - 1];
+            if (l > 0)          // dLoss/dh of the layer below, all t: dz . W^T
+                gemm(0, L * B, in, 4 * u, S + dz_o[l], gs, 4 * u, 1, params + p.ld[l].w_off, p.n_params, 4 * u, 1,
+                     S + dH_o[l - 1], gs, in, nullptr, 0);
+            // weight gradients: reductions over (t, seq) as GEMMs with the composite dimension as K
+            gemm(1, in, 4 * u, L * B, Ain, gs, in, 0, S + dz_o[l], gs, 4 * u, 0,
+                 S + grad_o + p.ld[l].w_off, gs, 4 * u, nullptr, 0);
+            if (L > 1)
+                gemm(1, u, 4 * u, (L - 1) * B, S + hs_o[l], gs, u, 0, S + dz_o[l] + (size_t)B * 4 * u, gs, 4 * u, 0,
+                     S + grad_o + p.ld[l].u_off, gs, 4 * u, nullptr, 0);
+            else        // lookback 1: no recurrent step, no gradient
+                for (int j = 0; j < J; ++j)
+                    GB_CUDA_CHECK(cudaMemsetAsync(S + (size_t)j * per_job + grad_o + p.ld[l].u_off, 0,
+                                                  sizeof(float) * (size_t)u * 4 * u, stream));
+            lstm_colsum_kernel<<<dim3(cdiv(4 * u, 32), 1, J), 256, 0, stream>>>(g, B, L * B, 4 * u, S + dz_o[l], gs,
+                                                                               S + grad_o, gs, p.ld[l].b_off);
         }
         // ---------------- Adam
         AdamArgs ad{};

@@ -47,12 +47,31 @@ struct SortedWin {
         for (; i + 1 < n; ++i) at(i) = at(i + 1);
         --n;
     }
-    // the outgoing value's slot is refilled by shifting towards the incoming value's position
+    // The outgoing value's slot is refilled by shifting the run between it and the incoming value's
+    // position by one.  Both ends come from binary searches, so the shift loop has a known trip count
+    // and its loads do not depend on its stores (4 independent load/store pairs in flight).
     __device__ __forceinline__ void replace(float x_old, float x_new) {
-        int i = lower_bound(x_old);
-        if (x_new >= x_old) { while (i + 1 < n && at(i + 1) < x_new) { at(i) = at(i + 1); ++i; } }
-        else                { while (i > 0 && at(i - 1) > x_new) { at(i) = at(i - 1); --i; } }
-        at(i) = x_new;
+        const int p = lower_bound(x_old);                      // slot of the outgoing value
+        if (x_new >= x_old) {
+            int q = lower_bound(x_new) - 1;                    // last slot holding a value < x_new
+            if (q < p) q = p;
+            int i = p;
+            for (; i + 4 <= q; i += 4) {
+                const float a = at(i + 1), b = at(i + 2), c = at(i + 3), d = at(i + 4);
+                at(i) = a; at(i + 1) = b; at(i + 2) = c; at(i + 3) = d;
+            }
+            for (; i < q; ++i) at(i) = at(i + 1);
+            at(q) = x_new;
+        } else {
+            const int q = lower_bound(x_new);                  // first slot holding a value >= x_new
+            int i = p;
+            for (; i - 4 >= q; i -= 4) {
+                const float a = at(i - 1), b = at(i - 2), c = at(i - 3), d = at(i - 4);
+                at(i) = a; at(i - 1) = b; at(i - 2) = c; at(i - 3) = d;
+            }
+            for (; i > q; --i) at(i) = at(i - 1);
+            at(q) = x_new;
+        }
     }
 };
 

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--cpu-windows", type=int, default=64)
     ap.add_argument("--max-windows", type=int, default=18944)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--fit-jobs", type=int, default=0, help="also time KerasLSTMBaseEstimator.fit (1 epoch) for J jobs")
+    ap.add_argument("--fit-rows", type=int, default=1152)
     a = ap.parse_args()
     import torch
     from gordo_b200.fleet import Schedule
@@ -55,6 +57,27 @@ def main():
     t0 = time.time(); want = olstm.lstm_predict(spec, p, Xc, a.lookback, 0); dt = time.time() - t0
     res["cpu_oracle_windows_per_s_1core"] = a.cpu_windows / dt
     res["max_abs_err_vs_oracle"] = float(np.abs(out[: a.cpu_windows].cpu().numpy() - want).max())
+    if a.fit_jobs > 0:
+        # training: J independent jobs of fit_rows rows, 1 epoch, batch 32 (models.py:557-616);
+        # FLOPs ~ 3 x forward per window
+        J, n = a.fit_jobs, a.fit_rows
+        flt = LSTMFleet(topo, J, 0, dev)
+        P = topo.init_params(J, g, dev)
+        Xf = torch.rand((J * n, a.tags), generator=g, device=dev)
+        lo = np.arange(J, dtype=np.int64) * n; hi = lo + n
+        flt.fit_jobs(Xf, Xf, lo, hi, P.clone(), epochs=1); torch.cuda.synchronize()
+        Pw = P.clone()
+        e0.record(); hl, pl = flt.fit_jobs(Xf, Xf, lo, hi, Pw, epochs=1); e1.record(); torch.cuda.synchronize()
+        fms = e0.elapsed_time(e1)
+        wins = J * (n - a.lookback + 1)
+        res["fit"] = {"jobs": J, "rows_per_job": n, "ms": fms, "train_windows_per_s": wins / (fms * 1e-3),
+                      "achieved_tflops_fp32": wins * 3 * flops_per_window / (fms * 1e-3) / 1e12,
+                      "optimizer_steps": -(-(n - a.lookback + 1) // 32) + 1, "loss": float(hl[0, 0])}
+        cw = 40                                   # CPU oracle: one job, a few windows
+        pc = olstm.lstm_unflatten(P[0].cpu().numpy(), spec)
+        Xo = Xf[: cw + a.lookback - 1].cpu().numpy()
+        t0 = time.time(); olstm.lstm_fit(spec, pc, Xo, Xo, lookback_window=a.lookback, lookahead=0); dt = time.time() - t0
+        res["fit"]["cpu_oracle_train_windows_per_s_1core"] = (cw + 1) / dt
     print(json.dumps(res))
 
 
