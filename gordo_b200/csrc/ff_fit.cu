@@ -13,13 +13,14 @@
 //   loss    : D_L[b][n] = dLoss/dz_L, MSE / accuracy / L1 sums
 //   backward, l = L-1..0:  A: D_{l-1}[b][k] = (sum_n D_l[b][n] W_l[k][n] + l1 sign(h)) act'(h)
 //                          B: g = sum_b h_l[k][b] D_l[b][n]  -> Adam update of W_l[k][n], b_l[n]
-// Layouts: h feature-major [w][Bs] (Bs odd), D batch-major [B][ldd] (ldd odd): every phase reads
-// shared memory either with consecutive lanes on consecutive words or as a broadcast.
+// Layouts: h and D feature-major [w][Bs], Bs a multiple of 4: a thread owns 4 consecutive samples of
+// one feature (forward, backward A) or one weight (backward B), reads activations / deltas as 16-byte
+// words along the batch and a weight once per 4 FMAs; samples past the batch end carry zero deltas.
 #include "common.cuh"
 
 namespace {
 
-constexpr int FIT_THREADS = 256;
+constexpr int FIT_THREADS = 512;
 
 struct FitArgs {
     gb200_ff_arch arch;
@@ -34,9 +35,26 @@ struct FitArgs {
     int64_t n_params;
     int state_in_smem;      // 2: W,m,v in smem  1: W in smem  0: all global
     int h_floats;           // sum_l w_l * Bs
-    int ldd;                // odd row stride of the D buffers
-    int Bs;                 // odd column stride of h
+    int d_floats;           // max_l w_l * Bs
+    int Bs;                 // sample stride of h and D (multiple of 4: 16-byte reads along the batch)
+    int Bq;                 // 4-sample groups per batch
+    const int32_t* order;   // CTA -> job, longest job first
 };
+
+// Jobs differ in length (CV folds of 1/4, 2/4, 3/4 of the rows next to full final fits) and CTAs are
+// dispatched in index order: hand out the longest jobs first so the last wave is made of short ones.
+__global__ void fit_order_kernel(int n_jobs, const int64_t* __restrict__ lo, const int64_t* __restrict__ hi,
+                                 int32_t* __restrict__ order) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    const int64_t mine = hi[j] - lo[j];
+    int rank = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const int64_t other = hi[i] - lo[i];
+        rank += (other > mine) || (other == mine && i < j);
+    }
+    order[rank] = j;
+}
 
 // act' from the OUTPUT h alone (tanh 1-h^2, sigmoid h(1-h), relu/elu via sign of h,
 // softplus sigma(z) = 1 - exp(-h))
@@ -63,30 +81,36 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
+// STATE: where W / Adam m, v live (2: all in shared memory, 1: W only, 0: global).  A template
+// parameter so that the compiler knows the address space: plain LDS/STS with 32-bit addressing
+// instead of generic loads in every inner loop.
+// BQ: 4-sample groups per batch when known at compile time (8 = Keras' default batch of 32), else 0.
+template <int STATE, int BQ>
 __global__ void __launch_bounds__(FIT_THREADS, 1)
 ff_fit_kernel(const __grid_constant__ FitArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float red[FIT_THREADS / 32];
     __shared__ int s_argmax_hits;
 
-    const int job = blockIdx.x, tid = threadIdx.x;
+    const int job = a.order ? a.order[blockIdx.x] : blockIdx.x, tid = threadIdx.x;
     const int L = a.arch.n_layers;
     const int T_in = a.arch.widths[0], T_out = a.arch.widths[L];
-    const int B = a.batch, Bs = a.Bs, ldd = a.ldd;
+    const int B = a.batch;
+    const int Bq = BQ ? BQ : a.Bq, Bs = BQ ? 4 * BQ + 4 : a.Bs;
     const int64_t P = a.n_params;
 
     float* hbuf = smem;                               // all layer activations of the batch
-    float* D0 = hbuf + a.h_floats;                    // [B][ldd]
-    float* D1 = D0 + B * ldd;
-    float* st = D1 + B * ldd;                         // optional on-chip W / m / v
+    float* D0 = hbuf + a.h_floats;                    // [max_w][Bs]
+    float* D1 = D0 + a.d_floats;
+    float* st = D1 + a.d_floats;                      // optional on-chip W / m / v
     float* gW = a.params + (size_t)job * P;
     float* gM = a.adam_mv + (size_t)job * 2 * P;
     float* gV = gM + P;
-    float* W = a.state_in_smem >= 1 ? st : gW;
-    float* Mo = a.state_in_smem >= 2 ? st + P : gM;
-    float* Vo = a.state_in_smem >= 2 ? st + 2 * P : gV;
-    if (a.state_in_smem >= 1) for (int64_t i = tid; i < P; i += FIT_THREADS) W[i] = gW[i];
-    if (a.state_in_smem >= 2) for (int64_t i = tid; i < P; i += FIT_THREADS) { Mo[i] = gM[i]; Vo[i] = gV[i]; }
+    float* W = STATE >= 1 ? st : gW;
+    float* Mo = STATE >= 2 ? st + P : gM;
+    float* Vo = STATE >= 2 ? st + 2 * P : gV;
+    if (STATE >= 1) for (int64_t i = tid; i < P; i += FIT_THREADS) W[i] = gW[i];
+    if (STATE >= 2) for (int64_t i = tid; i < P; i += FIT_THREADS) { Mo[i] = gM[i]; Vo[i] = gV[i]; }
 
     const int64_t r_lo = a.lo[job];
     const int n = (int)(a.hi[job] - r_lo);
@@ -111,29 +135,46 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
                 if (sc) v = fmaf(v, sc[k], mn[k]);
                 hbuf[k * Bs + b] = v;
             }
+            // samples past the end of a short batch: zero inputs keep every activation finite
+            for (int i = tid; i < (4 * Bq - nb) * T_in; i += FIT_THREADS) {
+                const int b = nb + i / T_in, k = i % T_in;
+                hbuf[k * Bs + b] = 0.0f;
+            }
             if (tid == 0) s_argmax_hits = 0;
             __syncthreads();
-            // ---- forward
+            // ---- forward: a thread owns one output feature for 4 consecutive samples, so a weight is
+            // read once per 4 FMAs and the activations come as one 16-byte read
             float l1_sum = 0.0f;
             {
-                int ho = 0; int64_t po = 0;
+                int ho = 0; int po = 0;
                 for (int l = 0; l < L; ++l) {
                     const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
                     const int code = a.arch.acts[l];
-                    const float* Wl = W + po; const float* bl = Wl + (int64_t)win * wout;
+                    const float* Wl = W + po; const float* bl = Wl + win * wout;
                     const float* hin = hbuf + ho; float* hout = hbuf + ho + win * Bs;
                     const float c1 = a.arch.l1[l];
-                    for (int i = tid; i < wout * 32; i += FIT_THREADS) {
-                        const int nn = i >> 5, b = i & 31;
-                        for (int bb = b; bb < nb; bb += 32) {
-                            float acc = bl[nn];
-                            for (int k = 0; k < win; ++k) acc = fmaf(hin[k * Bs + bb], Wl[k * wout + nn], acc);
-                            const float h = gb_act(code, acc);
-                            hout[nn * Bs + bb] = h;
-                            if (c1 != 0.0f) l1_sum += c1 * fabsf(h);
+                    for (int i = tid; i < wout * Bq; i += FIT_THREADS) {
+                        const int nn = i / Bq, b4 = (i - nn * Bq) * 4;
+                        const float bias = bl[nn];
+                        float a0 = bias, a1 = bias, a2 = bias, a3 = bias;
+                        const float* wp = Wl + nn; const float* hp = hin + b4;
+                        #pragma unroll 4
+                        for (int k = 0; k < win; ++k, wp += wout, hp += Bs) {
+                            const float w = *wp;
+                            const float4 h4 = *reinterpret_cast<const float4*>(hp);
+                            a0 = fmaf(h4.x, w, a0); a1 = fmaf(h4.y, w, a1); a2 = fmaf(h4.z, w, a2); a3 = fmaf(h4.w, w, a3);
+                        }
+                        float4 o;
+                        o.x = gb_act(code, a0); o.y = gb_act(code, a1); o.z = gb_act(code, a2); o.w = gb_act(code, a3);
+                        *reinterpret_cast<float4*>(hout + nn * Bs + b4) = o;
+                        if (c1 != 0.0f) {
+                            if (b4 < nb) l1_sum += c1 * fabsf(o.x);
+                            if (b4 + 1 < nb) l1_sum += c1 * fabsf(o.y);
+                            if (b4 + 2 < nb) l1_sum += c1 * fabsf(o.z);
+                            if (b4 + 3 < nb) l1_sum += c1 * fabsf(o.w);
                         }
                     }
-                    ho += win * Bs; po += (int64_t)win * wout + wout;
+                    ho += win * Bs; po += win * wout + wout;
                     __syncthreads();
                 }
             }
@@ -150,15 +191,21 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
                 const float inv = 2.0f / (float)(nb * T_out);
                 const int code = a.arch.acts[L - 1];
                 const float cL = a.arch.l1[L - 1] * (a.l1_mean ? 1.0f / (float)nb : 1.0f);
-                for (int i = tid; i < nb * T_out; i += FIT_THREADS) {
+                // D is feature-major like h ([n][Bs]); samples past nb carry zeros so that the
+                // batch reductions below can run over whole 4-sample groups
+                for (int i = tid; i < 4 * Bq * T_out; i += FIT_THREADS) {
                     const int b = i / T_out, nn = i - b * T_out;
-                    const int64_t r = r_lo + (perm ? perm[(int64_t)e * n + s0 + b] : s0 + b);
-                    const float yh = hL[nn * Bs + b];
-                    const float diff = yh - ysrc[r * T_out + nn];
-                    sq = fmaf(diff, diff, sq);
-                    float dh = inv * diff;
-                    if (cL != 0.0f) dh += cL * (yh > 0.0f ? 1.0f : (yh < 0.0f ? -1.0f : 0.0f));
-                    Dcur[b * ldd + nn] = dh * act_grad_from_h(code, yh);
+                    float dv = 0.0f;
+                    if (b < nb) {
+                        const int64_t r = r_lo + (perm ? perm[(int64_t)e * n + s0 + b] : s0 + b);
+                        const float yh = hL[nn * Bs + b];
+                        const float diff = yh - ysrc[r * T_out + nn];
+                        sq = fmaf(diff, diff, sq);
+                        float dh = inv * diff;
+                        if (cL != 0.0f) dh += cL * (yh > 0.0f ? 1.0f : (yh < 0.0f ? -1.0f : 0.0f));
+                        dv = dh * act_grad_from_h(code, yh);
+                    }
+                    Dcur[nn * Bs + b] = dv;
                 }
                 if (tid < nb && a.hist_acc) {
                     // Keras 'accuracy' on a float [B,T] target = categorical accuracy; binary at T_out == 1
@@ -196,11 +243,11 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
             const float l1_scale = a.l1_mean ? 1.0f / (float)nb : 1.0f;
             // ---- backward
             {
-                int ho = 0; int64_t po = 0;
-                int hoffs[GB200_MAX_LAYERS + 1]; int64_t poffs[GB200_MAX_LAYERS];
+                int ho = 0; int po = 0;
+                int hoffs[GB200_MAX_LAYERS + 1]; int poffs[GB200_MAX_LAYERS];
                 for (int l = 0; l < L; ++l) {
                     hoffs[l] = ho; poffs[l] = po;
-                    ho += a.arch.widths[l] * Bs; po += (int64_t)a.arch.widths[l] * a.arch.widths[l + 1] + a.arch.widths[l + 1];
+                    ho += a.arch.widths[l] * Bs; po += a.arch.widths[l] * a.arch.widths[l + 1] + a.arch.widths[l + 1];
                 }
                 hoffs[L] = ho;
                 for (int l = L - 1; l >= 0; --l) {
@@ -208,38 +255,69 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
                     float* Wl = W + poffs[l];
                     const float* hin = hbuf + hoffs[l];
                     if (l > 0) {
-                        // A: dLoss/dz_{l-1}  (reads the not-yet-updated W_l)
+                        // A: dLoss/dz_{l-1} for 4 samples per thread (reads the not-yet-updated W_l)
                         const int pcode = a.arch.acts[l - 1];
                         const float c1 = a.arch.l1[l - 1] * l1_scale;
-                        for (int i = tid; i < win * 32; i += FIT_THREADS) {
-                            const int k = i >> 5, b = i & 31;
-                            for (int bb = b; bb < nb; bb += 32) {
-                                float acc = 0.0f;
-                                for (int nn = 0; nn < wout; ++nn) acc = fmaf(Dcur[bb * ldd + nn], Wl[k * wout + nn], acc);
-                                const float h = hin[k * Bs + bb];
-                                if (c1 != 0.0f) acc += c1 * (h > 0.0f ? 1.0f : (h < 0.0f ? -1.0f : 0.0f));
-                                Dnext[bb * ldd + k] = acc * act_grad_from_h(pcode, h);
+                        for (int i = tid; i < win * Bq; i += FIT_THREADS) {
+                            const int k = i / Bq, b4 = (i - k * Bq) * 4;
+                            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                            const float* wp = Wl + k * wout; const float* dq = Dcur + b4;
+                            #pragma unroll 4
+                            for (int nn = 0; nn < wout; ++nn, ++wp, dq += Bs) {
+                                const float w = *wp;
+                                const float4 d4 = *reinterpret_cast<const float4*>(dq);
+                                a0 = fmaf(d4.x, w, a0); a1 = fmaf(d4.y, w, a1); a2 = fmaf(d4.z, w, a2); a3 = fmaf(d4.w, w, a3);
                             }
+                            const float4 h4 = *reinterpret_cast<const float4*>(hin + k * Bs + b4);
+                            const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+                            float av[4] = {a0, a1, a2, a3};
+                            #pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float acc = av[q];
+                                if (c1 != 0.0f) acc += c1 * (hv[q] > 0.0f ? 1.0f : (hv[q] < 0.0f ? -1.0f : 0.0f));
+                                av[q] = b4 + q < nb ? acc * act_grad_from_h(pcode, hv[q]) : 0.0f;
+                            }
+                            *reinterpret_cast<float4*>(Dnext + k * Bs + b4) = make_float4(av[0], av[1], av[2], av[3]);
                         }
                         __syncthreads();
                     }
-                    // B: gradients of W_l, b_l and their Adam update
+                    // B: gradients of W_l, b_l (sum over the batch, 4 samples per 16-byte read) and their Adam update
                     const int n_w = win * wout;
-                    for (int i = tid; i < n_w + wout; i += FIT_THREADS) {
-                        float g = 0.0f;
-                        if (i < n_w) {
-                            const int k = i / wout, nn = i - k * wout;
-                            for (int b = 0; b < nb; ++b) g = fmaf(hin[k * Bs + b], Dcur[b * ldd + nn], g);
-                        } else {
-                            const int nn = i - n_w;
-                            for (int b = 0; b < nb; ++b) g += Dcur[b * ldd + nn];
-                        }
-                        const int64_t p = poffs[l] + i;
+                    auto adam_update = [&](int i, float g) {
+                        const int p = poffs[l] + i;
                         float m = Mo[p], v = Vo[p];
                         m += (g - m) * (1.0f - b1);
                         v += (g * g - v) * (1.0f - b2);
                         Mo[p] = m; Vo[p] = v;
                         Wl[i] -= alpha * m / (sqrtf(v) + eps);
+                    };
+                    {
+                        // weight (k, nn) of item i, advanced without a division per item
+                        int k = tid / wout, nn = tid - k * wout;
+                        const int dk = FIT_THREADS / wout, dn = FIT_THREADS - dk * wout;
+                        for (int i = tid; i < n_w; i += FIT_THREADS) {
+                            const float4* hp = reinterpret_cast<const float4*>(hin + k * Bs);
+                            const float4* dp = reinterpret_cast<const float4*>(Dcur + nn * Bs);
+                            float g = 0.0f;
+            #define GB_FIT_DOT4(q) { const float4 h4 = hp[q], d4 = dp[q]; \
+                g = fmaf(h4.x, d4.x, g); g = fmaf(h4.y, d4.y, g); g = fmaf(h4.z, d4.z, g); g = fmaf(h4.w, d4.w, g); }
+                            if constexpr (BQ > 0) {
+                                #pragma unroll
+                                for (int q = 0; q < BQ; ++q) GB_FIT_DOT4(q)
+                            } else {
+                                for (int q = 0; q < Bq; ++q) GB_FIT_DOT4(q)
+                            }
+            #undef GB_FIT_DOT4
+                            adam_update(i, g);
+                            nn += dn; k += dk;
+                            if (nn >= wout) { nn -= wout; ++k; }
+                        }
+                    }
+                    for (int nn = tid; nn < wout; nn += FIT_THREADS) {
+                        const float4* dp = reinterpret_cast<const float4*>(Dcur + nn * Bs);
+                        float g = 0.0f;
+                        for (int q = 0; q < Bq; ++q) { const float4 d4 = dp[q]; g += d4.x; g += d4.y; g += d4.z; g += d4.w; }
+                        adam_update(n_w + nn, g);
                     }
                     __syncthreads();
                     float* tmp = Dcur; Dcur = Dnext; Dnext = tmp;
@@ -252,8 +330,8 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
         }
     }
     __syncthreads();
-    if (a.state_in_smem >= 1) for (int64_t i = tid; i < P; i += FIT_THREADS) gW[i] = W[i];
-    if (a.state_in_smem >= 2) for (int64_t i = tid; i < P; i += FIT_THREADS) { gM[i] = Mo[i]; gV[i] = Vo[i]; }
+    if (STATE >= 1) for (int64_t i = tid; i < P; i += FIT_THREADS) gW[i] = W[i];
+    if (STATE >= 2) for (int64_t i = tid; i < P; i += FIT_THREADS) { gM[i] = Mo[i]; gV[i] = Vo[i]; }
     if (tid == 0 && a.adam_t) a.adam_t[job] = t;
 }
 
@@ -275,17 +353,29 @@ int gb_launch_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int n_jo
     a.n_params = gb200_ff_param_count(arch);
     int sum_w = 0, max_w = 0;
     for (int l = 0; l <= arch->n_layers; ++l) { sum_w += arch->widths[l]; if (arch->widths[l] > max_w) max_w = arch->widths[l]; }
-    a.Bs = batch_size | 1;
-    a.ldd = max_w | 1;
+    a.Bq = (batch_size + 3) / 4;
+    a.Bs = 4 * a.Bq + 4;            // 16-byte rows; +4 keeps the 8 row groups of a warp on distinct banks
     a.h_floats = sum_w * a.Bs;
-    const size_t base = ((size_t)a.h_floats + 2 * (size_t)batch_size * a.ldd) * sizeof(float);
+    a.d_floats = max_w * a.Bs;
+    const size_t base = ((size_t)a.h_floats + 2 * (size_t)a.d_floats) * sizeof(float);
     const size_t cap = 227 * 1024 - 256;
     GB_REQUIRE(base <= cap, "ff_fit: batch_size %d x widths do not fit in shared memory", batch_size);
+    GB_REQUIRE(a.n_params < (1ll << 30), "ff_fit: topology too large");
     const size_t pbytes = (size_t)a.n_params * sizeof(float);
     a.state_in_smem = base + 3 * pbytes <= cap ? 2 : (base + pbytes <= cap ? 1 : 0);
     const size_t smem = base + (a.state_in_smem == 2 ? 3 * pbytes : a.state_in_smem == 1 ? pbytes : 0);
-    GB_CUDA_CHECK(cudaFuncSetAttribute(ff_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ff_fit_kernel<<<n_jobs, FIT_THREADS, smem, stream>>>(a);
-    GB_CUDA_CHECK(cudaGetLastError());
+    auto* kern = a.state_in_smem == 2 ? (a.Bq == 8 ? ff_fit_kernel<2, 8> : ff_fit_kernel<2, 0>)
+               : a.state_in_smem == 1 ? ff_fit_kernel<1, 0> : ff_fit_kernel<0, 0>;
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int32_t* order = nullptr;
+    if (n_jobs > 1) {
+        GB_CUDA_CHECK(cudaMallocAsync(&order, sizeof(int32_t) * n_jobs, stream));
+        fit_order_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(n_jobs, lo, hi, order);
+    }
+    a.order = order;
+    kern<<<n_jobs, FIT_THREADS, smem, stream>>>(a);
+    cudaError_t le = cudaGetLastError();
+    if (order) cudaFreeAsync(order, stream);
+    GB_CUDA_CHECK(le);
     return GB_OK;
 }
