@@ -203,7 +203,7 @@ class FleetModelBuilder:
             vfleet.set_params(params[sel]); vfleet.in_scale = in_scale[sel].contiguous()
             vfleet.in_min = in_min[sel].contiguous(); vfleet.err_scale = err_scale[sel].contiguous()
             vs = Schedule(rows_lo=te_lo, rows_hi=te_hi, rows_total=int(off[-1]))
-            prec = self.cv_precision if vfleet.tc_eligible() else "f32"
+            prec = vfleet.auto_precision(self.cv_precision)
             res = vfleet.score(vs, xd, yd, precision=prec,
                                columns=("model-output", "tag-anomaly-unscaled", "total-anomaly-scaled"))
             tl = torch.as_tensor(np.asarray(te_lo, np.int64), device=dev)

@@ -148,6 +148,16 @@ class FFFleet:
     def tc_eligible(self) -> bool:
         return N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch)) > 0
 
+    def auto_precision(self, requested: str = "bf16") -> str:
+        """
+        The scorer to launch for a caller that asked for ``requested``: the tcgen05 path when the
+        topology is eligible and wide enough to profit -- with every layer at most 8 wide (5-tag
+        Machines) the exact fp32 kernel is both faster and exact (profiles/README.md r1g).
+        """
+        if requested == "bf16" and self.tc_eligible() and max(self.topo.widths) > 8:
+            return "bf16"
+        return "f32"
+
     def packed(self) -> torch.Tensor:
         """bf16 tcgen05 operand image of the current weights (re-packed when they change)."""
         if self._packed is None or self._packed_version != self._version:

@@ -248,7 +248,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         xd = torch.as_tensor(np.ascontiguousarray(Xv, np.float32), device=dev)
         yd = None if (Xv.shape == yv.shape and np.array_equal(Xv, yv)) else \
             torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
-        prec = est._precision if fleet.tc_eligible() else "f32"
+        prec = fleet.auto_precision(est._precision)
         res = self._add_smooth_columns(fleet.score(Schedule([len(Xv)]), xd, yd, precision=prec))
         return {k: v.cpu().numpy() for k, v in res.items()}
 

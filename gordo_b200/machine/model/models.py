@@ -371,7 +371,7 @@ class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
         fleet = FFFleet(topo, 1, dev)
         fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
         xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
-        prec = self._precision if fleet.tc_eligible() else "f32"
+        prec = fleet.auto_precision(self._precision)
         return fleet.predict(Schedule([len(X)]), xd, precision=prec).cpu().numpy()
 
     def transform(self, X, **kwargs) -> np.ndarray:
