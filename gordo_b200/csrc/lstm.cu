@@ -15,6 +15,7 @@
 // lstm_wgrad (sum over batch x time as one reduction per weight), Keras-form Adam.
 // The tensor-core (tcgen05) recurrent kernel is the next step for this path.
 #include "common.cuh"
+#include "ptx.cuh"
 #include <vector>
 #include <stdlib.h>
 
@@ -488,6 +489,141 @@ lstm_bgemm_kernel(const __grid_constant__ GemmArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same batched GEMM on the tensor cores, fp32-accurate: every fp32 operand element x is split
+// into hi = tf32(x) and lo = tf32(x - hi) while it is staged into shared memory (tcgen05 canonical
+// K-major, no swizzle: [K/4][rows/8][8 rows][4 elements]) and the product is accumulated in tensor
+// memory as A_hi.B_hi + A_hi.B_lo + A_lo.B_hi (tcgen05.mma kind::tf32, fp32 accumulate; the dropped
+// lo.lo term is below 2^-21 relative).  One CTA = one 128 x 128 tile of C; two shared-memory stages
+// of K = 32: the threads stage slab i+1 (global loads issued one slab ahead, into registers) while
+// the MMAs of slab i run; a stage is reused when the tcgen05.commit of the MMAs that read it lands.
+constexpr int TK = 16;                       // K per stage
+constexpr int T_LBO = 2048 + 16;             // byte stride between K chunks of 4 (padded: bank spread)
+constexpr int T_IMG = (TK / 4) * T_LBO;      // one operand image: 128 rows x TK
+constexpr int T_STAGE = 4 * T_IMG;           // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_THREADS = 256;
+constexpr int T_ELEMS = 128 * TK / TC_THREADS;   // elements per thread per operand per slab
+
+// AK / BK: operand is k-contiguous (element (row, k) at P[row*ld + k]) or row-contiguous (P[k*ld + row]);
+// COMP: the composite (t, seq) dimension is K (weight gradients) instead of the rows of A and C.
+// Template parameters, so that the per-element index math of the staging loops folds to constants.
+template <bool AK, bool BK, bool COMP>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+lstm_bgemm_tc_kernel(const __grid_constant__ GemmArgs a) {
+    using namespace gbptx;
+    extern __shared__ __align__(128) uint8_t tsm[];
+    __shared__ __align__(8) uint64_t done[2];
+    __shared__ uint32_t s_tmem;
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    if (nb == 0) return;
+    const int sd = a.seq_dim;
+    const bool full = nb == sd;
+    const float* __restrict__ A = a.A + (size_t)grp * a.a_grp;
+    const float* __restrict__ B = a.B + (size_t)grp * a.b_grp;
+    float* C = a.C + (size_t)grp * a.c_grp;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&done[0], 1); mbar_init(&done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    // element e of this thread: (row, kk) inside the 128 x TK slab, fixed for the whole K loop
+    //   k-contiguous  : kk = tid % TK,           row = tid / TK + e * (TC_THREADS / TK)
+    //   row-contiguous: row = tid % 128,         kk  = tid / 128 + e * (TC_THREADS / 128)
+    auto row_of = [&](bool kc, int e) { return kc ? tid / TK + e * (TC_THREADS / TK) : (tid & 127); };
+    auto kk_of = [&](bool kc, int e) { return kc ? (tid & (TK - 1)) : (tid >> 7) + e * (TC_THREADS / 128); };
+    float ra[T_ELEMS], rb[T_ELEMS];
+    auto fetch = [&](int k0) {
+        #pragma unroll
+        for (int e = 0; e < T_ELEMS; ++e) {
+            const int m = m0 + row_of(AK, e), k = k0 + kk_of(AK, e);
+            float v = 0.0f;
+            if (m < a.M && k < a.K && (full || ((COMP ? k : m) % sd) < nb))
+                v = AK ? A[(size_t)m * a.lda + k] : A[(size_t)k * a.lda + m];
+            ra[e] = v;
+        }
+        #pragma unroll
+        for (int e = 0; e < T_ELEMS; ++e) {
+            const int n = n0 + row_of(BK, e), k = k0 + kk_of(BK, e);
+            float v = 0.0f;
+            if (n < a.N && k < a.K && (full || !COMP || (k % sd) < nb))
+                v = BK ? B[(size_t)n * a.ldb + k] : B[(size_t)k * a.ldb + n];
+            rb[e] = v;
+        }
+    };
+    auto put = [&](uint8_t* hi_img, uint8_t* lo_img, int row, int kk, float v) {
+        const uint32_t off = (uint32_t)(kk >> 2) * T_LBO + (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16 + (uint32_t)(kk & 3) * 4;
+        const uint32_t hi = f32_to_tf32(v);
+        const uint32_t lo = f32_to_tf32(v - __uint_as_float(hi));
+        *reinterpret_cast<uint32_t*>(hi_img + off) = hi;
+        *reinterpret_cast<uint32_t*>(lo_img + off) = lo;
+    };
+    const uint32_t idesc = make_idesc_tf32(128, 128);
+    const int nit = (a.K + TK - 1) / TK;
+    fetch(0);
+    for (int it = 0; it < nit; ++it) {
+        const int s = it & 1;
+        uint8_t* st = tsm + (size_t)s * T_STAGE;
+        if (it >= 2) mbar_wait(&done[s], (uint32_t)((it >> 1) - 1) & 1u);      // the MMAs that read this stage are done
+        #pragma unroll
+        for (int e = 0; e < T_ELEMS; ++e) put(st, st + T_IMG, row_of(AK, e), kk_of(AK, e), ra[e]);
+        #pragma unroll
+        for (int e = 0; e < T_ELEMS; ++e) put(st + 2 * T_IMG, st + 3 * T_IMG, row_of(BK, e), kk_of(BK, e), rb[e]);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (it + 1 < nit) fetch((it + 1) * TK);        // next slab's global loads fly under the MMAs
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t ah = smem_u32(st), al = ah + T_IMG, bh = ah + 2 * T_IMG, bl = ah + 3 * T_IMG;
+            #pragma unroll
+            for (int ks = 0; ks < TK / 8; ++ks) {
+                const uint32_t ko = (uint32_t)ks * 2 * T_LBO;             // K = 8 -> two chunks of 4
+                const uint64_t dah = make_desc(ah + ko, T_LBO, 128), dal = make_desc(al + ko, T_LBO, 128);
+                const uint64_t dbh = make_desc(bh + ko, T_LBO, 128), dbl = make_desc(bl + ko, T_LBO, 128);
+                umma_tf32(tmem, dal, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);    // small terms first
+                umma_tf32(tmem, dah, dbl, idesc, 1u);
+                umma_tf32(tmem, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&done[s]);
+        }
+    }
+    {
+        const int last = nit - 1;
+        mbar_wait(&done[last & 1], (uint32_t)(last >> 1) & 1u);       // a commit covers every earlier MMA of the thread
+        tc_fence_after();
+    }
+    // ---- epilogue: warp w reads lanes (w & 3) * 32 .. +31 (its tensor-memory sub-partition) of the
+    // column range (w >> 2) * (128 / (warps / 4)) .. of the accumulator
+    constexpr int CW = 128 / (TC_THREADS / 128);         // columns per warp
+    const float* bias = a.bias ? a.bias + (size_t)grp * a.bias_grp : nullptr;
+    const int m = m0 + (warp & 3) * 32 + lane;
+    const bool row_ok = m < a.M && (COMP || full || (m % sd) < nb);
+    #pragma unroll 1
+    for (int c = 0; c < CW / 16; ++c) {
+        const int col0 = (warp >> 2) * CW + c * 16;
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0, v);
+        if (row_ok) {
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + col0 + j;
+                if (n < a.N) C[(size_t)m * a.ldc + n] = v[j] + (bias ? bias[n] : 0.0f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
 // layer-0 operand of a training step, dense: xs[t][seq][k] = scale(x[rows_lo + seq_base + seq + t][k])
 __global__ void lstm_gather_x_kernel(GroupCtx g, int B, int L, int T_in, const float* __restrict__ x,
                                      const float* __restrict__ in_scale, const float* __restrict__ in_min,
@@ -597,6 +733,7 @@ __global__ void lstm_rec_fwd_kernel(const __grid_constant__ RecArgs a) {
                     acc[i] = (sq < nb && cj < nu) ? gates[((size_t)t * B + sq) * 4 * u + cg * u + j0 + cj] : 0.0f;
                 }
                 if (t > 0) {
+                    #pragma unroll 4
                     for (int k = 0; k < u; ++k) {
                         const float uv = Us[k * nc + col];
                         const float4* h4 = reinterpret_cast<const float4*>(hcur + (size_t)k * BP + sb);
@@ -704,6 +841,7 @@ __global__ void lstm_rec_bwd_kernel(const __grid_constant__ RecArgs a) {
             const int owner = jc / us, jl = jc - owner * us;
             for (int sb = sg * REC_SG; sb < BP; sb += a.NG * REC_SG) {
                 float acc[REC_SG] = {};
+                #pragma unroll 4
                 for (int n = 0; n < nc; ++n) {
                     const float uv = UT[n * u + jc];
                     const float4* d4 = reinterpret_cast<const float4*>(dzT + (size_t)n * BP + sb);
@@ -994,6 +1132,9 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
     // the per-time-step launch path stays as the fallback for very wide layers (GB200_LSTM_REC=0 forces it)
     bool use_rec = true;
     { const char* e = getenv("GB200_LSTM_REC"); if (e && atoi(e) == 0) use_rec = false; }
+    // batched GEMMs: tcgen05 3xTF32 (fp32-accurate) by default, GB200_LSTM_GEMM=simt for the CUDA-core kernel
+    bool use_tc_gemm = true;
+    { const char* e = getenv("GB200_LSTM_GEMM"); if (e && e[0] == 's') use_tc_gemm = false; }
     // sequence buffers are [t][seq][width]: t stride = B*width, seq stride = width
     auto run_step = [&](int seq_base, int cap, float* primer_out) -> int {
         GroupCtx g{d_rows_lo, d_nwin, seq_base, cap};
@@ -1002,17 +1143,26 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
         // time steps is one GEMM, the recurrence adds h_{t-1}.U step by step
         auto gemm = [&](int comp, int M, int N, int K, const float* A, int64_t a_grp, int lda, int a_kc,
                         const float* Bm, int64_t b_grp, int ldb, int b_kc, float* Cm, int64_t c_grp, int ldc,
-                        const float* bias, int64_t bias_grp) {
+                        const float* bias, int64_t bias_grp) -> int {
             GemmArgs ga{};
             ga.g = g; ga.seq_dim = B; ga.M = M; ga.N = N; ga.K = K; ga.comp = comp;
             ga.A = A; ga.a_grp = a_grp; ga.lda = lda; ga.a_kcontig = a_kc;
             ga.B = Bm; ga.b_grp = b_grp; ga.ldb = ldb; ga.b_kcontig = b_kc;
             ga.C = Cm; ga.c_grp = c_grp; ga.ldc = ldc; ga.bias = bias; ga.bias_grp = bias_grp;
+            if (use_tc_gemm && (int64_t)cdiv(N, 128) * cdiv(M, 128) * J >= 64) {      // enough 128x128 tiles to fill the GPU
+                auto* kern = comp ? lstm_bgemm_tc_kernel<false, false, true>
+                           : (b_kc ? lstm_bgemm_tc_kernel<true, true, false> : lstm_bgemm_tc_kernel<true, false, false>);
+                GB_REQUIRE(comp ? (!a_kc && !b_kc) : (a_kc != 0), "lstm gemm: operand layout combination not instantiated");
+                GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * T_STAGE));
+                kern<<<dim3(cdiv(N, 128), cdiv(M, 128), J), TC_THREADS, 2 * T_STAGE, stream>>>(ga);
+                return GB_OK;
+            }
             // big tiles once they fill the GPU, small ones for a handful of jobs
             if ((int64_t)cdiv(N, 128) * cdiv(M, 128) * J >= 148)
                 lstm_bgemm_kernel<128, 128><<<dim3(cdiv(N, 128), cdiv(M, 128), J), 256, 0, stream>>>(ga);
             else
                 lstm_bgemm_kernel<64, 64><<<dim3(cdiv(N, 64), cdiv(M, 64), J), 256, 0, stream>>>(ga);
+            return GB_OK;
         };
         {
             const int64_t tot = (int64_t)L * B * p.T_in;

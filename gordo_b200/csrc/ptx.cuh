@@ -91,6 +91,21 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
 }
 
 
+// kind::tf32: 32-bit operands (10-bit mantissa used), K = 8 per instruction; A/B format code 2
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+    uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r;
+}
+
 // ---- A operand in tensor memory (tcgen05.mma "TS" form): D[tmem] (+)= A[tmem] . B[smem].
 // A is K-major, one row per TMEM lane, bf16 pairs packed per 32-bit column (element 2j in the low half).
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
