@@ -534,11 +534,12 @@ lstm_bgemm_tc_kernel(const __grid_constant__ GemmArgs a) {
     tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    // element e of this thread: (row, kk) inside the 128 x TK slab, fixed for the whole K loop
-    //   k-contiguous  : kk = tid % TK,           row = tid / TK + e * (TC_THREADS / TK)
-    //   row-contiguous: row = tid % 128,         kk  = tid / 128 + e * (TC_THREADS / 128)
-    auto row_of = [&](bool kc, int e) { return kc ? tid / TK + e * (TC_THREADS / TK) : (tid & 127); };
-    auto kk_of = [&](bool kc, int e) { return kc ? (tid & (TK - 1)) : (tid >> 7) + e * (TC_THREADS / 128); };
+    // element i = tid + e * TC_THREADS of an operand: (row, kk) inside the 128 x TK slab, fixed for the K loop
+    //   k-contiguous  : kk = i % TK, row = i / TK               (a warp reads 2 rows x 64 B)
+    //   row-contiguous: 8 rows x 4 k per warp: row = 8 * ((i >> 5) & 15) + (i & 7), kk = 4 * (i >> 9) + ((i >> 3) & 3)
+    //                   -- 32-byte global segments, and the 32 lanes of a shared store hit 32 different banks
+    auto row_of = [&](bool kc, int e) { const int i = tid + e * TC_THREADS; return kc ? i / TK : 8 * ((i >> 5) & 15) + (i & 7); };
+    auto kk_of = [&](bool kc, int e) { const int i = tid + e * TC_THREADS; return kc ? (i & (TK - 1)) : 4 * (i >> 9) + ((i >> 3) & 3); };
     float ra[T_ELEMS], rb[T_ELEMS];
     auto fetch = [&](int k0) {
         #pragma unroll
@@ -606,6 +607,133 @@ lstm_bgemm_tc_kernel(const __grid_constant__ GemmArgs a) {
     const float* bias = a.bias ? a.bias + (size_t)grp * a.bias_grp : nullptr;
     const int m = m0 + (warp & 3) * 32 + lane;
     const bool row_ok = m < a.M && (COMP || full || (m % sd) < nb);
+    #pragma unroll 1
+    for (int c = 0; c < CW / 16; ++c) {
+        const int col0 = (warp >> 2) * CW + c * 16;
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0, v);
+        if (row_ok) {
+            #pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + col0 + j;
+                if (n < a.N) C[(size_t)m * a.ldc + n] = v[j] + (bias ? bias[n] : 0.0f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// Vector variant of the staging for GEMMs whose operands are both k-contiguous and 16-byte aligned
+// (dz.W^T: every dLoss/dx GEMM): 4 consecutive k of a row are one 16-byte global load and one 16-byte
+// core-matrix row of the K-major image.  Ragged edges and partial batches use guarded scalar loads.
+// (For row-contiguous operands two alternatives were measured and dropped: MN-major images did not
+// reproduce the K-major results, and an in-warp 4x4 shuffle transpose was slower than the scalar
+// staging with its conflict-free lane mapping -- profiles/README.md r1g.)
+constexpr int V_LBO_K = 2048 + 32;           // stride between K chunks of 4 (16 row groups x 128 B, padded: bank spread)
+constexpr int V_IMG = (TK / 4) * V_LBO_K;
+constexpr int V_STAGE = 4 * V_IMG;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+lstm_bgemm_tcv_kernel(const __grid_constant__ GemmArgs a) {
+    using namespace gbptx;
+    extern __shared__ __align__(128) uint8_t tsm[];
+    __shared__ __align__(8) uint64_t done[2];
+    __shared__ uint32_t s_tmem;
+    const int grp = blockIdx.z;
+    const int nb = group_nb(a.g, grp);
+    if (nb == 0) return;
+    const int sd = a.seq_dim;
+    const bool full = nb == sd;
+    const float* __restrict__ A = a.A + (size_t)grp * a.a_grp;
+    const float* __restrict__ B = a.B + (size_t)grp * a.b_grp;
+    float* C = a.C + (size_t)grp * a.c_grp;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&done[0], 1); mbar_init(&done[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&s_tmem, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    constexpr int UNITS = 128 * TK / 4 / TC_THREADS;        // 16-byte units per thread per operand per slab
+    // unit i = tid + e * TC_THREADS: k chunk i & 3 of row i >> 2
+    float4 ra[UNITS], rb[UNITS];
+    auto fetch_op = [&](const float* __restrict__ P, int ld, int r0, int rows, bool rows_masked, int k0, float4* out) {
+        #pragma unroll
+        for (int e = 0; e < UNITS; ++e) {
+            const int i = tid + e * TC_THREADS;
+            const int row = r0 + (i >> 2), k = k0 + (i & 3) * 4;
+            const bool row_ok = row < rows && (full || !rows_masked || (row % sd) < nb);
+            if (row_ok && k + 3 < a.K) {
+                out[e] = *reinterpret_cast<const float4*>(P + (size_t)row * ld + k);
+            } else {
+                float t[4];
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = (row_ok && k + q < a.K) ? P[(size_t)row * ld + k + q] : 0.0f;
+                out[e] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    };
+    auto fetch = [&](int k0) {
+        fetch_op(A, a.lda, m0, a.M, true, k0, ra);      // the (t, seq) mask lives on the rows of A
+        fetch_op(B, a.ldb, n0, a.N, false, k0, rb);
+    };
+    auto put = [&](uint8_t* hi_img, uint8_t* lo_img, int e, const float4& v) {
+        const int i = tid + e * TC_THREADS;
+        const int row = i >> 2;
+        const uint32_t off = (uint32_t)(i & 3) * V_LBO_K + (uint32_t)(row >> 3) * 128 + (uint32_t)(row & 7) * 16;
+        uint4 hi, lo;
+        hi.x = f32_to_tf32(v.x); hi.y = f32_to_tf32(v.y); hi.z = f32_to_tf32(v.z); hi.w = f32_to_tf32(v.w);
+        lo.x = f32_to_tf32(v.x - __uint_as_float(hi.x)); lo.y = f32_to_tf32(v.y - __uint_as_float(hi.y));
+        lo.z = f32_to_tf32(v.z - __uint_as_float(hi.z)); lo.w = f32_to_tf32(v.w - __uint_as_float(hi.w));
+        *reinterpret_cast<uint4*>(hi_img + off) = hi;
+        *reinterpret_cast<uint4*>(lo_img + off) = lo;
+    };
+    const uint32_t idesc = make_idesc_tf32(128, 128);
+    const int nit = (a.K + TK - 1) / TK;
+    fetch(0);
+    for (int it = 0; it < nit; ++it) {
+        const int s = it & 1;
+        uint8_t* st = tsm + (size_t)s * V_STAGE;
+        if (it >= 2) mbar_wait(&done[s], (uint32_t)((it >> 1) - 1) & 1u);
+        #pragma unroll
+        for (int e = 0; e < UNITS; ++e) put(st, st + V_IMG, e, ra[e]);
+        #pragma unroll
+        for (int e = 0; e < UNITS; ++e) put(st + 2 * V_IMG, st + 3 * V_IMG, e, rb[e]);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (it + 1 < nit) fetch((it + 1) * TK);
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t ah = smem_u32(st), al = ah + V_IMG, bh = ah + 2 * V_IMG, bl = ah + 3 * V_IMG;
+            #pragma unroll
+            for (int ks = 0; ks < TK / 8; ++ks) {
+                const uint32_t ko = (uint32_t)ks * 2 * V_LBO_K;             // K = 8 -> two chunks of 4
+                const uint64_t dah = make_desc(ah + ko, V_LBO_K, 128), dal = make_desc(al + ko, V_LBO_K, 128);
+                const uint64_t dbh = make_desc(bh + ko, V_LBO_K, 128), dbl = make_desc(bl + ko, V_LBO_K, 128);
+                umma_tf32(tmem, dal, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                umma_tf32(tmem, dah, dbl, idesc, 1u);
+                umma_tf32(tmem, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&done[s]);
+        }
+    }
+    {
+        const int last = nit - 1;
+        mbar_wait(&done[last & 1], (uint32_t)(last >> 1) & 1u);
+        tc_fence_after();
+    }
+    constexpr int CW = 128 / (TC_THREADS / 128);
+    const float* bias = a.bias ? a.bias + (size_t)grp * a.bias_grp : nullptr;
+    const int m = m0 + (warp & 3) * 32 + lane;
+    const bool row_ok = m < a.M && (full || (m % sd) < nb);
     #pragma unroll 1
     for (int c = 0; c < CW / 16; ++c) {
         const int col0 = (warp >> 2) * CW + c * 16;
@@ -1133,8 +1261,13 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
     bool use_rec = true;
     { const char* e = getenv("GB200_LSTM_REC"); if (e && atoi(e) == 0) use_rec = false; }
     // batched GEMMs: tcgen05 3xTF32 (fp32-accurate) by default, GB200_LSTM_GEMM=simt for the CUDA-core kernel
-    bool use_tc_gemm = true;
-    { const char* e = getenv("GB200_LSTM_GEMM"); if (e && e[0] == 's') use_tc_gemm = false; }
+    // GB200_LSTM_GEMM: "simt" CUDA-core GEMM only; "tc" / "tcs" force the tensor-core GEMM for every launch
+    // (vector / scalar staging) -- the parity tests use these; default: tensor cores from 64 tiles up
+    bool use_vec = true, use_tc_gemm = true, force_tc = false;
+    if (const char* e = getenv("GB200_LSTM_GEMM")) {
+        if (e[0] == 's') use_tc_gemm = false;
+        else if (e[0] == 't') { force_tc = true; use_vec = !(e[1] == 'c' && e[2] == 's'); }
+    }
     // sequence buffers are [t][seq][width]: t stride = B*width, seq stride = width
     auto run_step = [&](int seq_base, int cap, float* primer_out) -> int {
         GroupCtx g{d_rows_lo, d_nwin, seq_base, cap};
@@ -1149,7 +1282,16 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
             ga.A = A; ga.a_grp = a_grp; ga.lda = lda; ga.a_kcontig = a_kc;
             ga.B = Bm; ga.b_grp = b_grp; ga.ldb = ldb; ga.b_kcontig = b_kc;
             ga.C = Cm; ga.c_grp = c_grp; ga.ldc = ldc; ga.bias = bias; ga.bias_grp = bias_grp;
-            if (use_tc_gemm && (int64_t)cdiv(N, 128) * cdiv(M, 128) * J >= 64) {      // enough 128x128 tiles to fill the GPU
+            if (use_tc_gemm && (force_tc || (int64_t)cdiv(N, 128) * cdiv(M, 128) * J >= 64)) {      // enough 128x128 tiles to fill the GPU
+                // 16-byte staging when both operands are k-contiguous and every row starts 16-byte aligned
+                const bool vec = use_vec && !comp && a_kc && b_kc && lda % 4 == 0 && ldb % 4 == 0 && a_grp % 4 == 0 && b_grp % 4 == 0
+                                 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bm) & 15) == 0;
+                if (vec) {
+                    auto* kv = lstm_bgemm_tcv_kernel;
+                    GB_CUDA_CHECK(cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * V_STAGE));
+                    kv<<<dim3(cdiv(N, 128), cdiv(M, 128), J), TC_THREADS, 2 * V_STAGE, stream>>>(ga);
+                    return GB_OK;
+                }
                 auto* kern = comp ? lstm_bgemm_tc_kernel<false, false, true>
                            : (b_kc ? lstm_bgemm_tc_kernel<true, true, false> : lstm_bgemm_tc_kernel<true, false, false>);
                 GB_REQUIRE(comp ? (!a_kc && !b_kc) : (a_kc != 0), "lstm gemm: operand layout combination not instantiated");
