@@ -56,7 +56,8 @@ def test_rolling_min_max_matches_pandas(window):
 
 
 @pytest.mark.parametrize("T,func,l1_mean,batch", [(10, "tanh", False, 32), (50, "tanh", False, 32),
-                                                   (7, "relu", True, 16), (5, "sigmoid", False, 32)])
+                                                   (7, "relu", True, 16), (5, "sigmoid", False, 32),
+                                                   (6, "tanh", False, 10), (9, "tanh", True, 33)])      # batches that are not multiples of 4
 def test_ff_fit_matches_oracle(T, func, l1_mean, batch):
     from gordo_b200.fleet import FFFleet, FFTopology
     rng = np.random.default_rng(100 + T)
