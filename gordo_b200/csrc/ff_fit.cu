@@ -11,8 +11,8 @@
 //   gather  : h0[k][b] = x[row_b][k]*scale+min            (rows given by the permutation)
 //   forward : h_{l+1}[n][b] = act(b_l[n] + sum_k h_l[k][b] W_l[k][n])
 //   loss    : D_L[b][n] = dLoss/dz_L, MSE / accuracy / L1 sums
-//   backward, l = L-1..0:  A: D_{l-1}[b][k] = (sum_n D_l[b][n] W_l[k][n] + l1 sign(h)) act'(h)
-//                          B: g = sum_b h_l[k][b] D_l[b][n]  -> Adam update of W_l[k][n], b_l[n]
+//   deltas  : l = L-1..1:  D_l = (D_{l+1} . W_l^T + l1 sign(h_l)) act'(h_l)     (every D_l kept)
+//   update  : one barrier-free sweep over all layers: g = sum_b h_l[k][b] D_{l+1}[n][b] -> Adam update of W_l[k][n], b_l[n]
 // Layouts: h and D feature-major [w][Bs], Bs a multiple of 4: a thread owns 4 consecutive samples of
 // one feature (forward, backward A) or one weight (backward B), reads activations / deltas as 16-byte
 // words along the batch and a weight once per 4 FMAs; samples past the batch end carry zero deltas.
@@ -35,7 +35,6 @@ struct FitArgs {
     int64_t n_params;
     int state_in_smem;      // 2: W,m,v in smem  1: W in smem  0: all global
     int h_floats;           // sum_l w_l * Bs
-    int d_floats;           // max_l w_l * Bs
     int Bs;                 // sample stride of h and D (multiple of 4: 16-byte reads along the batch)
     int Bq;                 // 4-sample groups per batch
     const int32_t* order;   // CTA -> job, longest job first
@@ -100,9 +99,8 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
     const int64_t P = a.n_params;
 
     float* hbuf = smem;                               // all layer activations of the batch
-    float* D0 = hbuf + a.h_floats;                    // [max_w][Bs]
-    float* D1 = D0 + a.d_floats;
-    float* st = D1 + a.d_floats;                      // optional on-chip W / m / v
+    float* Dall = hbuf + a.h_floats;                  // dLoss/dz of every layer, laid out like hbuf
+    float* st = Dall + a.h_floats;                    // optional on-chip W / m / v
     float* gW = a.params + (size_t)job * P;
     float* gM = a.adam_mv + (size_t)job * 2 * P;
     float* gV = gM + P;
@@ -179,13 +177,17 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
                 }
             }
             // ---- loss, dLoss/dz_L, accuracy
-            const float* hL;
+            int hoffs[GB200_MAX_LAYERS + 1]; int poffs[GB200_MAX_LAYERS];
             {
-                int ho = 0;
-                for (int l = 0; l < L; ++l) ho += a.arch.widths[l] * Bs;
-                hL = hbuf + ho;
+                int ho = 0, po = 0;
+                for (int l = 0; l < L; ++l) {
+                    hoffs[l] = ho; poffs[l] = po;
+                    ho += a.arch.widths[l] * Bs; po += a.arch.widths[l] * a.arch.widths[l + 1] + a.arch.widths[l + 1];
+                }
+                hoffs[L] = ho;
             }
-            float* Dcur = D0; float* Dnext = D1;
+            const float* hL = hbuf + hoffs[L];
+            float* DL = Dall + hoffs[L];
             float sq = 0.0f;
             {
                 const float inv = 2.0f / (float)(nb * T_out);
@@ -205,7 +207,7 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
                         if (cL != 0.0f) dh += cL * (yh > 0.0f ? 1.0f : (yh < 0.0f ? -1.0f : 0.0f));
                         dv = dh * act_grad_from_h(code, yh);
                     }
-                    Dcur[nn * Bs + b] = dv;
+                    DL[nn * Bs + b] = dv;
                 }
                 if (tid < nb && a.hist_acc) {
                     // Keras 'accuracy' on a float [B,T] target = categorical accuracy; binary at T_out == 1
@@ -241,88 +243,85 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
             const float tf = (float)t;
             const float alpha = lr * sqrtf(1.0f - powf(b2, tf)) / (1.0f - powf(b1, tf));
             const float l1_scale = a.l1_mean ? 1.0f / (float)nb : 1.0f;
-            // ---- backward
-            {
-                int ho = 0; int po = 0;
-                int hoffs[GB200_MAX_LAYERS + 1]; int poffs[GB200_MAX_LAYERS];
-                for (int l = 0; l < L; ++l) {
-                    hoffs[l] = ho; poffs[l] = po;
-                    ho += a.arch.widths[l] * Bs; po += a.arch.widths[l] * a.arch.widths[l + 1] + a.arch.widths[l + 1];
+            // ---- backward, deltas first: D_l = (D_{l+1} . W_l^T + l1 sign(h_l)) act'(h_l) for l = L-1 .. 1,
+            // every delta kept (one slot per activation) and every W still the forward pass's
+            for (int l = L - 1; l >= 1; --l) {
+                const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
+                const float* Wl = W + poffs[l];
+                const float* hin = hbuf + hoffs[l];
+                const float* Dcur = Dall + hoffs[l + 1];
+                float* Dnext = Dall + hoffs[l];
+                const int pcode = a.arch.acts[l - 1];
+                const float c1 = a.arch.l1[l - 1] * l1_scale;
+                for (int i = tid; i < win * Bq; i += FIT_THREADS) {
+                    const int k = i / Bq, b4 = (i - k * Bq) * 4;
+                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                    const float* wp = Wl + k * wout; const float* dq = Dcur + b4;
+                    #pragma unroll 4
+                    for (int nn = 0; nn < wout; ++nn, ++wp, dq += Bs) {
+                        const float w = *wp;
+                        const float4 d4 = *reinterpret_cast<const float4*>(dq);
+                        a0 = fmaf(d4.x, w, a0); a1 = fmaf(d4.y, w, a1); a2 = fmaf(d4.z, w, a2); a3 = fmaf(d4.w, w, a3);
+                    }
+                    const float4 h4 = *reinterpret_cast<const float4*>(hin + k * Bs + b4);
+                    const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+                    float av[4] = {a0, a1, a2, a3};
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float acc = av[q];
+                        if (c1 != 0.0f) acc += c1 * (hv[q] > 0.0f ? 1.0f : (hv[q] < 0.0f ? -1.0f : 0.0f));
+                        av[q] = b4 + q < nb ? acc * act_grad_from_h(pcode, hv[q]) : 0.0f;
+                    }
+                    *reinterpret_cast<float4*>(Dnext + k * Bs + b4) = make_float4(av[0], av[1], av[2], av[3]);
                 }
-                hoffs[L] = ho;
-                for (int l = L - 1; l >= 0; --l) {
-                    const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
-                    float* Wl = W + poffs[l];
-                    const float* hin = hbuf + hoffs[l];
-                    if (l > 0) {
-                        // A: dLoss/dz_{l-1} for 4 samples per thread (reads the not-yet-updated W_l)
-                        const int pcode = a.arch.acts[l - 1];
-                        const float c1 = a.arch.l1[l - 1] * l1_scale;
-                        for (int i = tid; i < win * Bq; i += FIT_THREADS) {
-                            const int k = i / Bq, b4 = (i - k * Bq) * 4;
-                            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                            const float* wp = Wl + k * wout; const float* dq = Dcur + b4;
-                            #pragma unroll 4
-                            for (int nn = 0; nn < wout; ++nn, ++wp, dq += Bs) {
-                                const float w = *wp;
-                                const float4 d4 = *reinterpret_cast<const float4*>(dq);
-                                a0 = fmaf(d4.x, w, a0); a1 = fmaf(d4.y, w, a1); a2 = fmaf(d4.z, w, a2); a3 = fmaf(d4.w, w, a3);
-                            }
-                            const float4 h4 = *reinterpret_cast<const float4*>(hin + k * Bs + b4);
-                            const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
-                            float av[4] = {a0, a1, a2, a3};
-                            #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                float acc = av[q];
-                                if (c1 != 0.0f) acc += c1 * (hv[q] > 0.0f ? 1.0f : (hv[q] < 0.0f ? -1.0f : 0.0f));
-                                av[q] = b4 + q < nb ? acc * act_grad_from_h(pcode, hv[q]) : 0.0f;
-                            }
-                            *reinterpret_cast<float4*>(Dnext + k * Bs + b4) = make_float4(av[0], av[1], av[2], av[3]);
-                        }
-                        __syncthreads();
-                    }
-                    // B: gradients of W_l, b_l (sum over the batch, 4 samples per 16-byte read) and their Adam update
-                    const int n_w = win * wout;
-                    auto adam_update = [&](int i, float g) {
-                        const int p = poffs[l] + i;
-                        float m = Mo[p], v = Vo[p];
-                        m += (g - m) * (1.0f - b1);
-                        v += (g * g - v) * (1.0f - b2);
-                        Mo[p] = m; Vo[p] = v;
-                        Wl[i] -= alpha * m / (sqrtf(v) + eps);
-                    };
-                    {
-                        // weight (k, nn) of item i, advanced without a division per item
-                        int k = tid / wout, nn = tid - k * wout;
-                        const int dk = FIT_THREADS / wout, dn = FIT_THREADS - dk * wout;
-                        for (int i = tid; i < n_w; i += FIT_THREADS) {
-                            const float4* hp = reinterpret_cast<const float4*>(hin + k * Bs);
-                            const float4* dp = reinterpret_cast<const float4*>(Dcur + nn * Bs);
-                            float g = 0.0f;
-            #define GB_FIT_DOT4(q) { const float4 h4 = hp[q], d4 = dp[q]; \
-                g = fmaf(h4.x, d4.x, g); g = fmaf(h4.y, d4.y, g); g = fmaf(h4.z, d4.z, g); g = fmaf(h4.w, d4.w, g); }
-                            if constexpr (BQ > 0) {
-                                #pragma unroll
-                                for (int q = 0; q < BQ; ++q) GB_FIT_DOT4(q)
-                            } else {
-                                for (int q = 0; q < Bq; ++q) GB_FIT_DOT4(q)
-                            }
-            #undef GB_FIT_DOT4
-                            adam_update(i, g);
-                            nn += dn; k += dk;
-                            if (nn >= wout) { nn -= wout; ++k; }
-                        }
-                    }
-                    for (int nn = tid; nn < wout; nn += FIT_THREADS) {
+                __syncthreads();
+            }
+            // ---- then ONE sweep over all weights of all layers: gradient (sum over the batch, 4 samples per
+            // 16-byte read) and Adam update in place.  No barrier between layers: nothing read here is written here.
+            for (int l = 0; l < L; ++l) {
+                const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
+                float* Wl = W + poffs[l];
+                const float* hin = hbuf + hoffs[l];
+                const float* Dcur = Dall + hoffs[l + 1];
+                const int n_w = win * wout;
+                auto adam_update = [&](int i, float g) {
+                    const int p = poffs[l] + i;
+                    float m = Mo[p], v = Vo[p];
+                    m += (g - m) * (1.0f - b1);
+                    v += (g * g - v) * (1.0f - b2);
+                    Mo[p] = m; Vo[p] = v;
+                    Wl[i] -= alpha * m / (sqrtf(v) + eps);
+                };
+                {
+                    // weight (k, nn) of item i, advanced without a division per item
+                    int k = tid / wout, nn = tid - k * wout;
+                    const int dk = FIT_THREADS / wout, dn = FIT_THREADS - dk * wout;
+                    for (int i = tid; i < n_w; i += FIT_THREADS) {
+                        const float4* hp = reinterpret_cast<const float4*>(hin + k * Bs);
                         const float4* dp = reinterpret_cast<const float4*>(Dcur + nn * Bs);
                         float g = 0.0f;
-                        for (int q = 0; q < Bq; ++q) { const float4 d4 = dp[q]; g += d4.x; g += d4.y; g += d4.z; g += d4.w; }
-                        adam_update(n_w + nn, g);
+            #define GB_FIT_DOT4(q) { const float4 h4 = hp[q], d4 = dp[q]; \
+                g = fmaf(h4.x, d4.x, g); g = fmaf(h4.y, d4.y, g); g = fmaf(h4.z, d4.z, g); g = fmaf(h4.w, d4.w, g); }
+                        if constexpr (BQ > 0) {
+                            #pragma unroll
+                            for (int q = 0; q < BQ; ++q) GB_FIT_DOT4(q)
+                        } else {
+                            for (int q = 0; q < Bq; ++q) GB_FIT_DOT4(q)
+                        }
+            #undef GB_FIT_DOT4
+                        adam_update(i, g);
+                        nn += dn; k += dk;
+                        if (nn >= wout) { nn -= wout; ++k; }
                     }
-                    __syncthreads();
-                    float* tmp = Dcur; Dcur = Dnext; Dnext = tmp;
+                }
+                for (int nn = tid; nn < wout; nn += FIT_THREADS) {
+                    const float4* dp = reinterpret_cast<const float4*>(Dcur + nn * Bs);
+                    float g = 0.0f;
+                    for (int q = 0; q < Bq; ++q) { const float4 d4 = dp[q]; g += d4.x; g += d4.y; g += d4.z; g += d4.w; }
+                    adam_update(n_w + nn, g);
                 }
             }
+            __syncthreads();
         }
         if (tid == 0) {
             if (a.hist_loss) a.hist_loss[(size_t)job * a.epochs + e] = n > 0 ? (float)(loss_acc / n) : NAN;
@@ -351,13 +350,12 @@ int gb_launch_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int n_jo
     a.epochs = epochs; a.batch = batch_size; a.l1_mean = l1_mean;
     a.params = params; a.adam_mv = adam_mv; a.adam_t = adam_t; a.hist_loss = hist_loss; a.hist_acc = hist_acc;
     a.n_params = gb200_ff_param_count(arch);
-    int sum_w = 0, max_w = 0;
-    for (int l = 0; l <= arch->n_layers; ++l) { sum_w += arch->widths[l]; if (arch->widths[l] > max_w) max_w = arch->widths[l]; }
+    int sum_w = 0;
+    for (int l = 0; l <= arch->n_layers; ++l) sum_w += arch->widths[l];
     a.Bq = (batch_size + 3) / 4;
     a.Bs = 4 * a.Bq + 4;            // 16-byte rows; +4 keeps the 8 row groups of a warp on distinct banks
     a.h_floats = sum_w * a.Bs;
-    a.d_floats = max_w * a.Bs;
-    const size_t base = ((size_t)a.h_floats + 2 * (size_t)a.d_floats) * sizeof(float);
+    const size_t base = 2 * (size_t)a.h_floats * sizeof(float);      // activations + one delta slot per activation
     const size_t cap = 227 * 1024 - 256;
     GB_REQUIRE(base <= cap, "ff_fit: batch_size %d x widths do not fit in shared memory", batch_size);
     GB_REQUIRE(a.n_params < (1ll << 30), "ff_fit: topology too large");
