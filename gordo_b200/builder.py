@@ -94,7 +94,7 @@ class FleetModelBuilder:
     # ------------------------------------------------------------------ bucketing
     @staticmethod
     def _standard_parts(model):
-        if type(model) is not DiffBasedAnomalyDetector or model.window is not None or model.shuffle:
+        if type(model) is not DiffBasedAnomalyDetector or model.shuffle:
             return None
         if not isinstance(model.scaler, MinMaxScaler):
             return None
@@ -117,11 +117,11 @@ class FleetModelBuilder:
         if isinstance(est, KerasLSTMBaseEstimator):
             return ("lstm", type(est).__name__, topo.key(), int(est.kwargs.get("epochs", 1)), int(est.batch_size),
                     mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
-                    tuple(sorted(topo.adam.items())), est.kwargs.get("precision", "f32"))
+                    tuple(sorted(topo.adam.items())), est.kwargs.get("precision", "f32"), model.window)
         fit = (int(est.kwargs.get("epochs", 1)), int(est.kwargs.get("batch_size") or 32),
                bool(est.kwargs.get("shuffle", True)), est.kwargs.get("l1_batch_norm", "sum"),
                mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
-               tuple(sorted(topo.adam.items())))
+               tuple(sorted(topo.adam.items())), model.window)
         return (topo.key(), fit)
 
     # ------------------------------------------------------------------ one-at-a-time fallback
@@ -195,6 +195,8 @@ class FleetModelBuilder:
         t_fit = time.time() - t_start
 
         feat_pf = agg_pf = None
+        win = protos[0].window
+        sfeat_h = sagg_h = None
         if k:
             # score every test fold with its fold model: virtual Machines over sub-ranges
             fold_jobs = np.array([m * per + i for m in range(M) for i in range(k)])
@@ -210,6 +212,9 @@ class FleetModelBuilder:
             th = torch.as_tensor(np.asarray(te_hi, np.int64), device=dev)
             feat_pf = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], tl, th, 6).reshape(M, k, To)
             agg_pf = FFFleet.rolling_min_max(res["total-anomaly-scaled"], tl, th, 6).reshape(M, k)
+            if win is not None:         # the "smooth" thresholds: same statistic over rolling(window) (diff.py:241-248)
+                sfeat_h = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], tl, th, win).reshape(M, k, To).double().cpu().numpy()
+                sagg_h = FFFleet.rolling_min_max(res["total-anomaly-scaled"], tl, th, win).reshape(M, k).double().cpu().numpy()
             # the builder's CV metrics (build_model.py:245-289): scoring scaler = MinMaxScaler fitted on the
             # full y of each Machine = the final job's error scaler
             full_scale = err_scale[torch.arange(M, device=dev) * per + k].double().cpu().numpy()
@@ -249,12 +254,9 @@ class FleetModelBuilder:
             if k:
                 model.feature_thresholds_per_fold_ = pd.DataFrame(feat_h[m], index=[f"fold-{i}" for i in range(k)], columns=tags)
                 model.aggregate_thresholds_per_fold_ = {f"fold-{i}": float(agg_h[m, i]) for i in range(k)}
-                model.smooth_feature_thresholds_per_fold_ = pd.DataFrame()
-                model.smooth_aggregate_thresholds_per_fold_ = {}
                 model.feature_thresholds_ = pd.Series(feat_h[m, -1], index=tags, name=f"fold-{k - 1}")
                 model.aggregate_threshold_ = float(agg_h[m, -1])
-                model.smooth_aggregate_threshold_ = None
-                model.smooth_feature_thresholds_ = None
+                _set_smooth_thresholds(model, None if sfeat_h is None else sfeat_h[m], None if sagg_h is None else sagg_h[m], tags, k)
             scores = _cv_score_dict({kk: v[m * k:(m + 1) * k] for kk, v in cv_metrics.items()}, tags) if k else {}
             meta = {"name": mc.name, "model_offset": 0, "model": model.get_metadata(),
                     "cross_validation": {"scores": scores,
@@ -265,6 +267,20 @@ class FleetModelBuilder:
                     "cv_fold_history": {f"fold-{i}": {"loss": [float(v) for v in hl_h[m * per + i]]} for i in range(k)}}
             out.append((model, meta))
         return out
+
+
+def _set_smooth_thresholds(model, sfeat, sagg, tags, k):
+    """The ``smooth_*`` threshold attributes of diff.py:241-264 ([k, T] / [k] arrays, or None without a window)."""
+    if sfeat is None:
+        model.smooth_feature_thresholds_per_fold_ = pd.DataFrame()
+        model.smooth_aggregate_thresholds_per_fold_ = {}
+        model.smooth_aggregate_threshold_ = None
+        model.smooth_feature_thresholds_ = None
+        return
+    model.smooth_feature_thresholds_per_fold_ = pd.DataFrame(sfeat, index=[f"fold-{i}" for i in range(k)], columns=tags)
+    model.smooth_aggregate_thresholds_per_fold_ = {f"fold-{i}": float(sagg[i]) for i in range(k)}
+    model.smooth_feature_thresholds_ = pd.Series(sfeat[-1], index=tags, name=f"fold-{k - 1}")
+    model.smooth_aggregate_threshold_ = float(sagg[-1])
 
 
 def _build_bucket_lstm_impl(self, mcs, protos, dev):
@@ -318,6 +334,11 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
         ol = torch.as_tensor(out_off[:-1].copy(), device=dev); oh = torch.as_tensor(out_off[1:].copy(), device=dev)
         feat_h = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], ol, oh, 6).reshape(M, k, To).double().cpu().numpy()
         agg_h = FFFleet.rolling_min_max(res["total-anomaly-scaled"], ol, oh, 6).reshape(M, k).double().cpu().numpy()
+        win = protos[0].window
+        sfeat_h = sagg_h = None
+        if win is not None:
+            sfeat_h = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], ol, oh, win).reshape(M, k, To).double().cpu().numpy()
+            sagg_h = FFFleet.rolling_min_max(res["total-anomaly-scaled"], ol, oh, win).reshape(M, k).double().cpu().numpy()
     torch.cuda.synchronize()
     t_total = time.time() - t0
     P_host = params.cpu().numpy(); hl_h = hl.cpu().numpy(); pl_h = pl.cpu().numpy()
@@ -338,12 +359,9 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
         if k:
             model.feature_thresholds_per_fold_ = pd.DataFrame(feat_h[m], index=[f"fold-{i}" for i in range(k)], columns=tags)
             model.aggregate_thresholds_per_fold_ = {f"fold-{i}": float(agg_h[m, i]) for i in range(k)}
-            model.smooth_feature_thresholds_per_fold_ = pd.DataFrame()
-            model.smooth_aggregate_thresholds_per_fold_ = {}
             model.feature_thresholds_ = pd.Series(feat_h[m, -1], index=tags, name=f"fold-{k - 1}")
             model.aggregate_threshold_ = float(agg_h[m, -1])
-            model.smooth_aggregate_threshold_ = None
-            model.smooth_feature_thresholds_ = None
+            _set_smooth_thresholds(model, None if sfeat_h is None else sfeat_h[m], None if sagg_h is None else sagg_h[m], tags, k)
         meta = {"name": mc.name, "model_offset": L - 1 + lookahead, "model": model.get_metadata(),
                 "fleet": {"machines_in_launch": M, "fit_jobs": J, "build_duration_sec": t_total}}
         out_models.append((model, meta))

@@ -38,7 +38,7 @@ def _rolling_min_max(values: np.ndarray, window: int):
     """`.rolling(window).min().max()` per column on the GPU (gb200_rolling_min_max)."""
     import torch
     from gordo_b200.fleet import FFFleet
-    v = np.ascontiguousarray(values, np.float32)
+    v = np.array(values, dtype=np.float32, order="C")          # private writable copy for torch
     one_d = v.ndim == 1
     if one_d:
         v = v[:, None]

@@ -271,3 +271,36 @@ def test_validation_split_val_loss_and_early_stopping():
     assert isinstance(EarlyStopping(monitor="val_accuracy").mode, str) and EarlyStopping(monitor="val_accuracy").mode == "max"
     with pytest.raises(NotImplementedError):
         KerasAutoEncoder(kind="feedforward_hourglass", callbacks=["keras.callbacks.TensorBoard"]).fit(Xs, Xs)
+
+
+def test_fleet_builder_smooth_thresholds_with_window():
+    """Detectors with ``window`` stay in the batched build: smooth thresholds = rolling(window).min().max() of the fold errors."""
+    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.fleet import FFTopology
+    T, rows, W = 5, [420, 377], 12
+    Xs = [_data(50 + i, n, T) for i, n in enumerate(rows)]
+    defn = {"gordo_b200.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"window": W, "smoothing_method": "sma", "base_estimator": {
+        "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler",
+            {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "shuffle": False}}]}}}}
+    mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=[f"t{j}" for j in range(T)]), model=defn,
+                        evaluation={"seed": 9}) for i, X in enumerate(Xs)]
+    built = FleetModelBuilder(mcs).build()
+    spec = factories.feedforward_hourglass(T)
+    topo = FFTopology(spec["widths"], spec["acts"], spec["l1"])
+    gen = torch.Generator(device="cuda:0"); gen.manual_seed(9)
+    init = topo.glorot_init(len(rows) * 4, gen, torch.device("cuda:0")).cpu().numpy()
+    for m, ((model, meta), X) in enumerate(zip(built, Xs)):
+        assert meta["fleet"]["machines_in_launch"] == 2               # batched, not the per-Machine fallback
+        Xd = X.astype(np.float64)
+        det = DiffDetector(lambda tag, m=m: FFBase(spec, dense.ff_unflatten(
+            init[m * 4 + (3 if tag == "final" else int(tag[-1]))], spec["widths"]), perms=None),
+            window=W, smoothing_method="sma")
+        det.cross_validate(Xd, Xd); det.fit(Xd, Xd)
+        np.testing.assert_allclose(model.smooth_feature_thresholds_.to_numpy(), det.smooth_feature_thresholds_, rtol=5e-3, atol=1e-5)
+        np.testing.assert_allclose(model.smooth_aggregate_threshold_, det.smooth_aggregate_threshold_, rtol=5e-3)
+        assert list(model.smooth_feature_thresholds_per_fold_.index) == ["fold-0", "fold-1", "fold-2"]
+        assert "smooth-aggregate-threshold" in model.get_metadata()
+        frame = model.anomaly(mcs[m].X, mcs[m].X)
+        want = det.anomaly(Xd, Xd)
+        np.testing.assert_allclose(frame["smooth-total-anomaly-scaled"].to_numpy().ravel(),
+                                   want["smooth-total-anomaly-scaled"], rtol=2e-2, atol=1e-6, equal_nan=True)
