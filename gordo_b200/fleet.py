@@ -97,6 +97,22 @@ class Schedule:
     def handle(self):
         return self._h
 
+    _single: "Dict[tuple, Schedule]" = {}
+
+    @classmethod
+    def single(cls, n_rows: int) -> "Schedule":
+        """
+        One Machine of ``n_rows`` rows, cached per (device, row count): a request path scores the same
+        few frame lengths again and again, and creating a schedule costs device allocations.
+        """
+        key = (torch.cuda.current_device(), int(n_rows))
+        sch = cls._single.get(key)
+        if sch is None:
+            if len(cls._single) >= 64:
+                cls._single.pop(next(iter(cls._single)))
+            sch = cls._single[key] = cls([int(n_rows)])
+        return sch
+
     def __del__(self):
         try:
             if self._h:

@@ -67,11 +67,18 @@ def assemble_frame(groups, index, frequency: Optional[timedelta]) -> pd.DataFram
         else:
             cols.extend((name, s) for s in names); numeric.append(v)
     block = np.hstack([a.astype(np.float64, copy=False) for a in numeric]) if numeric else np.empty((n, 0))
-    df = pd.DataFrame(block, index=idx, columns=pd.MultiIndex.from_tuples(cols[2:]))
-    df.insert(0, ("end", ""), pd.Series(end, index=idx, dtype=object))
-    df.insert(0, ("start", ""), pd.Series(start, index=idx, dtype=object))
-    df.columns = pd.MultiIndex.from_tuples(cols)
+    mi_full = _column_index(tuple(cols))
+    times = np.empty((n, 2), dtype=object)
+    times[:, 0] = start; times[:, 1] = end
+    # two homogeneous blocks (object times, float64 values) side by side; the column index is cached
+    df = pd.concat([pd.DataFrame(times, index=idx), pd.DataFrame(block, index=idx)], axis=1)
+    df.columns = mi_full
     return df
+
+
+@functools.lru_cache(maxsize=64)
+def _column_index(cols: tuple) -> pd.MultiIndex:
+    return pd.MultiIndex.from_tuples(list(cols))
 
 
 def make_base_dataframe(tags, model_input: np.ndarray, model_output: np.ndarray,

@@ -304,3 +304,28 @@ def test_fleet_builder_smooth_thresholds_with_window():
         want = det.anomaly(Xd, Xd)
         np.testing.assert_allclose(frame["smooth-total-anomaly-scaled"].to_numpy().ravel(),
                                    want["smooth-total-anomaly-scaled"], rtol=2e-2, atol=1e-6, equal_nan=True)
+
+
+def test_serving_cache_follows_the_model():
+    """The device-side copy kept between .anomaly() calls is rebuilt when thresholds, scalers or weights change."""
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_b200.machine.model.models import KerasAutoEncoder
+    X = pd.DataFrame(_data(60, 300, 4), columns=list("abcd")); X2 = pd.DataFrame(_data(61, 300, 4) * 3 + 1, columns=list("abcd"))
+    np.random.seed(1)
+    det = DiffBasedAnomalyDetector(base_estimator=Pipeline([("s", MinMaxScaler()), ("m", KerasAutoEncoder(kind="feedforward_hourglass"))]))
+    det.cross_validate(X=X, y=X); det.fit(X, X)
+    f1 = det.anomaly(X, X); f1b = det.anomaly(X, X)
+    pd.testing.assert_frame_equal(f1, f1b)
+    assert "_gb200_serving" in det.__dict__
+    det.aggregate_threshold_ = det.aggregate_threshold_ * 2.0
+    f2 = det.anomaly(X, X)
+    np.testing.assert_allclose(f2["total-anomaly-confidence"].to_numpy(), f1["total-anomaly-confidence"].to_numpy() / 2.0, rtol=1e-6)
+    np.testing.assert_array_equal(f2["model-output"].to_numpy(), f1["model-output"].to_numpy())
+    det.fit(X2, X2)                                  # new weights and new scalers
+    f3 = det.anomaly(X, X)
+    assert np.abs(f3["model-output"].to_numpy() - f1["model-output"].to_numpy()).max() > 1e-3
+    clone = pickle.loads(pickle.dumps(det))
+    assert "_gb200_serving" not in clone.__dict__ and "_gb200_serving" not in clone.base_estimator.steps[1][1].__dict__
+    pd.testing.assert_frame_equal(clone.anomaly(X, X), f3)
+    # a different frame length reuses the cached weights with another schedule
+    assert len(det.anomaly(X.iloc[:37], X.iloc[:37])) == 37
