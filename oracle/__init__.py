@@ -32,5 +32,10 @@ UNPINNED   : Dense / LSTM forward values, loss history, Adam trajectories: Tenso
              reference's tests hold no golden weight / output for any Keras model.  For
              those the oracle restates the published Keras 3.3.3 algorithms; "parity
              unpinned" -- see DESIGN.md.  The hand-written backward passes are cross-checked
-             against torch autograd on CPU (tests/test_oracle_grad.py).
+             against torch autograd on CPU (tests/test_oracle_grad.py), and the restated
+             algorithms against a second framework's own implementations: the stacked LSTM
+             forward / windowing / BPTT against ``torch.nn.LSTM``, the Dense training
+             trajectory against ``torch.nn.Linear`` + ``torch.optim.Adam``
+             (tests/test_oracle_torch_xcheck.py; Keras' epsilon placement is the one known
+             difference).  Also pinned: DiffBasedKFCVAnomalyDetector (tests/golden/kfcv_golden.npz).
 """
