@@ -6,14 +6,19 @@
 // a launch is window `seq_base + b` of its Machine, i.e. rows [start, start+L) of the Machine's
 // sample matrix, scaled on the fly (MinMaxScaler.transform fused into the layer-0 operand load).
 //
-// This round: exact fp32 arithmetic on CUDA cores, time-step-synchronous over all stacked layers
-// (state per layer, no [B,L,u] sequence buffers for inference):
+// Inference (this file: exact fp32; lstm_tc.cu: the tcgen05 pipeline):
 //   lstm_step_fwd      one (layer, t): tiled GEMM [seq x (in+u)] x [(in+u) x 4u] with the gate
 //                      non-linearities, cell update and h = o*act(c) fused in the epilogue
 //   lstm_dense_out     yhat = out_act(h_last . Wd + bd)
-// training adds the cached-activation forward, lstm_bwd_gates / lstm_bwd_data (BPTT),
-// lstm_wgrad (sum over batch x time as one reduction per weight), Keras-form Adam.
-// The tensor-core (tcgen05) recurrent kernel is the next step for this path.
+// Training (KerasLSTMBaseEstimator.fit, J jobs per launch), split by what is sequential:
+//   lstm_bgemm_tc[v]   everything that is not the recurrence -- x_t.W + b for all t, dz.W^T for all t,
+//                      the weight gradients over (t, seq) -- as batched GEMMs on tcgen05 (kind::tf32,
+//                      3xTF32 split: fp32-accurate); lstm_bgemm (CUDA cores) for small launches
+//   lstm_rec_fwd/bwd   the recurrence of a whole layer in one launch: a thread-block cluster per job,
+//                      U slices resident in shared memory, h_t / partial dh_rec exchanged through DSMEM
+//   lstm_step_fwd / lstm_bwd_gates / lstm_nt   the per-time-step launch path, kept for layers wider than
+//                      the cluster kernels take and as their parity reference (GB200_LSTM_REC=0)
+//   Keras-form Adam, loss history on the device.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <vector>

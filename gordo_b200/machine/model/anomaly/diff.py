@@ -304,15 +304,23 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         from gordo_b200.fleet import FFFleet, Schedule
         from gordo_b200.lstm import LSTMFleet
         topo = est.model.topology
-        fleet = LSTMFleet(topo, 1, est.lookahead, dev)
-        fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
-        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)[None], device=dev)
-        if sc is not None:
-            fleet.in_scale, fleet.in_min = f32(sc.scale_), f32(sc.min_)
+        f32 = lambda a: torch.as_tensor(np.array(a, np.float32)[None], device=dev)
+        parts = [est.model.params] + ([np.asarray(sc.scale_), np.asarray(sc.min_)] if sc is not None else [])
+        key = (dev.index, id(est.model), est.lookahead, sc is None,
+               hash(b"".join(np.ascontiguousarray(a).tobytes() for a in parts)))
+        cached = self.__dict__.get("_gb200_serving_lstm")
+        if cached is not None and cached[0] == key:
+            fleet = cached[1]
+        else:
+            fleet = LSTMFleet(topo, 1, est.lookahead, dev)
+            fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
+            if sc is not None:
+                fleet.in_scale, fleet.in_min = f32(sc.scale_), f32(sc.min_)
+            self.__dict__["_gb200_serving_lstm"] = (key, fleet)
         xd = torch.as_tensor(np.ascontiguousarray(Xv, np.float32), device=dev)
         yd = torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
         prec = est._precision if fleet.tc_eligible() else "f32"
-        out, off = fleet.predict(Schedule([len(Xv)]), xd, precision=prec)
+        out, off = fleet.predict(Schedule.single(len(Xv)), xd, precision=prec)
         n_out = int(off[-1])
         feat = self.__dict__.get("feature_thresholds_"); agg = self.__dict__.get("aggregate_threshold_")
         res = FFFleet.score_outputs(

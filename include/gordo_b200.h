@@ -216,7 +216,10 @@ int gb200_lstm_predict(gb200_fleet* f, const gb200_lstm_arch* arch, int precisio
                        void* scratch, int64_t scratch_bytes, void* stream);
 /* KerasLSTMBaseEstimator.fit (models.py:557-616): primer step on the first window, then
  * time-ordered batches; one job per fit.  Returns Keras History 'loss' of the main fit in
- * hist_loss [n_jobs, epochs] and the primer's loss in primer_loss [n_jobs]. */
+ * hist_loss [n_jobs, epochs] and the primer's loss in primer_loss [n_jobs].
+ * Arithmetic: float32 throughout; the batched GEMMs run on the tensor cores with a 3xTF32 split
+ * (relative error of a product below 2^-21), the recurrence on CUDA cores.  Environment knobs for
+ * tests: GB200_LSTM_GEMM = simt | tc | tcs, GB200_LSTM_REC = 0 (per-time-step launches). */
 int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t n_jobs,
                    const int64_t* job_rows_lo_host, const int64_t* job_rows_hi_host,
                    const float* in_scale, const float* in_min, const float* x, const float* y,
