@@ -25,7 +25,7 @@ from sklearn.preprocessing import MinMaxScaler
 
 from gordo_b200 import serializer
 from gordo_b200.fleet import FFFleet, FFTopology, Schedule, time_series_split_bounds
-from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector, DiffBasedKFCVAnomalyDetector
 from gordo_b200.machine.model.models import KerasAutoEncoder, KerasLSTMBaseEstimator, History, _Model
 
 
@@ -94,7 +94,10 @@ class FleetModelBuilder:
     # ------------------------------------------------------------------ bucketing
     @staticmethod
     def _standard_parts(model):
-        if type(model) is not DiffBasedAnomalyDetector or model.shuffle:
+        if type(model) is DiffBasedKFCVAnomalyDetector:
+            if model.smoothing_method not in ("smm", "sma", "ewma") or not model.window:
+                return None
+        elif type(model) is not DiffBasedAnomalyDetector or model.shuffle:
             return None
         if not isinstance(model.scaler, MinMaxScaler):
             return None
@@ -114,6 +117,11 @@ class FleetModelBuilder:
         y = X if mc.y is None else np.asarray(getattr(mc.y, "values", mc.y))
         est.kwargs.update({"n_features": X.shape[1], "n_features_out": y.shape[1]})
         topo = est._topology()
+        kfcv = None
+        if type(model) is DiffBasedKFCVAnomalyDetector:
+            if isinstance(est, KerasLSTMBaseEstimator):
+                return None                  # the K-fold variant is batched for the feed-forward family only
+            kfcv = (model.smoothing_method, float(model.threshold_percentile), bool(model.shuffle))
         if isinstance(est, KerasLSTMBaseEstimator):
             return ("lstm", type(est).__name__, topo.key(), int(est.kwargs.get("epochs", 1)), int(est.batch_size),
                     mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
@@ -121,7 +129,7 @@ class FleetModelBuilder:
         fit = (int(est.kwargs.get("epochs", 1)), int(est.kwargs.get("batch_size") or 32),
                bool(est.kwargs.get("shuffle", True)), est.kwargs.get("l1_batch_norm", "sum"),
                mc.evaluation.get("cv_mode", "full_build"), int(mc.evaluation.get("n_splits", 3)),
-               tuple(sorted(topo.adam.items())), model.window)
+               tuple(sorted(topo.adam.items())), model.window, kfcv)
         return (topo.key(), fit)
 
     # ------------------------------------------------------------------ one-at-a-time fallback
@@ -185,8 +193,17 @@ class FleetModelBuilder:
         gen = torch.Generator(device=dev); gen.manual_seed(seed)
         params = topo.glorot_init(J, gen, dev)
         n_job = (np.asarray(hi) - np.asarray(lo)).astype(np.int64)
+        is_kfcv = type(protos[0]) is DiffBasedKFCVAnomalyDetector
         pool = poff = None
-        if do_shuffle:
+        if is_kfcv and protos[0].shuffle and not do_shuffle:
+            # diff.py:166-170: rows shuffled once with random_state=0, then fed in that order every epoch
+            perms = []
+            for nj in n_job:
+                idx = np.arange(int(nj)); np.random.RandomState(0).shuffle(idx)
+                perms.append(np.tile(idx, epochs))
+            pool = torch.as_tensor(np.concatenate(perms).astype(np.int32), device=dev)
+            poff = torch.as_tensor(np.concatenate([[0], np.cumsum(n_job * epochs)[:-1]]).astype(np.int64), device=dev)
+        elif do_shuffle:
             pool = segmented_randperm(np.repeat(n_job, epochs), gen, dev)
             poff = torch.as_tensor(np.concatenate([[0], np.cumsum(n_job * epochs)[:-1]]).astype(np.int64), device=dev)
         hl, ha, _, _ = fleet.fit_jobs(xd, yd, lo_t, hi_t, params, in_scale=in_scale, in_min=in_min, epochs=epochs,
@@ -206,13 +223,30 @@ class FleetModelBuilder:
             vfleet.in_min = in_min[sel].contiguous(); vfleet.err_scale = err_scale[sel].contiguous()
             vs = Schedule(rows_lo=te_lo, rows_hi=te_hi, rows_total=int(off[-1]))
             prec = vfleet.auto_precision(self.cv_precision)
+            init = None
+            if is_kfcv:
+                # diff.py:580-612: predictions start as zeros and the validation error as NaN; rows no test
+                # fold covers keep them (with the builder's TimeSeriesSplit that is the first quarter)
+                R = int(off[-1])
+                zeros = torch.zeros((R, To), dtype=torch.float32, device=dev)
+                init = {"model-output": zeros,
+                        "tag-anomaly-unscaled": FFFleet.score_outputs(zeros, ysrc, [0, R], [0])["tag-anomaly-unscaled"],
+                        "total-anomaly-scaled": torch.full((R,), float("nan"), dtype=torch.float32, device=dev)}
             res = vfleet.score(vs, xd, yd, precision=prec,
-                               columns=("model-output", "tag-anomaly-unscaled", "total-anomaly-scaled"))
+                               columns=("model-output", "tag-anomaly-unscaled", "total-anomaly-scaled"), out=init)
             tl = torch.as_tensor(np.asarray(te_lo, np.int64), device=dev)
             th = torch.as_tensor(np.asarray(te_hi, np.int64), device=dev)
             feat_pf = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], tl, th, 6).reshape(M, k, To)
             agg_pf = FFFleet.rolling_min_max(res["total-anomaly-scaled"], tl, th, 6).reshape(M, k)
-            if win is not None:         # the "smooth" thresholds: same statistic over rolling(window) (diff.py:241-248)
+            if is_kfcv:
+                # thresholds = percentile of the smoothed validation errors over ALL rows of the Machine (diff.py:614-635)
+                ml = torch.as_tensor(off[:-1].astype(np.int64), device=dev); mh = torch.as_tensor(off[1:].astype(np.int64), device=dev)
+                det0 = protos[0]
+                kf_feat = FFFleet.quantile(FFFleet.smooth(res["tag-anomaly-unscaled"], ml, mh, det0.smoothing_method, det0.window),
+                                           ml, mh, det0.threshold_percentile)
+                kf_agg = FFFleet.quantile(FFFleet.smooth(res["total-anomaly-scaled"], ml, mh, det0.smoothing_method, det0.window),
+                                          ml, mh, det0.threshold_percentile)[:, 0]
+            elif win is not None:       # the "smooth" thresholds: same statistic over rolling(window) (diff.py:241-248)
                 sfeat_h = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], tl, th, win).reshape(M, k, To).double().cpu().numpy()
                 sagg_h = FFFleet.rolling_min_max(res["total-anomaly-scaled"], tl, th, win).reshape(M, k).double().cpu().numpy()
             # the builder's CV metrics (build_model.py:245-289): scoring scaler = MinMaxScaler fitted on the
@@ -222,7 +256,9 @@ class FleetModelBuilder:
         final = torch.arange(M, device=dev) * per + k
         fleet.set_params(params[final]); fleet.in_scale = in_scale[final].contiguous()
         fleet.in_min = in_min[final].contiguous(); fleet.err_scale = err_scale[final].contiguous()
-        if k:
+        if k and is_kfcv:
+            fleet.feat_thr = kf_feat.float().contiguous(); fleet.agg_thr = kf_agg.float().contiguous()
+        elif k:
             fleet.feat_thr = feat_pf[:, -1].contiguous(); fleet.agg_thr = agg_pf[:, -1].contiguous()
         torch.cuda.synchronize()
         t_total = time.time() - t_start
@@ -234,6 +270,8 @@ class FleetModelBuilder:
         xs_lo = (1.0 / in_scale.double()).cpu().numpy()           # data_range
         in_scale_h = in_scale.double().cpu().numpy(); in_min_h = in_min.double().cpu().numpy()
         es_h = err_scale.double().cpu().numpy()
+        kf_feat_h = kf_feat.cpu().numpy() if (k and is_kfcv) else None
+        kf_agg_h = kf_agg.cpu().numpy() if (k and is_kfcv) else None
         feat_h = feat_pf.double().cpu().numpy() if k else None
         agg_h = agg_pf.double().cpu().numpy() if k else None
         out = []
@@ -251,7 +289,10 @@ class FleetModelBuilder:
             _set_minmax(model.scaler, es_h[j], -ymin * es_h[j], ym, mc.y if mc.y is not None else mc.X)
             tags = list(mc.y.columns) if isinstance(mc.y, pd.DataFrame) else (
                 list(mc.X.columns) if isinstance(mc.X, pd.DataFrame) and alias else list(range(To)))
-            if k:
+            if k and is_kfcv:
+                model.feature_thresholds_ = pd.Series(kf_feat_h[m], index=tags, name=model.threshold_percentile)
+                model.aggregate_threshold_ = float(kf_agg_h[m])
+            elif k:
                 model.feature_thresholds_per_fold_ = pd.DataFrame(feat_h[m], index=[f"fold-{i}" for i in range(k)], columns=tags)
                 model.aggregate_thresholds_per_fold_ = {f"fold-{i}": float(agg_h[m, i]) for i in range(k)}
                 model.feature_thresholds_ = pd.Series(feat_h[m, -1], index=tags, name=f"fold-{k - 1}")

@@ -223,11 +223,14 @@ class KFCVDetector(DiffDetector):
         q = pd.DataFrame(sm).quantile(self.threshold_percentile).to_numpy()
         return float(q[0]) if np.asarray(metric).ndim == 1 else q
 
-    def cross_validate(self, X, y, n_splits=5, seed=0):
+    def cross_validate(self, X, y, n_splits=5, seed=0, splits=None):
+        """``splits``: explicit (train, test) index pairs instead of the default KFold -- gordo's builder
+        passes its own ``cv`` (TimeSeriesSplit by default, build_model.py:239-262); rows no test fold
+        covers keep a zero prediction and a NaN validation error, exactly as diff.py:580-612 leaves them."""
         X = np.asarray(X); y = np.asarray(y)
         y_pred = np.zeros_like(np.asarray(y, np.float64))
         y_val_mse = np.full(len(y), np.nan)
-        for i, (tr, te) in enumerate(kfold_split(len(X), n_splits, seed)):
+        for i, (tr, te) in enumerate(splits if splits is not None else kfold_split(len(X), n_splits, seed)):
             base = self._fit_base(f"fold-{i}", X[tr], y[tr])
             fold_scaler = MinMaxScaler().fit(y[tr])
             y_pred[te] = base.predict(X[te])

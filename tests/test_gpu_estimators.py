@@ -329,3 +329,40 @@ def test_serving_cache_follows_the_model():
     pd.testing.assert_frame_equal(clone.anomaly(X, X), f3)
     # a different frame length reuses the cached weights with another schedule
     assert len(det.anomaly(X.iloc[:37], X.iloc[:37])) == 37
+
+
+def test_fleet_builder_batches_kfcv_detectors():
+    """DiffBasedKFCVAnomalyDetector Machines in the batched build: builder folds (TimeSeriesSplit), thresholds =
+    percentile of the smoothed errors over all rows, uncovered rows keeping zero predictions (diff.py:580-635)."""
+    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.fleet import FFTopology
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedKFCVAnomalyDetector
+    from oracle.anomaly import KFCVDetector
+    T, rows, W = 5, [400, 333], 12
+    Xs = [_data(70 + i, n, T) for i, n in enumerate(rows)]
+    defn = {"gordo_b200.machine.model.anomaly.diff.DiffBasedKFCVAnomalyDetector": {
+        "window": W, "smoothing_method": "sma", "threshold_percentile": 0.95, "shuffle": False, "base_estimator": {
+        "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler",
+            {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "shuffle": False}}]}}}}
+    mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=[f"t{j}" for j in range(T)]), model=defn,
+                        evaluation={"seed": 4}) for i, X in enumerate(Xs)]
+    built = FleetModelBuilder(mcs).build()
+    spec = factories.feedforward_hourglass(T)
+    topo = FFTopology(spec["widths"], spec["acts"], spec["l1"])
+    gen = torch.Generator(device="cuda:0"); gen.manual_seed(4)
+    init = topo.glorot_init(len(rows) * 4, gen, torch.device("cuda:0")).cpu().numpy()
+    for m, ((model, meta), X) in enumerate(zip(built, Xs)):
+        assert type(model) is DiffBasedKFCVAnomalyDetector and meta["fleet"]["machines_in_launch"] == 2
+        Xd = X.astype(np.float64)
+        det = KFCVDetector(lambda tag, m=m: FFBase(spec, dense.ff_unflatten(
+            init[m * 4 + (3 if tag == "final" else int(tag[-1]))], spec["widths"]), perms=None),
+            window=W, smoothing_method="sma", threshold_percentile=0.95, shuffle=False)
+        det.cross_validate(Xd, Xd, splits=list(time_series_split(len(Xd), 3)))
+        det.fit(Xd, Xd)
+        np.testing.assert_allclose(model.feature_thresholds_.to_numpy(), det.feature_thresholds_, rtol=5e-3, atol=1e-5)
+        np.testing.assert_allclose(model.aggregate_threshold_, det.aggregate_threshold_, rtol=5e-3)
+        assert sorted(model.get_metadata()) == sorted(["aggregate-threshold", "feature-thresholds", "base_estimator", "scaler",
+                                                       "shuffle", "smoothing-method", "threshold-percentile", "window"])
+        frame = model.anomaly(mcs[m].X, mcs[m].X)
+        want = det.anomaly(Xd, Xd)
+        np.testing.assert_allclose(frame["total-anomaly-confidence"].to_numpy().ravel(), want["total-anomaly-confidence"], rtol=2e-2, atol=1e-5)
