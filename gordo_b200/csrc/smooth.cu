@@ -11,8 +11,8 @@
 // so a row step of a warp is one contiguous read and one contiguous write.  The moving median keeps
 // the window SORTED in shared memory ([w][threads], conflict-free) and replaces the outgoing value
 // by the incoming one with a single shift pass.  Mean / EWMA carry their state in float64 registers,
-// in the recurrences pandas uses.  Quantile: one CTA per (job, column), three-pass radix select
-// (11+11+10 bits of the order-preserving integer image of the float) per order statistic.
+// in the recurrences pandas uses.  Quantile: one CTA per (job, 8 adjacent columns), three-pass radix
+// select (11+11+10 bits of the order-preserving integer image of the float) + one pass for the next order statistic.
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -96,10 +96,10 @@ __global__ void smooth_kernel(const __grid_constant__ SmoothArgs a) {
     if (a.method == GB200_SMOOTH_SMM) {
         SortedWin sw{s_win + tid, nt, 0};
         const bool odd = (w & 1) != 0;
+        float nx = v[h0 * C], ox = NAN;                  // the next row's values are loaded one step ahead
         for (int64_t r = h0; r < o1; ++r) {
-            const float x_new = v[r * C];
-            const bool has_old = r - w >= h0;
-            const float x_old = has_old ? v[(r - w) * C] : NAN;
+            const float x_new = nx, x_old = ox;
+            if (r + 1 < o1) { nx = v[(r + 1) * C]; ox = (r + 1 - w >= h0) ? v[(r + 1 - w) * C] : NAN; }
             const bool vo = x_old == x_old, vn = x_new == x_new;
             if (vo && vn) sw.replace(x_old, x_new);
             else { if (vo) sw.remove(x_old); if (vn) sw.insert(x_new); }
@@ -154,79 +154,110 @@ __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// value of 0-based ascending rank `rank` among the non-NaN elements of the column (all threads call)
-__device__ float radix_select(const float* __restrict__ v, int64_t n_rows, int C, int64_t rank,
-                              int* hist, int* scan, int* s_pick) {
-    uint32_t prefix = 0, mask = 0;
-    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
-    for (int p = 0; p < 3; ++p) {
-        const int nb = 1 << bits[p];
-        for (int i = threadIdx.x; i < Q_BINS; i += Q_THREADS) hist[i] = 0;
-        __syncthreads();
-        for (int64_t r = threadIdx.x; r < n_rows; r += Q_THREADS) {
-            const float x = v[r * C];
-            if (x == x) {
-                const uint32_t k = f2key(x);
-                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shifts[p]) & (nb - 1)], 1);
-            }
-        }
-        __syncthreads();
-        // each thread owns Q_BINS / Q_THREADS consecutive bins; inclusive scan of the per-thread sums
-        constexpr int PER = Q_BINS / Q_THREADS;
-        int local = 0;
-        for (int i = 0; i < PER; ++i) local += hist[threadIdx.x * PER + i];
-        scan[threadIdx.x] = local;
-        __syncthreads();
-        for (int off = 1; off < Q_THREADS; off <<= 1) {
-            const int t = threadIdx.x >= off ? scan[threadIdx.x - off] : 0;
-            __syncthreads();
-            scan[threadIdx.x] += t;
-            __syncthreads();
-        }
-        const int64_t before = (int64_t)scan[threadIdx.x] - local;           // elements in lower bins
-        if (rank >= before && rank < before + local) {
-            int64_t acc = before; int b = threadIdx.x * PER;
-            for (;; ++b) { const int h = hist[b]; if (rank < acc + h) break; acc += h; }
-            s_pick[0] = b; s_pick[1] = (int)(rank - acc);
-        }
-        __syncthreads();
-        prefix |= (uint32_t)s_pick[0] << shifts[p];
-        mask |= (uint32_t)(nb - 1) << shifts[p];
-        rank = s_pick[1];
-        __syncthreads();
-    }
-    return key2f(prefix);
-}
+// One CTA = one job x QC adjacent columns: a row's QC values share one or two 32-byte sectors, so the
+// strided column walk costs 1/QC of the L2 traffic of a CTA per column.  Three histogram passes
+// (11 + 11 + 10 bits) select the order statistic of rank k = floor((n-1) q) of every column -- the first
+// pass's histogram also counts the non-NaN rows -- and one more pass finds the next order statistic
+// (count of values <= it, smallest value above it) for the linear interpolation.
+constexpr int QC = 8;
 
 __global__ void __launch_bounds__(Q_THREADS)
 quantile_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, const float* __restrict__ v,
                 int C, double q, double* __restrict__ out) {
-    __shared__ int hist[Q_BINS];
-    __shared__ int scan[Q_THREADS];
-    __shared__ int s_pick[2];
-    __shared__ int64_t s_n;
-    const int job = blockIdx.y, col = blockIdx.x;
+    extern __shared__ int qhist[];                    // [QC][Q_BINS]
+    __shared__ uint32_t s_prefix[QC], s_mask[QC], s_mingt[QC];
+    __shared__ long long s_rank[QC], s_n[QC];
+    __shared__ unsigned long long s_le[QC];
+    const int job = blockIdx.y, c0 = blockIdx.x * QC;
+    const int nc = min(QC, C - c0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t j0 = lo[job], n_rows = hi[job] - j0;
-    const float* base = v + j0 * C + col;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    int64_t cnt = 0;
-    for (int64_t r = threadIdx.x; r < n_rows; r += Q_THREADS) { const float x = base[r * C]; cnt += (x == x); }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd((unsigned long long*)&s_n, (unsigned long long)cnt);
-    __syncthreads();
-    const int64_t n = s_n;
-    double res = NAN;
-    if (n > 0) {
-        const double h = (double)(n - 1) * q;
-        const int64_t k = (int64_t)floor(h);
-        const double frac = h - (double)k;
-        const float va = radix_select(base, n_rows, C, k, hist, scan, s_pick);
-        float vb = va;
-        if (frac > 0.0 && k + 1 < n) vb = radix_select(base, n_rows, C, k + 1, hist, scan, s_pick);
-        res = (double)va + ((double)vb - (double)va) * frac;
+    const float* base = v + j0 * C + c0;
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    if (tid < QC) { s_prefix[tid] = 0; s_mask[tid] = 0; s_rank[tid] = 0; s_n[tid] = 0; s_le[tid] = 0; s_mingt[tid] = 0xffffffffu; }
+    for (int p = 0; p < 3; ++p) {
+        const int nb = 1 << bits[p];
+        for (int i = tid; i < QC * Q_BINS; i += Q_THREADS) qhist[i] = 0;
+        __syncthreads();
+        for (int64_t r = tid; r < n_rows; r += Q_THREADS) {
+            const float* row = base + r * C;
+            for (int j = 0; j < nc; ++j) {
+                const float x = row[j];
+                if (x == x) {
+                    const uint32_t k = f2key(x);
+                    if ((k & s_mask[j]) == s_prefix[j]) {
+                        // scores cluster in a few bins: lanes that hit the same bin add once, together
+                        const int bin = (int)((k >> shifts[p]) & (nb - 1));
+                        const unsigned peers = __match_any_sync(__activemask(), bin);
+                        if (lane == __ffs(peers) - 1) atomicAdd(&qhist[j * Q_BINS + bin], __popc(peers));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (warp < nc) {
+            // warp `warp` resolves column `warp`: lane l owns nb/32 consecutive bins
+            const int j = warp, per = nb / 32;
+            const int* h = qhist + j * Q_BINS + lane * per;
+            long long local = 0;
+            for (int i = 0; i < per; ++i) local += h[i];
+            long long incl = local;
+            for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const long long total = __shfl_sync(0xffffffffu, incl, 31);
+            long long rank = s_rank[j];
+            if (p == 0) { rank = total > 0 ? (long long)floor((double)(total - 1) * q) : 0; if (lane == 0) s_n[j] = total; }
+            const long long before = incl - local;
+            if (total > 0 && rank >= before && rank < before + local) {
+                long long acc = before; int b = 0;
+                for (;; ++b) { const int hb = h[b]; if (rank < acc + hb) break; acc += hb; }
+                s_prefix[j] |= (uint32_t)(lane * per + b) << shifts[p];
+                s_rank[j] = rank - acc;
+            }
+            if (lane == 0) s_mask[j] |= (uint32_t)(nb - 1) << shifts[p];
+        }
+        __syncthreads();
     }
-    if (threadIdx.x == 0) out[(size_t)job * C + col] = res;
+    // ---- the next order statistic: #values <= a and the smallest value above a (key order = value order)
+    {
+        unsigned long long le[QC]; uint32_t mg[QC];
+        #pragma unroll
+        for (int j = 0; j < QC; ++j) { le[j] = 0; mg[j] = 0xffffffffu; }
+        for (int64_t r = tid; r < n_rows; r += Q_THREADS) {
+            const float* row = base + r * C;
+            #pragma unroll
+            for (int j = 0; j < QC; ++j) {
+                if (j >= nc) break;
+                const float x = row[j];
+                if (x == x) {
+                    const uint32_t k = f2key(x);
+                    if (k <= s_prefix[j]) ++le[j]; else mg[j] = min(mg[j], k);
+                }
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j < QC; ++j) {
+            for (int o = 16; o > 0; o >>= 1) {
+                le[j] += __shfl_down_sync(0xffffffffu, le[j], o);
+                mg[j] = min(mg[j], __shfl_down_sync(0xffffffffu, mg[j], o));
+            }
+            if (lane == 0 && j < nc) { atomicAdd(&s_le[j], le[j]); atomicMin(&s_mingt[j], mg[j]); }
+        }
+    }
+    __syncthreads();
+    if (tid < nc) {
+        const long long n = s_n[tid];
+        double res = NAN;
+        if (n > 0) {
+            const double h = (double)(n - 1) * q;
+            const long long k = (long long)floor(h);
+            const double frac = h - (double)k;
+            const double va = (double)key2f(s_prefix[tid]);
+            double vb = va;
+            if (frac > 0.0 && k + 1 < n && s_le[tid] < (unsigned long long)(k + 2)) vb = (double)key2f(s_mingt[tid]);
+            res = va + (vb - va) * frac;
+        }
+        out[(size_t)job * C + c0 + tid] = res;
+    }
 }
 
 int max_rows_host(int n_jobs, const int64_t* lo, const int64_t* hi, cudaStream_t stream, int64_t* out) {
@@ -294,8 +325,10 @@ int gb_launch_quantile(int n_jobs, const int64_t* lo, const int64_t* hi, const f
                        double q, double* out, cudaStream_t stream) {
     if (n_jobs <= 0) return GB_OK;
     GB_REQUIRE(q >= 0.0 && q <= 1.0, "quantile: q must be in [0, 1]");
-    dim3 grid(n_cols, n_jobs);
-    quantile_kernel<<<grid, Q_THREADS, 0, stream>>>(lo, hi, v, n_cols, q, out);
+    dim3 grid((n_cols + QC - 1) / QC, n_jobs);
+    const int smem = QC * Q_BINS * (int)sizeof(int);
+    GB_CUDA_CHECK(cudaFuncSetAttribute(quantile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    quantile_kernel<<<grid, Q_THREADS, smem, stream>>>(lo, hi, v, n_cols, q, out);
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
 }
