@@ -96,3 +96,40 @@ def test_c5_shape_many_tiny_machines():
     ts = res["total-anomaly-scaled"].view(M, rows)
     want = ts.unfold(1, 6, 1).min(-1).values.max(1).values
     assert torch.equal(thr, want)
+
+
+def test_c4_full_size_lstm_properties():
+    """
+    c4: KerasLSTMAutoEncoder 200 tags, lookback 128, hourglass 167-133-100-100-133-167, 100 000 rows
+    (99 873 windows) on the tcgen05 pipeline.  Windows are independent sequences, so: a series cut at
+    another offset gives the same windows bit for bit (different tile alignment), one Machine split into
+    two overlapping Machines gives the same rows, and the exact fp32 kernel agrees on a slice within the
+    stated bf16 tolerance.
+    """
+    from gordo_b200.fleet import Schedule
+    from gordo_b200.lstm import LSTMFleet
+    from gordo_b200.machine.model.factories.lstm_autoencoder import lstm_hourglass
+    T, L, n = 200, 128, 100_000
+    topo = lstm_hourglass(T, lookback_window=L)
+    g = torch.Generator(device=DEV); g.manual_seed(5)
+    X = torch.rand((n, T), generator=g, device=DEV)
+    one = LSTMFleet(topo, 1, 0, DEV)
+    one.set_params(topo.init_params(1, g, DEV))
+    assert one.tc_eligible()
+    out, off = one.predict(Schedule([n]), X, precision="bf16")
+    assert int(off[-1]) == n - L + 1 and out.shape == (n - L + 1, T) and bool(torch.isfinite(out).all())
+    # (a) the same series entered 131 rows later: window k of X[131:] is window k + 131 of X
+    a = 131
+    out_a, _ = one.predict(Schedule([n - a]), X[a:].contiguous(), precision="bf16")
+    assert torch.equal(out_a, out[a:])
+    # (b) one Machine as two overlapping Machines of the same model
+    n1 = 40_007
+    two = LSTMFleet(topo, 2, 0, DEV)
+    two.set_params(one.params.repeat(2, 1))
+    Xs = torch.cat([X[:n1], X[n1 - L + 1:]])
+    out2, off2 = two.predict(Schedule([n1, n - (n1 - L + 1)]), Xs, precision="bf16")
+    assert int(off2[-1]) == n - L + 1 and torch.equal(out2, out)
+    # (c) exact fp32 kernel on the first 300 windows
+    ref, _ = one.predict(Schedule([300 + L - 1]), X[:300 + L - 1].contiguous(), precision="f32")
+    scale = ref.abs().max().item()
+    assert (out[:300] - ref).abs().max().item() <= 3e-2 * max(1.0, scale)
