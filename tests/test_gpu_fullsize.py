@@ -133,3 +133,44 @@ def test_c4_full_size_lstm_properties():
     ref, _ = one.predict(Schedule([300 + L - 1]), X[:300 + L - 1].contiguous(), precision="f32")
     scale = ref.abs().max().item()
     assert (out[:300] - ref).abs().max().item() <= 3e-2 * max(1.0, scale)
+
+
+def test_c2_full_size_fit_properties():
+    """
+    Training at the c2 row count (8 jobs x 100 000 rows x 50 tags, batch 32, 1 epoch = 3 125 dependent Adam
+    steps per job): a job trained inside the fleet launch equals the same job trained alone bit for bit
+    (jobs share nothing, whatever CTA order they get), a rerun reproduces itself, the loss is finite and
+    lower than at the start.
+    """
+    from gordo_b200.builder import segmented_randperm
+    J, rows, T = 8, 100_000, 50
+    fl, sched, X = _fleet(J, T, rows, seed=21)
+    dev = torch.device(DEV)
+    g = torch.Generator(device=DEV); g.manual_seed(9)
+    lo = torch.arange(J, device=DEV, dtype=torch.int64) * rows
+    hi = lo + rows - torch.arange(J, device=DEV, dtype=torch.int64) * 3_001       # jobs of different length
+    n_job = (hi - lo).cpu().numpy()
+    pool = segmented_randperm(n_job, g, dev)
+    poff = torch.as_tensor(np.concatenate([[0], np.cumsum(n_job)[:-1]]).astype(np.int64), device=DEV)
+    P0 = fl.params.clone()
+
+    def run(sel):
+        p = P0[sel].clone()
+        hl, _, _, _ = fl.fit_jobs(X, None, lo[sel].contiguous(), hi[sel].contiguous(), p,
+                                  in_scale=fl.in_scale[sel].contiguous(), in_min=fl.in_min[sel].contiguous(),
+                                  epochs=1, batch_size=32, perm_pool=pool, perm_off=poff[sel].contiguous())
+        torch.cuda.synchronize()
+        return p, hl
+
+    sel_all = torch.arange(J, device=DEV)
+    p_all, h_all = run(sel_all)
+    p_again, h_again = run(sel_all)
+    assert torch.equal(p_all, p_again) and torch.equal(h_all, h_again)
+    p_one, h_one = run(torch.tensor([5], device=DEV))
+    assert torch.equal(p_one[0], p_all[5]) and torch.equal(h_one[0], h_all[5])
+    assert bool(torch.isfinite(p_all).all()) and bool(torch.isfinite(h_all).all())
+    # the epoch-mean loss is far below the loss of the untrained net on the same rows
+    res0 = fl.score(sched, X, precision="f32", columns=("model-output",))
+    xs = X * fl.in_scale.repeat_interleave(rows, 0) + fl.in_min.repeat_interleave(rows, 0)
+    start_mse = ((res0["model-output"] - xs) ** 2).mean().item()
+    assert h_all.max().item() < 0.5 * start_mse
