@@ -38,13 +38,15 @@ __device__ __forceinline__ int find_machine(const int32_t* tile_off, int n, int 
     return lo;
 }
 
-template <bool SMEM_W>
-__global__ void __launch_bounds__(TILE)
+// NT = threads per CTA = rows per pass; a 128-row tile of the schedule is walked in 128 / NT passes.
+// Wide topologies take NT = 64 or 32 so that the weights still fit next to the activation buffers.
+template <bool SMEM_W, int NT>
+__global__ void __launch_bounds__(NT)
 ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float* act0 = smem;                               // [max_w][TILE]
-    float* act1 = act0 + (size_t)a.max_w * TILE;      // [max_w][TILE]
-    float* wsm  = act1 + (size_t)a.max_w * TILE;      // padded weights (SMEM_W)
+    float* act0 = smem;                               // [max_w][NT]
+    float* act1 = act0 + (size_t)a.max_w * NT;        // [max_w][NT]
+    float* wsm  = act1 + (size_t)a.max_w * NT;        // padded weights (SMEM_W)
     __shared__ int s_m;
 
     const int tid = threadIdx.x;
@@ -67,18 +69,20 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
             for (int l = 0; l < L; ++l) {
                 const int win = a.arch.widths[l], wout = a.arch.widths[l + 1];
                 const int ldw = (wout + 7) & ~7;
-                for (int i = tid; i < win * ldw; i += TILE) {
+                for (int i = tid; i < win * ldw; i += NT) {
                     int k = i / ldw, n = i - k * ldw;
                     wsm[so + i] = n < wout ? P[go + (int64_t)k * wout + n] : 0.0f;
                 }
                 so += win * ldw; go += (int64_t)win * wout;
-                for (int i = tid; i < ldw; i += TILE) wsm[so + i] = i < wout ? P[go + i] : 0.0f;
+                for (int i = tid; i < ldw; i += NT) wsm[so + i] = i < wout ? P[go + i] : 0.0f;
                 so += ldw; go += wout;
             }
             cur_m = m;
         }
-        const int64_t row = a.row_lo[m] + (int64_t)(tile - a.tile_off[m]) * TILE + tid;
+        for (int sub = 0; sub < TILE / NT; ++sub) {
+        const int64_t row = a.row_lo[m] + (int64_t)(tile - a.tile_off[m]) * TILE + sub * NT + tid;
         const bool valid = row < a.row_hi[m];
+        if (sub > 0) __syncthreads();         // the previous pass is done with the activation buffers
 
         // ---- input: MinMaxScaler.transform in fp32
         {
@@ -88,7 +92,7 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
             for (int k = 0; k < T_in; ++k) {
                 float v = valid ? xr[k] : 0.0f;
                 if (sc) v = fmaf(v, sc[k], mn[k]);
-                act0[k * TILE + tid] = v;
+                act0[k * NT + tid] = v;
             }
         }
         __syncthreads();            // weights staged (and s_m consumed)
@@ -113,7 +117,7 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
                     acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
                     #pragma unroll 4
                     for (int k = 0; k < win; ++k) {
-                        const float h = hin[k * TILE + tid];
+                        const float h = hin[k * NT + tid];
                         const float4 w0 = *reinterpret_cast<const float4*>(W + k * ldw + n0);
                         const float4 w1 = *reinterpret_cast<const float4*>(W + k * ldw + n0 + 4);
                         acc[0] = fmaf(h, w0.x, acc[0]); acc[1] = fmaf(h, w0.y, acc[1]);
@@ -125,7 +129,7 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
                     #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[j] = (n0 + j < wout) ? __ldg(B + n0 + j) : 0.0f;
                     for (int k = 0; k < win; ++k) {
-                        const float h = hin[k * TILE + tid];
+                        const float h = hin[k * NT + tid];
                         const float* wr = W + (int64_t)k * wout + n0;
                         #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -136,35 +140,61 @@ ff_score_f32_kernel(const __grid_constant__ ScoreArgs a) {
                 for (int j = 0; j < 8; ++j)
                     if (n0 + j < wout) {
                         const float h = gb_act(code, acc[j]);
-                        hout[(n0 + j) * TILE + tid] = h;
+                        hout[(n0 + j) * NT + tid] = h;
                         if (c1 != 0.0f) act_l1 = fmaf(c1, fabsf(h), act_l1);
                     }
             }
             float* t = hin; hin = hout; hout = t;     // each thread reads only its own column
         }
 
-        // ---- epilogue: DiffBasedAnomalyDetector columns (diff.py:350-444)
-        if (valid) {
+        // ---- epilogue: DiffBasedAnomalyDetector columns (diff.py:350-444).  A thread owns a row, but rows
+        // are only 4*T bytes apart: writing them straight from the thread would touch every 32-byte sector
+        // T times with 4 bytes.  Each column is staged row-major in the free activation buffer and leaves
+        // as one contiguous, fully coalesced run (the tile's rows are consecutive in every output array).
+        {
+            const int64_t row0 = a.row_lo[m] + (int64_t)(tile - a.tile_off[m]) * TILE + sub * NT;
+            const int nvalid = (int)max((int64_t)0, min((int64_t)NT, a.row_hi[m] - row0));
             const float* yr = (a.y ? a.y : a.x) + row * T_out;
             const float* es = a.err_scale ? a.err_scale + (size_t)m * T_out : nullptr;
             const float* ft = a.feat_thr ? a.feat_thr + (size_t)m * T_out : nullptr;
+            float* stage = hout;                                    // [NT][T_out] row-major
+            __syncthreads();                                        // hout was the last layer's input: every thread is done reading it
+            auto flush = [&](float* dst) {
+                __syncthreads();
+                float* o = dst + row0 * T_out;
+                for (int i = tid; i < nvalid * T_out; i += NT) o[i] = stage[i];
+                __syncthreads();
+            };
+            if (a.model_out) {
+                for (int j = 0; j < T_out; ++j) stage[tid * T_out + j] = hin[j * NT + tid];
+                flush(a.model_out);
+            }
             float ss = 0.0f, su = 0.0f;
             for (int j = 0; j < T_out; ++j) {
-                const float yh = hin[j * TILE + tid];
-                const float d = fabsf(yh - yr[j]);
-                const float s = es ? d * fabsf(es[j]) : d;
-                su = fmaf(d, d, su); ss = fmaf(s, s, ss);
-                const int64_t o = row * T_out + j;
-                if (a.model_out) a.model_out[o] = yh;
-                if (a.tag_unscaled) a.tag_unscaled[o] = d;
-                if (a.tag_scaled) a.tag_scaled[o] = s;
-                if (a.conf && ft) a.conf[o] = d / ft[j];
+                const float d = valid ? fabsf(hin[j * NT + tid] - yr[j]) : 0.0f;
+                const float sc = es ? d * fabsf(es[j]) : d;
+                su = fmaf(d, d, su); ss = fmaf(sc, sc, ss);
+                stage[tid * T_out + j] = d;
             }
-            const float ts = ss / (float)T_out, tu = su / (float)T_out;
-            if (a.total_scaled) a.total_scaled[row] = ts;
-            if (a.total_unscaled) a.total_unscaled[row] = tu;
-            if (a.total_conf && a.agg_thr) a.total_conf[row] = ts / a.agg_thr[m];
-            if (a.activity) a.activity[row] = act_l1;
+            if (a.tag_unscaled) flush(a.tag_unscaled); else __syncthreads();
+            if (a.tag_scaled) {
+                for (int j = 0; j < T_out; ++j) { const float d = stage[tid * T_out + j]; stage[tid * T_out + j] = es ? d * fabsf(es[j]) : d; }
+                flush(a.tag_scaled);
+                if (a.conf && ft)       // back to the unscaled error for the confidence column
+                    for (int j = 0; j < T_out; ++j) stage[tid * T_out + j] = valid ? fabsf(hin[j * NT + tid] - yr[j]) : 0.0f;
+            }
+            if (a.conf && ft) {
+                for (int j = 0; j < T_out; ++j) stage[tid * T_out + j] = stage[tid * T_out + j] / ft[j];
+                flush(a.conf);
+            }
+            if (valid) {
+                const float ts = ss / (float)T_out, tu = su / (float)T_out;
+                if (a.total_scaled) a.total_scaled[row] = ts;
+                if (a.total_unscaled) a.total_unscaled[row] = tu;
+                if (a.total_conf && a.agg_thr) a.total_conf[row] = ts / a.agg_thr[m];
+                if (a.activity) a.activity[row] = act_l1;
+            }
+        }
         }
         __syncthreads();            // act buffers / s_m reused by the next tile
     }
@@ -197,20 +227,27 @@ int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, cons
     }
     a.max_w = max_w;
     if (f->tiles_total == 0) return GB_OK;
-    const size_t act_bytes = (size_t)2 * max_w * TILE * sizeof(float);
     const size_t smem_cap = 227 * 1024 - 64;
+    // rows per pass: 128 when the padded weights fit beside two [max_w][128] activation buffers, else 64 / 32
+    int nt = 128;
+    while (nt > 32 && (size_t)2 * max_w * nt * sizeof(float) + (size_t)wfloats * sizeof(float) > smem_cap) nt >>= 1;
+    const size_t act_bytes = (size_t)2 * max_w * nt * sizeof(float);
     GB_REQUIRE(act_bytes <= smem_cap, "ff_score_f32: layer width %d too large for the fp32 kernel", max_w);
     const bool smem_w = act_bytes + (size_t)wfloats * sizeof(float) <= smem_cap;
+    if (!smem_w) nt = 128;                    // weights stay in global memory anyway: widest pass
+    const size_t act_b = (size_t)2 * max_w * nt * sizeof(float);
     a.smem_w_floats = smem_w ? wfloats : 0;
-    const size_t smem = act_bytes + (smem_w ? (size_t)wfloats * sizeof(float) : 0);
-    auto kern = smem_w ? ff_score_f32_kernel<true> : ff_score_f32_kernel<false>;
+    const size_t smem = act_b + (smem_w ? (size_t)wfloats * sizeof(float) : 0);
+    void (*kern)(ScoreArgs) = !smem_w ? ff_score_f32_kernel<false, 128>
+                            : nt == 128 ? ff_score_f32_kernel<true, 128>
+                            : nt == 64 ? ff_score_f32_kernel<true, 64> : ff_score_f32_kernel<true, 32>;
     GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    GB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
+    GB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = f->sm_count * per_sm;
     if (grid > f->tiles_total) grid = f->tiles_total;
-    kern<<<grid, TILE, smem, stream>>>(a);
+    kern<<<grid, nt, smem, stream>>>(a);
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
 }
