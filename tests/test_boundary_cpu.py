@@ -197,3 +197,37 @@ def test_frame_layout_matches_reference_golden():
             assert df[("start", "")].iloc[:3].tolist() == case["start"]
             assert df[("end", "")].iloc[:3].tolist() == case["end"]
         np.testing.assert_array_equal(df["model-output"].to_numpy(), npz[pre + "col_model-output"])
+
+
+def test_fleet_builder_bucketing_rules():
+    """Which Machines share a batched launch (host logic only: no device needed)."""
+    import pandas as pd
+    from gordo_b200 import serializer
+    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+
+    def machine(detector="DiffBasedAnomalyDetector", det_kw=None, est="KerasAutoEncoder", est_kw=None, tags=4, evaluation=None):
+        kw = {"kind": "feedforward_hourglass" if est == "KerasAutoEncoder" else "lstm_hourglass"}
+        kw.update(est_kw or {})
+        d = {f"gordo_b200.machine.model.anomaly.diff.{detector}": dict(det_kw or {}, base_estimator={
+            "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler",
+                                                    {f"gordo_b200.machine.model.models.{est}": kw}]}})}
+        return FleetMachine("m", pd.DataFrame(np.zeros((50, tags))), model=d, evaluation=evaluation or {})
+
+    b = FleetModelBuilder([])
+    key = lambda mc: b._bucket_key(serializer.from_definition(mc.definition()), mc)
+    base = key(machine())
+    assert base is not None and base == key(machine())                       # same topology + fit settings: one bucket
+    assert key(machine(tags=5)) != base                                      # another topology
+    assert key(machine(est_kw={"epochs": 3})) != base                        # another fit schedule
+    assert key(machine(det_kw={"window": 12})) not in (None, base)           # smoothing window: batched, own bucket
+    assert key(machine(evaluation={"cv_mode": "build_only"})) != base
+    assert key(machine(det_kw={"shuffle": True})) is None                    # detector-level shuffle: per-Machine path
+    assert key(machine(est_kw={"validation_split": 0.1})) is None            # callbacks / validation: per-Machine path
+    assert key(machine(evaluation={"cv_mode": "cross_val_only"})) is None
+    kf = key(machine(detector="DiffBasedKFCVAnomalyDetector"))
+    assert kf not in (None, base)                                            # K-fold detector over the FF estimator: batched
+    assert key(machine(detector="DiffBasedKFCVAnomalyDetector", det_kw={"threshold_percentile": 0.9})) != kf
+    assert key(machine(detector="DiffBasedKFCVAnomalyDetector", det_kw={"smoothing_method": "median"})) is None
+    lstm = key(machine(est="KerasLSTMAutoEncoder", est_kw={"lookback_window": 4}))
+    assert lstm is not None and lstm[0] == "lstm"
+    assert key(machine(detector="DiffBasedKFCVAnomalyDetector", est="KerasLSTMAutoEncoder", est_kw={"lookback_window": 4})) is None
