@@ -58,6 +58,8 @@ SIGNATURES = {
     "gb200_lstm_fit": (C.c_int, [C.POINTER(LSTMArch), C.POINTER(Adam), _I32, C.POINTER(_I64), C.POINTER(_I64)]
                        + [_P] * 4 + [_I32, _I32] + [_P] * 3 + [_P, _I64, _P]),
     "gb200_score_outputs": (C.c_int, [_I32, _P, _P, _I32] + [_P] * 12),
+    "gb200_host_expand_columns": (C.c_int, [_I32, _P, _I32] + [_P] * 7 + [_I32]),
+    "gb200_host_stream_seconds": (C.c_double, [_P, _P, _I64, _I32, _I32]),
 }
 
 _lib = None

@@ -1,5 +1,5 @@
 """
-FleetModelBuilder -- the batched twin of gordo.builder.ModelBuilder._build
+FleetBuild / FleetModelBuilder -- the batched twin of gordo.builder.ModelBuilder._build
 (gordo/builder/build_model.py:192-339) for a whole project:
 
     for machine in machines: ModelBuilder(machine).build()          # local_build.py:69-70
@@ -13,7 +13,17 @@ and the result is materialised as the same fitted objects a per-Machine build pr
 (DiffBasedAnomalyDetector[Pipeline[MinMaxScaler, KerasAutoEncoder]]), ready for serializer.dump /
 gordo.server.  Machines whose model is not that standard composition are built one at a time
 through the estimator API (still on the GPU).
+
+Two classes:
+  FleetBuild          the batched engine: FleetBuild(machines).build() -> [(model, metadata)]
+  FleetModelBuilder   the reference's builder seam (gordo/builder/utils.py:8-17, cli/cli.py:147-150): a
+                      ``ModelBuilder`` subclass whenever ``gordo`` is importable -- same constructor, ``build()``
+                      returns ``(model, machine)`` -- plus ``build_fleet`` / ``local_build``, the batched twins of
+                      ``for machine in machines: ModelBuilder(machine).build()`` (local_build.py:67-70), and
+                      ``build_sharded`` for one process per GPU.
 """
+import datetime
+import threading
 import time
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence
@@ -46,6 +56,35 @@ class FleetMachine:
                     {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass"}}]}}}}
 
 
+def _metrics_dict(y: pd.DataFrame, scaler="sklearn.preprocessing.MinMaxScaler"):
+    """ModelBuilder.build_metrics_dict (build_model.py:377-446): ``{metric}-{tag}`` per target tag and ``{metric}``."""
+    from sklearn import metrics as skm
+    from gordo_b200.machine.model.utils import metric_wrapper
+    if isinstance(scaler, (str, dict)):
+        scaler = serializer.from_definition(scaler)
+    if scaler is not None:
+        scaler.fit(y)
+
+    def per_tag(fn, j):
+        def _score(y_true, y_pred):
+            return fn(np.asarray(getattr(y_true, "values", y_true))[:, j], np.asarray(getattr(y_pred, "values", y_pred))[:, j])
+        return _score
+
+    out = {}
+    for name in DEFAULT_METRICS:
+        fn = getattr(skm, name)
+        ms = name.replace("_", "-")
+        for j, col in enumerate(y.columns):
+            out[f"{ms}-{str(col).replace(' ', '-')}"] = skm.make_scorer(metric_wrapper(per_tag(fn, j), scaler=scaler))
+        out[ms] = skm.make_scorer(metric_wrapper(fn, scaler=scaler))
+    return out
+
+
+def _plain_minmax(sc) -> bool:
+    return (type(sc) is MinMaxScaler and tuple(getattr(sc, "feature_range", (0, 1))) == (0, 1)
+            and not getattr(sc, "clip", False))
+
+
 def segmented_randperm(lengths: Sequence[int], generator, device):
     """Independent random permutations of range(len) for every segment, concatenated (int32)."""
     import torch
@@ -61,11 +100,28 @@ def segmented_randperm(lengths: Sequence[int], generator, device):
     return (order - starts[seg]).to(torch.int32).contiguous()
 
 
-class FleetModelBuilder:
-    def __init__(self, machines: Sequence[FleetMachine], device: Optional[str] = None, cv_precision: str = "f32"):
+def job_seeds(seed: int, n: int) -> List[int]:
+    """
+    The torch seeds of the ``n`` successive fits of ONE Machine's build, exactly as the per-Machine path
+    draws them: ``ModelBuilder.set_seed`` seeds numpy (build_model.py:341-345), then every ``fit`` (CV folds
+    in order, then the final fit) draws ``np.random.randint(0, 2**31 - 1)`` (models.py ``fit``).
+    """
+    rs = np.random.RandomState(int(seed))
+    return [int(rs.randint(0, 2 ** 31 - 1)) for _ in range(n)]
+
+
+class FleetBuild:
+    def __init__(self, machines: Sequence[FleetMachine], device: Optional[str] = None, cv_precision: str = "f32",
+                 streams: int = 1):
+        """
+        streams: topology buckets built concurrently, each on its own CUDA stream from its own host thread
+        (a heterogeneous project is many small buckets; one bucket alone cannot fill 148 SMs).
+        """
         self.machines = list(machines)
         self.device = device
         self.cv_precision = cv_precision
+        self.streams = max(1, int(streams))
+        self.last_bucket_count = 0
 
     # ------------------------------------------------------------------ public
     def build(self):
@@ -85,8 +141,35 @@ class FleetModelBuilder:
                 results[i] = self._build_one(model, mc)
             else:
                 buckets.setdefault(key, []).append(i)
-        for key, idxs in buckets.items():
-            built = self._build_bucket([self.machines[i] for i in idxs], [prototypes[i] for i in idxs], dev)
+        self.last_bucket_count = len(buckets)
+
+        def run(item):
+            key, idxs = item
+            return idxs, self._build_bucket([self.machines[i] for i in idxs], [prototypes[i] for i in idxs], dev)
+
+        # largest buckets first so the small ones fill the tail
+        order = sorted(buckets.items(), key=lambda kv: -sum(len(np.asarray(getattr(self.machines[i].X, "values", self.machines[i].X)))
+                                                            for i in kv[1]))
+        if self.streams <= 1 or len(order) <= 1:
+            done = [run(it) for it in order]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            main = torch.cuda.current_stream(dev)
+            ready = torch.cuda.Event(); ready.record(main)
+            local = threading.local()
+
+            def run_on_stream(item):
+                if not hasattr(local, "stream"):
+                    torch.cuda.set_device(dev)
+                    local.stream = torch.cuda.Stream(device=dev)
+                    local.stream.wait_event(ready)
+                with torch.cuda.stream(local.stream):
+                    out = run(item)
+                    local.stream.synchronize()
+                return out
+            with ThreadPoolExecutor(max_workers=min(self.streams, len(order))) as pool:
+                done = list(pool.map(run_on_stream, order))
+        for idxs, built in done:
             for i, r in zip(idxs, built):
                 results[i] = r
         return results
@@ -99,10 +182,12 @@ class FleetModelBuilder:
                 return None
         elif type(model) is not DiffBasedAnomalyDetector or model.shuffle:
             return None
-        if not isinstance(model.scaler, MinMaxScaler):
+        # the batched path fits both scalers with plain (0, 1) MinMax semantics (gb200_minmax_fit): any
+        # other feature_range, or clip=True, builds through the estimator API like the reference
+        if not _plain_minmax(model.scaler):
             return None
         be = model.base_estimator
-        if isinstance(be, Pipeline) and len(be.steps) == 2 and isinstance(be.steps[0][1], MinMaxScaler) \
+        if isinstance(be, Pipeline) and len(be.steps) == 2 and _plain_minmax(be.steps[0][1]) \
                 and (type(be.steps[1][1]) is KerasAutoEncoder or isinstance(be.steps[1][1], KerasLSTMBaseEstimator)):
             return be.steps[1][1]
         return None
@@ -133,20 +218,40 @@ class FleetModelBuilder:
         return (topo.key(), fit)
 
     # ------------------------------------------------------------------ one-at-a-time fallback
-    def _build_one(self, model, mc: FleetMachine):
+    def _build_one(self, model, mc: FleetMachine, metrics: bool = False):
+        """
+        The reference's own sequence for one Machine (build_model.py:239-339): cross_validate -> fit -> offset ->
+        metadata, through the estimator API.  ``metrics``: also the builder's CV scoring metrics
+        (build_model.py:245-289: 4 metrics x (tags + 1) scorers on MinMax-scaled y / yhat).
+        """
         np.random.seed(int(mc.evaluation.get("seed", 0)))
         X = mc.X if isinstance(mc.X, pd.DataFrame) else pd.DataFrame(np.asarray(mc.X))
         y = X if mc.y is None else (mc.y if isinstance(mc.y, pd.DataFrame) else pd.DataFrame(np.asarray(mc.y)))
-        meta: Dict[str, Any] = {"name": mc.name}
+        meta: Dict[str, Any] = {"name": mc.name, "cross_validation": {"scores": {}, "splits": {}}}
         t0 = time.time()
-        if mc.evaluation.get("cv_mode", "full_build") != "build_only" and hasattr(model, "cross_validate"):
-            from sklearn.model_selection import TimeSeriesSplit
-            model.cross_validate(X=X, y=y, cv=TimeSeriesSplit(n_splits=int(mc.evaluation.get("n_splits", 3))))
+        cv_mode = mc.evaluation.get("cv_mode", "full_build")
+        if cv_mode != "build_only" and hasattr(model, "predict"):
+            from sklearn.model_selection import TimeSeriesSplit, cross_validate
+            cv = TimeSeriesSplit(n_splits=int(mc.evaluation.get("n_splits", 3)))
+            kwargs = {}
+            if metrics:
+                kwargs["scoring"] = _metrics_dict(y, mc.evaluation.get("scoring_scaler", "sklearn.preprocessing.MinMaxScaler"))
+            if hasattr(model, "cross_validate"):
+                cvo = model.cross_validate(X=X, y=y, cv=cv, **kwargs)
+            else:
+                cvo = cross_validate(model, X=X, y=y, cv=cv, return_estimator=True, **kwargs)
+            for name in kwargs.get("scoring", {}):
+                v = np.asarray(cvo[f"test_{name}"], np.float64)
+                d = {"fold-mean": float(v.mean()), "fold-std": float(v.std()), "fold-max": float(v.max()), "fold-min": float(v.min())}
+                d.update({f"fold-{i + 1}": float(x) for i, x in enumerate(v)})
+                meta["cross_validation"]["scores"][name] = d
+            meta["cross_validation"]["splits"] = {f"fold-{i + 1}-n-train": int(len(tr)) for i, (tr, _) in enumerate(cv.split(X))}
             meta["cv_duration_sec"] = time.time() - t0
-        t1 = time.time()
-        model.fit(X, y)
-        meta["model_training_duration_sec"] = time.time() - t1
-        meta["model_offset"] = len(X) - len(model.predict(X))
+        if cv_mode != "cross_val_only":
+            t1 = time.time()
+            model.fit(X, y)
+            meta["model_training_duration_sec"] = time.time() - t1
+            meta["model_offset"] = len(X) - len(model.predict(X))
         meta["model"] = model.get_metadata() if hasattr(model, "get_metadata") else {}
         return model, meta
 
@@ -189,26 +294,36 @@ class FleetModelBuilder:
         fleet = FFFleet(topo, M, dev)
         in_scale, in_min = FFFleet.minmax_fit(xd, lo_t, hi_t)                 # Pipeline's MinMaxScaler per job
         err_scale, _ = FFFleet.minmax_fit(ysrc, lo_t, hi_t)                   # detector scaler per job (diff.py:173)
-        seed = int(mcs[0].evaluation.get("seed", 0))
-        gen = torch.Generator(device=dev); gen.manual_seed(seed)
-        params = topo.glorot_init(J, gen, dev)
+        # every fit job draws its initial weights and its per-epoch permutations from ITS OWN generator, seeded as
+        # the per-Machine path seeds it (job_seeds): a Machine's model does not depend on which bucket it shares
+        gen = torch.Generator(device=dev)
         n_job = (np.asarray(hi) - np.asarray(lo)).astype(np.int64)
         is_kfcv = type(protos[0]) is DiffBasedKFCVAnomalyDetector
+        kf_shuffle = is_kfcv and protos[0].shuffle and not do_shuffle
+        params = torch.empty((J, P), dtype=torch.float32, device=dev)
+        perms = []
+        for m, mc in enumerate(mcs):
+            for i, sd in enumerate(job_seeds(int(mc.evaluation.get("seed", 0)), per)):
+                j = m * per + i
+                gen.manual_seed(sd)
+                params[j] = topo.glorot_init(1, gen, dev)[0]
+                if do_shuffle and n_job[j] > 0:
+                    perms += [torch.randperm(int(n_job[j]), generator=gen, device=dev) for _ in range(epochs)]
         pool = poff = None
-        if is_kfcv and protos[0].shuffle and not do_shuffle:
+        if kf_shuffle:
             # diff.py:166-170: rows shuffled once with random_state=0, then fed in that order every epoch
-            perms = []
+            hp = []
             for nj in n_job:
                 idx = np.arange(int(nj)); np.random.RandomState(0).shuffle(idx)
-                perms.append(np.tile(idx, epochs))
-            pool = torch.as_tensor(np.concatenate(perms).astype(np.int32), device=dev)
-            poff = torch.as_tensor(np.concatenate([[0], np.cumsum(n_job * epochs)[:-1]]).astype(np.int64), device=dev)
-        elif do_shuffle:
-            pool = segmented_randperm(np.repeat(n_job, epochs), gen, dev)
+                hp.append(np.tile(idx, epochs))
+            pool = torch.as_tensor(np.concatenate(hp).astype(np.int32), device=dev)
+        elif do_shuffle and perms:
+            pool = torch.cat(perms).to(torch.int32).contiguous()
+        if pool is not None:
             poff = torch.as_tensor(np.concatenate([[0], np.cumsum(n_job * epochs)[:-1]]).astype(np.int64), device=dev)
         hl, ha, _, _ = fleet.fit_jobs(xd, yd, lo_t, hi_t, params, in_scale=in_scale, in_min=in_min, epochs=epochs,
                                       batch_size=batch, perm_pool=pool, perm_off=poff, l1_mean=l1_mean)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         t_fit = time.time() - t_start
 
         feat_pf = agg_pf = None
@@ -260,7 +375,7 @@ class FleetModelBuilder:
             fleet.feat_thr = kf_feat.float().contiguous(); fleet.agg_thr = kf_agg.float().contiguous()
         elif k:
             fleet.feat_thr = feat_pf[:, -1].contiguous(); fleet.agg_thr = agg_pf[:, -1].contiguous()
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         t_total = time.time() - t_start
         self.last_fleet = fleet
         self.last_schedule_rows = rows
@@ -299,7 +414,9 @@ class FleetModelBuilder:
                 model.aggregate_threshold_ = float(agg_h[m, -1])
                 _set_smooth_thresholds(model, None if sfeat_h is None else sfeat_h[m], None if sagg_h is None else sagg_h[m], tags, k)
             scores = _cv_score_dict({kk: v[m * k:(m + 1) * k] for kk, v in cv_metrics.items()}, tags) if k else {}
-            meta = {"name": mc.name, "model_offset": 0, "model": model.get_metadata(),
+            # build_model.py:448-471: offset = len(X) - len(predict(X)); the feed-forward scorer emits one row per input row
+            meta = {"name": mc.name, "model_offset": int(rows[m]) - fleet.out_rows(int(rows[m])), "model": model.get_metadata(),
+                    "model_training_duration_sec": t_fit, "cv_duration_sec": (t_total - t_fit) if k else None,
                     "cross_validation": {"scores": scores,
                                          "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
                                                     enumerate(time_series_split_bounds(int(rows[m]), k))} if k else {}},
@@ -356,8 +473,12 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
     t0 = time.time()
     in_scale, in_min = FFFleet.minmax_fit(xd, lo_t, hi_t)
     err_scale, _ = FFFleet.minmax_fit(yd, lo_t, hi_t)
-    gen = torch.Generator(device=dev); gen.manual_seed(int(mcs[0].evaluation.get("seed", 0)))
-    params = topo.init_params(J, gen, dev)
+    gen = torch.Generator(device=dev)
+    params = torch.empty((J, topo.n_params), dtype=torch.float32, device=dev)
+    for m, mc in enumerate(mcs):
+        for i, sd in enumerate(job_seeds(int(mc.evaluation.get("seed", 0)), per)):
+            gen.manual_seed(sd)
+            params[m * per + i] = topo.init_params(1, gen, dev)[0]
     trainer = LSTMFleet(topo, J, lookahead, dev)
     hl, pl = trainer.fit_jobs(xd, yd, lo, hi, params, in_scale=in_scale, in_min=in_min, epochs=epochs, batch_size=batch)
     feat_h = agg_h = None
@@ -380,7 +501,7 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
         if win is not None:
             sfeat_h = FFFleet.rolling_min_max(res["tag-anomaly-unscaled"], ol, oh, win).reshape(M, k, To).double().cpu().numpy()
             sagg_h = FFFleet.rolling_min_max(res["total-anomaly-scaled"], ol, oh, win).reshape(M, k).double().cpu().numpy()
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()
     t_total = time.time() - t0
     P_host = params.cpu().numpy(); hl_h = hl.cpu().numpy(); pl_h = pl.cpu().numpy()
     in_scale_h = in_scale.double().cpu().numpy(); in_min_h = in_min.double().cpu().numpy(); es_h = err_scale.double().cpu().numpy()
@@ -403,13 +524,17 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
             model.feature_thresholds_ = pd.Series(feat_h[m, -1], index=tags, name=f"fold-{k - 1}")
             model.aggregate_threshold_ = float(agg_h[m, -1])
             _set_smooth_thresholds(model, None if sfeat_h is None else sfeat_h[m], None if sagg_h is None else sagg_h[m], tags, k)
-        meta = {"name": mc.name, "model_offset": L - 1 + lookahead, "model": model.get_metadata(),
+        # build_model.py:448-471: len(X) - len(predict(X)), from the fleet's own output-row count
+        meta = {"name": mc.name, "model_offset": int(rows[m]) - trainer.out_rows(int(rows[m])), "model": model.get_metadata(),
+                "model_training_duration_sec": t_total, "cv_duration_sec": None,
+                "cross_validation": {"scores": {}, "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
+                                                              enumerate(time_series_split_bounds(int(rows[m]), k))} if k else {}},
                 "fleet": {"machines_in_launch": M, "fit_jobs": J, "build_duration_sec": t_total}}
         out_models.append((model, meta))
     return out_models
 
 
-FleetModelBuilder._build_bucket_lstm = _build_bucket_lstm_impl
+FleetBuild._build_bucket_lstm = _build_bucket_lstm_impl
 
 
 def _cv_score_dict(metrics: Dict[str, np.ndarray], tags) -> Dict[str, Dict[str, float]]:
@@ -446,3 +571,214 @@ def _set_minmax(scaler: MinMaxScaler, scale, min_, data, frame):
     scaler.n_samples_seen_ = len(data)
     if isinstance(frame, pd.DataFrame) and all(isinstance(c, str) for c in frame.columns):
         scaler.feature_names_in_ = np.asarray(frame.columns, dtype=object)
+
+
+# ======================================================================================== the builder seam
+try:                                        # gordo installed: be a real ModelBuilder (builder/utils.py:8-17)
+    from gordo.builder.build_model import ModelBuilder as _ReferenceModelBuilder
+except Exception:                           # not installed (this image): same public contract, standalone
+    _ReferenceModelBuilder = None
+
+DEFAULT_METRICS = ("explained_variance_score", "r2_score", "mean_squared_error", "mean_absolute_error")
+
+
+def redirect_definition(definition, enable: bool = True):
+    """``gordo.machine.model.*`` class paths of a model definition -> ``gordo_b200.machine.model.*`` (deep copy)."""
+    if not enable:
+        return definition
+    src, dst = "gordo.machine.model.", "gordo_b200.machine.model."
+    if isinstance(definition, str):
+        return dst + definition[len(src):] if definition.startswith(src) else definition
+    if isinstance(definition, dict):
+        return {redirect_definition(k): redirect_definition(v) for k, v in definition.items()}
+    if isinstance(definition, (list, tuple)):
+        return type(definition)(redirect_definition(v) for v in definition)
+    return definition
+
+
+def build_metadata_dict(meta: Dict[str, Any], builder_version: str = "gordo_b200") -> Dict[str, Any]:
+    """A FleetBuild metadata record in the layout of gordo.machine.metadata.BuildMetadata (metadata.py:17-56)."""
+    cv = meta.get("cross_validation", {})
+    return {"model": {"model_offset": int(meta.get("model_offset", 0)),
+                      "model_creation_date": str(datetime.datetime.now(datetime.timezone.utc).astimezone()),
+                      "model_builder_version": builder_version,
+                      "model_training_duration_sec": meta.get("model_training_duration_sec"),
+                      "cross_validation": {"cv_duration_sec": meta.get("cv_duration_sec"),
+                                           "scores": cv.get("scores", {}), "splits": cv.get("splits", {})},
+                      "model_meta": meta.get("model", {})},
+            "dataset": {"query_duration_sec": meta.get("query_duration_sec"), "dataset_meta": meta.get("dataset_meta", {})}}
+
+
+class _StandaloneModelBuilder:
+    """
+    ``ModelBuilder``'s public contract (build_model.py:49-190) without gordo: ``machine`` is a ``FleetMachine``
+    (data already fetched) or any object with ``name``, ``model``, ``evaluation`` and ``dataset.get_data()``.
+    """
+
+    def __init__(self, machine, back_compatibles=None, default_data_provider=None):
+        self.machine = machine
+        self.back_compatibles = back_compatibles
+        self.default_data_provider = default_data_provider
+        self._cached_model_path = None
+
+    @property
+    def cached_model_path(self):
+        return self._cached_model_path
+
+    @cached_model_path.setter
+    def cached_model_path(self, value):
+        self._cached_model_path = value
+
+    @property
+    def gordo_version(self):
+        return "gordo_b200"
+
+    def set_seed(self, seed: int):
+        import random
+        np.random.seed(seed)
+        random.seed(seed)
+
+    @staticmethod
+    def _determine_offset(model, X) -> int:
+        X = getattr(X, "values", X)
+        out = model.predict(X) if hasattr(model, "predict") else model.transform(X)
+        return len(X) - len(out)
+
+    def build(self, output_dir=None, model_register_dir=None, replace_cache=False):
+        """(model, machine) like ModelBuilder.build (build_model.py:104-190); the disk registry is gordo's own."""
+        if model_register_dir:
+            raise NotImplementedError("the model register (gordo.util.disk_registry) needs gordo itself")
+        model, machine = self._build()
+        if output_dir and getattr(machine, "evaluation", {}).get("cv_mode") != "cross_val_only":
+            import json
+            import os
+            import pickle
+            os.makedirs(output_dir, exist_ok=True)
+            with open(os.path.join(output_dir, "model.pkl"), "wb") as f:      # serializer/serializer.py:189-196
+                pickle.dump(model, f)
+            with open(os.path.join(output_dir, "metadata.json"), "w") as f:
+                json.dump({"name": machine.name, "metadata": {"build_metadata": machine.build_metadata}}, f, default=str)
+            self.cached_model_path = output_dir
+        return model, machine
+
+
+class FleetModelBuilder(_ReferenceModelBuilder or _StandaloneModelBuilder):
+    """
+    ``--model-builder-class gordo_b200.builder.FleetModelBuilder`` (cli/cli.py:81-86,147-150).
+
+    * ``FleetModelBuilder(machine).build(...)`` -- one Machine, the reference's contract: ``(model, machine)``.
+      With gordo installed this IS ``ModelBuilder.build`` (dataset fetch, CV, fit, offset, metadata, cache,
+      ``serializer.dump`` all inherited); ``gordo.machine.model.*`` class paths of the Machine's model are
+      redirected to their ``gordo_b200`` twins first (``redirect_gordo``), so an unmodified project builds on the GPU.
+    * ``FleetModelBuilder.build_fleet(machines)`` -- the whole project at once (FleetBuild), one entry per Machine.
+    * ``FleetModelBuilder.build_sharded(machines, rank, world)`` -- one process per GPU, Machines dealt by cost.
+    """
+
+    redirect_gordo = True
+
+    def _build(self):
+        if _ReferenceModelBuilder is not None:
+            if self.redirect_gordo:
+                self.machine.model = redirect_definition(self.machine.model)
+            return super()._build()
+        mc = _as_fleet_machine(self.machine)
+        model = serializer.from_definition(redirect_definition(mc.definition(), self.redirect_gordo))
+        self.set_seed(int(mc.evaluation.get("seed", 0)))
+        built, meta = FleetBuild([mc])._build_one(model, mc, metrics=True)
+        mc.build_metadata = build_metadata_dict(meta, self.gordo_version)
+        return built, mc
+
+    # ------------------------------------------------------------------ the fleet
+    @classmethod
+    def build_fleet(cls, machines: Sequence[Any], device: Optional[str] = None, streams: int = 8,
+                    cv_precision: str = "f32"):
+        """
+        Batched twin of ``for machine in machines: ModelBuilder(machine).build()`` (local_build.py:67-70).
+        Returns ``[(model, machine)]``; ``machine.build_metadata`` (FleetMachine) or
+        ``machine.metadata.build_metadata`` (gordo Machine) carries the reference's BuildMetadata record, and the
+        raw FleetBuild record stays available as ``machine.fleet_metadata``.
+        """
+        fms = [_as_fleet_machine(m) for m in machines]
+        for fm in fms:
+            fm.model = redirect_definition(fm.definition(), cls.redirect_gordo)
+        built = FleetBuild(fms, device=device, cv_precision=cv_precision, streams=streams).build()
+        out = []
+        for src, fm, (model, meta) in zip(machines, fms, built):
+            record = build_metadata_dict(meta)
+            target = src if not isinstance(src, FleetMachine) else fm
+            if hasattr(target, "metadata") and hasattr(target.metadata, "build_metadata") and _ReferenceModelBuilder is not None:
+                from gordo.machine.metadata import BuildMetadata
+                target.metadata.build_metadata = BuildMetadata.from_dict(record)
+            else:
+                target.build_metadata = record
+            target.fleet_metadata = meta
+            out.append((model, target))
+        return out
+
+    @classmethod
+    def local_build(cls, config_str: str, **kw):
+        """``gordo.builder.local_build`` (local_build.py:14-70) with the Machines built as one fleet; needs gordo."""
+        if _ReferenceModelBuilder is None:
+            raise ImportError("FleetModelBuilder.local_build parses a gordo project config: gordo is not installed")
+        import io
+        from gordo.workflow.config_elements.normalized_config import NormalizedConfig
+        from gordo.workflow.workflow_generator.workflow_generator import get_dict_from_yaml
+        normed = NormalizedConfig(get_dict_from_yaml(io.StringIO(config_str)), project_name="local-build")
+        return cls.build_fleet(normed.machines, **kw)
+
+    # ------------------------------------------------------------------ one process per GPU
+    @staticmethod
+    def shard_indices(machines: Sequence[Any], world_size: int) -> List[List[int]]:
+        """Machines dealt to ranks by estimated cost, largest first (partition.lpt)."""
+        from gordo_b200.partition import lpt, machine_cost
+        costs = []
+        for m in machines:
+            fm = _as_fleet_machine(m)
+            n, T = np.shape(getattr(fm.X, "values", fm.X))[:2]
+            d = str(fm.definition())
+            lstm = "LSTM" in d
+            look = 1
+            if lstm:
+                import re
+                hit = re.search(r"lookback_window'?:\s*(\d+)", d)
+                look = int(hit.group(1)) if hit else 1
+            w = [T, max(1, round(0.83 * T)), max(1, round(0.67 * T)), max(1, round(0.5 * T))]
+            f = 2.0 * 2 * sum(a * b for a, b in zip(w[:-1], w[1:]))
+            costs.append(machine_cost(int(n), f * (4.0 if lstm else 1.0), 1, look))
+        return lpt(costs, world_size)
+
+    @classmethod
+    def build_sharded(cls, machines: Sequence[Any], rank: int, world_size: int, *, gather: bool = False,
+                      build_fn=None, **kw) -> Dict[int, Any]:
+        """
+        This rank's share of the project: ``{machine index: (model, machine)}``.  No data-path collective --
+        Machines are independent; with ``gather=True`` (torch.distributed initialised) rank 0 receives every
+        rank's results (pickled host objects), which is the host-side concat of SURVEY.md §8e.
+        """
+        mine = cls.shard_indices(machines, world_size)[rank]
+        build = build_fn or (lambda ms: cls.build_fleet(ms, **kw))
+        results = dict(zip(mine, build([machines[i] for i in mine])))
+        if gather:
+            import torch.distributed as dist
+            parts = [None] * world_size if rank == 0 else None
+            dist.gather_object(results, parts, dst=0)
+            if rank == 0:
+                results = {k: v for part in parts for k, v in part.items()}
+        return results
+
+
+def _as_fleet_machine(machine) -> FleetMachine:
+    if isinstance(machine, FleetMachine):
+        return machine
+    if hasattr(machine, "dataset") and not hasattr(machine, "X"):
+        ds = machine.dataset
+        if _ReferenceModelBuilder is not None and not hasattr(ds, "get_data"):
+            from gordo_core.base import GordoBaseDataset
+            ds = GordoBaseDataset.from_dict(machine.dataset.to_dict())
+        t0 = time.time()
+        X, y = ds.get_data()
+        fm = FleetMachine(name=machine.name, X=X, y=y, model=machine.model, evaluation=dict(machine.evaluation or {}))
+        fm.query_duration_sec = time.time() - t0
+        return fm
+    return FleetMachine(name=machine.name, X=machine.X, y=getattr(machine, "y", None), model=getattr(machine, "model", None),
+                        evaluation=dict(getattr(machine, "evaluation", {}) or {}))

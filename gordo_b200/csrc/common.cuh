@@ -7,6 +7,12 @@
 #include <math.h>
 #include "../../include/gordo_b200.h"
 
+// Opt-in shared-memory ceiling of sm_100 (227 KB).  Every kernel with a run-time smem size raises its
+// limit to THIS constant, never to the size of the launch at hand: cudaFuncSetAttribute is
+// process-global, and two host threads launching the same kernel for different topologies on
+// different streams would otherwise race on it.
+#define GB_SMEM_OPTIN_MAX 232448
+
 #define GB_OK 0
 #define GB_ERR_ARG -1
 #define GB_ERR_CUDA -2

@@ -38,6 +38,7 @@ struct FitArgs {
     int Bs;                 // sample stride of h and D (multiple of 4: 16-byte reads along the batch)
     int Bq;                 // 4-sample groups per batch
     const int32_t* order;   // CTA -> job, longest job first
+    float* scratch;         // HG: per-job activations + deltas in global memory (2 * h_floats floats each)
 };
 
 // Jobs differ in length (CV folds of 1/4, 2/4, 3/4 of the rows next to full final fits) and CTAs are
@@ -84,7 +85,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // parameter so that the compiler knows the address space: plain LDS/STS with 32-bit addressing
 // instead of generic loads in every inner loop.
 // BQ: 4-sample groups per batch when known at compile time (8 = Keras' default batch of 32), else 0.
-template <int STATE, int BQ>
+// HG: the batch's activations and deltas do not fit in shared memory next to nothing else (wide default
+// topologies such as 256-128-64, or batch_size 128 with > 60 tags): they live in a per-job global scratch
+// (L1/L2 resident: a few hundred KB) and shared memory only holds W when that fits.  Same arithmetic,
+// same order of operations; __syncthreads() orders the global accesses of the block as it does the shared ones.
+template <int STATE, int BQ, bool HG = false>
 __global__ void __launch_bounds__(FIT_THREADS, 1)
 ff_fit_kernel(const __grid_constant__ FitArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -98,9 +103,9 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
     const int Bq = BQ ? BQ : a.Bq, Bs = BQ ? 4 * BQ + 4 : a.Bs;
     const int64_t P = a.n_params;
 
-    float* hbuf = smem;                               // all layer activations of the batch
+    float* hbuf = HG ? a.scratch + (size_t)job * 2 * a.h_floats : smem;      // all layer activations of the batch
     float* Dall = hbuf + a.h_floats;                  // dLoss/dz of every layer, laid out like hbuf
-    float* st = Dall + a.h_floats;                    // optional on-chip W / m / v
+    float* st = HG ? smem : Dall + a.h_floats;        // optional on-chip W / m / v
     float* gW = a.params + (size_t)job * P;
     float* gM = a.adam_mv + (size_t)job * 2 * P;
     float* gV = gM + P;
@@ -209,22 +214,24 @@ ff_fit_kernel(const __grid_constant__ FitArgs a) {
                     }
                     DL[nn * Bs + b] = dv;
                 }
-                if (tid < nb && a.hist_acc) {
+                if (a.hist_acc) {
                     // Keras 'accuracy' on a float [B,T] target = categorical accuracy; binary at T_out == 1
-                    const int64_t r = r_lo + (perm ? perm[(int64_t)e * n + s0 + tid] : s0 + tid);
-                    int hit;
-                    if (T_out == 1) {
-                        hit = ((hL[tid] > 0.5f ? 1.0f : 0.0f) == ysrc[r]) ? 1 : 0;
-                    } else {
-                        int ay = 0, ap = 0; float by = ysrc[r * T_out], bp = hL[tid];
-                        for (int j = 1; j < T_out; ++j) {
-                            const float vy = ysrc[r * T_out + j], vp = hL[j * Bs + tid];
-                            if (vy > by) { by = vy; ay = j; }
-                            if (vp > bp) { bp = vp; ap = j; }
+                    for (int b = tid; b < nb; b += FIT_THREADS) {
+                        const int64_t r = r_lo + (perm ? perm[(int64_t)e * n + s0 + b] : s0 + b);
+                        int hit;
+                        if (T_out == 1) {
+                            hit = ((hL[b] > 0.5f ? 1.0f : 0.0f) == ysrc[r]) ? 1 : 0;
+                        } else {
+                            int ay = 0, ap = 0; float by = ysrc[r * T_out], bp = hL[b];
+                            for (int j = 1; j < T_out; ++j) {
+                                const float vy = ysrc[r * T_out + j], vp = hL[j * Bs + b];
+                                if (vy > by) { by = vy; ay = j; }
+                                if (vp > bp) { bp = vp; ap = j; }
+                            }
+                            hit = ay == ap;
                         }
-                        hit = ay == ap;
+                        if (hit) atomicAdd(&s_argmax_hits, 1);
                     }
-                    if (hit) atomicAdd(&s_argmax_hits, 1);
                 }
             }
             if (a.hist_loss) {
@@ -355,16 +362,25 @@ int gb_launch_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int n_jo
     a.Bq = (batch_size + 3) / 4;
     a.Bs = 4 * a.Bq + 4;            // 16-byte rows; +4 keeps the 8 row groups of a warp on distinct banks
     a.h_floats = sum_w * a.Bs;
-    const size_t base = 2 * (size_t)a.h_floats * sizeof(float);      // activations + one delta slot per activation
+    size_t base = 2 * (size_t)a.h_floats * sizeof(float);      // activations + one delta slot per activation
     const size_t cap = 227 * 1024 - 256;
-    GB_REQUIRE(base <= cap, "ff_fit: batch_size %d x widths do not fit in shared memory", batch_size);
     GB_REQUIRE(a.n_params < (1ll << 30), "ff_fit: topology too large");
+    const bool hg = base > cap;         // the batch's activations go to a global scratch (see the HG note)
+    float* scratch = nullptr;
+    if (hg) {
+        GB_REQUIRE((size_t)n_jobs * base < (64ull << 30), "ff_fit: batch_size %d x widths need too much scratch", batch_size);
+        GB_CUDA_CHECK(cudaMallocAsync(&scratch, (size_t)n_jobs * base, stream));
+        base = 0;
+    }
+    a.scratch = scratch;
     const size_t pbytes = (size_t)a.n_params * sizeof(float);
     a.state_in_smem = base + 3 * pbytes <= cap ? 2 : (base + pbytes <= cap ? 1 : 0);
     const size_t smem = base + (a.state_in_smem == 2 ? 3 * pbytes : a.state_in_smem == 1 ? pbytes : 0);
-    auto* kern = a.state_in_smem == 2 ? (a.Bq == 8 ? ff_fit_kernel<2, 8> : ff_fit_kernel<2, 0>)
+    auto* kern = hg ? (a.state_in_smem == 2 ? ff_fit_kernel<2, 0, true> : a.state_in_smem == 1 ? ff_fit_kernel<1, 0, true>
+                                                                                                 : ff_fit_kernel<0, 0, true>)
+               : a.state_in_smem == 2 ? (a.Bq == 8 ? ff_fit_kernel<2, 8> : ff_fit_kernel<2, 0>)
                : a.state_in_smem == 1 ? ff_fit_kernel<1, 0> : ff_fit_kernel<0, 0>;
-    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
     int32_t* order = nullptr;
     if (n_jobs > 1) {
         GB_CUDA_CHECK(cudaMallocAsync(&order, sizeof(int32_t) * n_jobs, stream));
@@ -374,6 +390,7 @@ int gb_launch_ff_fit(const gb200_ff_arch* arch, const gb200_adam* adam, int n_jo
     kern<<<n_jobs, FIT_THREADS, smem, stream>>>(a);
     cudaError_t le = cudaGetLastError();
     if (order) cudaFreeAsync(order, stream);
+    if (scratch) cudaFreeAsync(scratch, stream);
     GB_CUDA_CHECK(le);
     return GB_OK;
 }

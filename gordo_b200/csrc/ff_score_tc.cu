@@ -558,7 +558,7 @@ int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const
     int tot = 32; while (tot < nwg * cols) tot <<= 1;
     a.tmem_cols_total = tot;
     const size_t smem = fixed + nwg * per_wg;
-    GB_CUDA_CHECK(cudaFuncSetAttribute(ff_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA_CHECK(cudaFuncSetAttribute(ff_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
     int grid = f->sm_count;
     const int min_tiles_per_cta = nwg;            // keep every warpgroup of a CTA busy
     const int max_grid = (f->tiles_total + min_tiles_per_cta - 1) / min_tiles_per_cta;

@@ -6,13 +6,17 @@
 
 namespace {
 
+// float min / max through integer atomics: the branch is on the SIGN BIT (not on v >= 0, which is
+// true for -0.0f and would send its bit pattern 0x80000000 = INT_MIN down the signed path)
 __device__ __forceinline__ void atomic_min_f(float* addr, float v) {
-    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
-    else           atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+    v += 0.0f;                                   // canonicalise -0.0 to +0.0
+    if (__float_as_int(v) >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else                        atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_max_f(float* addr, float v) {
-    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-    else           atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+    v += 0.0f;
+    if (__float_as_int(v) >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else                        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
 constexpr int RED_THREADS = 256;

@@ -8,6 +8,7 @@ This is the batched twin of what the reference does one Machine at a time:
 PyTorch is used for device memory, streams and RNG only.
 """
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -98,6 +99,7 @@ class Schedule:
         return self._h
 
     _single: "Dict[tuple, Schedule]" = {}
+    _single_lock = threading.Lock()
 
     @classmethod
     def single(cls, n_rows: int) -> "Schedule":
@@ -106,11 +108,12 @@ class Schedule:
         few frame lengths again and again, and creating a schedule costs device allocations.
         """
         key = (torch.cuda.current_device(), int(n_rows))
-        sch = cls._single.get(key)
-        if sch is None:
-            if len(cls._single) >= 64:
-                cls._single.pop(next(iter(cls._single)))
-            sch = cls._single[key] = cls([int(n_rows)])
+        with cls._single_lock:                  # gordo.server shares one model between gthread workers
+            sch = cls._single.get(key)
+            if sch is None:
+                if len(cls._single) >= 64:
+                    cls._single.pop(next(iter(cls._single)))
+                sch = cls._single[key] = cls([int(n_rows)])
         return sch
 
     def __del__(self):
@@ -148,6 +151,11 @@ class FFFleet:
         self._packed = None
         self._packed_version = -1
         self._version = 0
+        self._pack_lock = threading.Lock()
+
+    def out_rows(self, n_rows: int) -> int:
+        """Rows ``predict`` returns for ``n_rows`` input rows (a Dense stack: one per row; cf. LSTMFleet.out_rows)."""
+        return int(n_rows)
 
     # ------------------------------------------------------------------ parameters
     def set_params(self, params: torch.Tensor):
@@ -176,16 +184,18 @@ class FFFleet:
 
     def packed(self) -> torch.Tensor:
         """bf16 tcgen05 operand image of the current weights (re-packed when they change)."""
-        if self._packed is None or self._packed_version != self._version:
-            nbytes = N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch))
-            if nbytes <= 0:
-                raise ValueError("topology is not eligible for the tensor-core path")
-            if self._packed is None:
-                self._packed = torch.empty((self.M, nbytes), dtype=torch.uint8, device=self.device)
-            N.check(N.lib().gb200_ff_pack_bf16(C.byref(self.topo.arch), self.M, N.ptr(self.params),
-                                               N.ptr(self._packed), _stream_ptr()), "gb200_ff_pack_bf16")
-            self._packed_version = self._version
-        return self._packed
+        with self._pack_lock:
+            if self._packed is None or self._packed_version != self._version:
+                nbytes = N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch))
+                if nbytes <= 0:
+                    raise ValueError("topology is not eligible for the tensor-core path")
+                packed = torch.empty((self.M, nbytes), dtype=torch.uint8, device=self.device)
+                N.check(N.lib().gb200_ff_pack_bf16(C.byref(self.topo.arch), self.M, N.ptr(self.params),
+                                                   N.ptr(packed), _stream_ptr()), "gb200_ff_pack_bf16")
+                if torch.cuda.current_stream() != torch.cuda.default_stream():
+                    torch.cuda.current_stream().synchronize()      # another thread / stream may read it next
+                self._packed, self._packed_version = packed, self._version
+            return self._packed
 
     # ------------------------------------------------------------------ scalers / thresholds
     @staticmethod

@@ -30,6 +30,13 @@ from gordo_b200.machine.model.base import GordoBase
 from gordo_b200.machine.model.models import KerasAutoEncoder, KerasLSTMBaseEstimator
 
 
+import threading
+
+# gordo.server shares ONE model object between its gthread workers (server/utils.py:334-335): creating the
+# device-side serving state is serialised; scoring itself runs concurrently (stream-ordered, per-call buffers)
+_SERVING_LOCK = threading.RLock()
+
+
 def _rows(a, idx):
     return a.iloc[idx] if isinstance(a, pd.DataFrame) else a[idx]
 
@@ -214,8 +221,8 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         """(input MinMaxScaler or None, KerasAutoEncoder) when the fused launch applies, else None."""
         if not isinstance(self.scaler, MinMaxScaler) or not hasattr(self.scaler, "scale_"):
             return None
-        if tuple(getattr(self.scaler, "feature_range", (0, 1))) != (0, 1):
-            return None
+        if tuple(getattr(self.scaler, "feature_range", (0, 1))) != (0, 1) or getattr(self.scaler, "clip", False):
+            return None         # the fused |d| * scale_ identity only holds for an unclipped (0, 1) scaler
         be = self.base_estimator
         ours = lambda e: (type(e) is KerasAutoEncoder or isinstance(e, KerasLSTMBaseEstimator)) and e.model is not None
         if ours(be):
@@ -280,6 +287,15 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         cached = self.__dict__.get("_gb200_serving")
         if cached is not None and cached[0] == key:
             return cached[1]
+        with _SERVING_LOCK:
+            return self._serving_fleet_build(key, sc, est, topo, dev, feat, agg)
+
+    def _serving_fleet_build(self, key, sc, est, topo, dev, feat, agg):
+        import torch
+        from gordo_b200.fleet import FFFleet
+        cached = self.__dict__.get("_gb200_serving")
+        if cached is not None and cached[0] == key:             # another thread built it while this one waited
+            return cached[1]
         fleet = FFFleet(topo, 1, dev)
         fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
         f32 = lambda a: torch.as_tensor(np.array(a, np.float32)[None], device=dev)
@@ -308,15 +324,16 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         parts = [est.model.params] + ([np.asarray(sc.scale_), np.asarray(sc.min_)] if sc is not None else [])
         key = (dev.index, id(est.model), est.lookahead, sc is None,
                hash(b"".join(np.ascontiguousarray(a).tobytes() for a in parts)))
-        cached = self.__dict__.get("_gb200_serving_lstm")
-        if cached is not None and cached[0] == key:
-            fleet = cached[1]
-        else:
-            fleet = LSTMFleet(topo, 1, est.lookahead, dev)
-            fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
-            if sc is not None:
-                fleet.in_scale, fleet.in_min = f32(sc.scale_), f32(sc.min_)
-            self.__dict__["_gb200_serving_lstm"] = (key, fleet)
+        with _SERVING_LOCK:
+            cached = self.__dict__.get("_gb200_serving_lstm")
+            if cached is not None and cached[0] == key:
+                fleet = cached[1]
+            else:
+                fleet = LSTMFleet(topo, 1, est.lookahead, dev)
+                fleet.set_params(torch.as_tensor(est.model.params[None], device=dev))
+                if sc is not None:
+                    fleet.in_scale, fleet.in_min = f32(sc.scale_), f32(sc.min_)
+                self.__dict__["_gb200_serving_lstm"] = (key, fleet)
         xd = torch.as_tensor(np.ascontiguousarray(Xv, np.float32), device=dev)
         yd = torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
         prec = est._precision if fleet.tc_eligible() else "f32"

@@ -16,6 +16,7 @@ Selectable purely from Machine YAML:
 """
 import importlib
 import logging
+import threading
 from copy import copy, deepcopy
 from importlib.util import find_spec
 from typing import Any, Callable, Dict, Optional, Tuple, Union
@@ -31,6 +32,10 @@ from gordo_b200.machine.model.factories import *  # noqa: F401,F403  (registers 
 from gordo_b200.machine.model.register import register_model_builder
 
 logger = logging.getLogger(__name__)
+
+# one fitted model object is shared by the server's gthread workers (gordo/server/utils.py:334-335):
+# creating its device-side serving state is serialised, predicting is not
+_SERVING_LOCK = threading.RLock()
 
 
 def _torch():
@@ -371,13 +376,14 @@ class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
         dev = torch.device("cuda", torch.cuda.current_device())
         # the device copy of the weights (and their bf16 operand image) is kept between calls
         key = (dev.index, id(self.model), hash(self.model.params.tobytes()))
-        cached = self.__dict__.get("_gb200_serving")
-        if cached is not None and cached[0] == key:
-            fleet = cached[1]
-        else:
-            fleet = FFFleet(topo, 1, dev)
-            fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
-            self.__dict__["_gb200_serving"] = (key, fleet)
+        with _SERVING_LOCK:
+            cached = self.__dict__.get("_gb200_serving")
+            if cached is not None and cached[0] == key:
+                fleet = cached[1]
+            else:
+                fleet = FFFleet(topo, 1, dev)
+                fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
+                self.__dict__["_gb200_serving"] = (key, fleet)
         xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
         prec = fleet.auto_precision(self._precision)
         return fleet.predict(Schedule.single(len(X)), xd, precision=prec).cpu().numpy()
@@ -461,13 +467,14 @@ class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin):
         dev = torch.device("cuda", torch.cuda.current_device())
         # the device copy of the weights and the kernel scratch are kept between calls
         key = (dev.index, id(self.model), self.lookahead, hash(self.model.params.tobytes()))
-        cached = self.__dict__.get("_gb200_serving")
-        if cached is not None and cached[0] == key:
-            fleet = cached[1]
-        else:
-            fleet = LSTMFleet(self.model.topology, 1, self.lookahead, dev)
-            fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
-            self.__dict__["_gb200_serving"] = (key, fleet)
+        with _SERVING_LOCK:
+            cached = self.__dict__.get("_gb200_serving")
+            if cached is not None and cached[0] == key:
+                fleet = cached[1]
+            else:
+                fleet = LSTMFleet(self.model.topology, 1, self.lookahead, dev)
+                fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
+                self.__dict__["_gb200_serving"] = (key, fleet)
         xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
         prec = self._precision if fleet.tc_eligible() else "f32"       # "bf16": tcgen05 step kernel
         out, _ = fleet.predict(Schedule.single(len(X)), xd, precision=prec)

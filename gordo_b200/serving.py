@@ -1,0 +1,332 @@
+"""
+Fleet twin of the reference's anomaly request path.
+
+gordo.server answers ``POST .../anomaly/prediction`` one Machine at a time:
+``anomaly_df = g.model.anomaly(g.X, g.y, frequency=...)`` (gordo/server/blueprints/anomaly.py:50) with host
+frames in and a host frame out.  ``FleetAnomalyServer.anomaly(X)`` is that call for M Machines of
+one topology at once: HOST sample matrices in (pinned, or any array / list of frames), HOST anomaly
+columns out -- every column of diff.py:310-458 materialised in pinned host memory, sliceable per
+Machine and convertible to the reference's frame (``result.frame(m, index, frequency)``).
+
+The call is bound by PCIe and host DRAM, not by the GPU (the fused scorer runs at ~4.6e9 rows/s, a
+Gen5 x16 link moves 1e5 x 50 float32 rows in 0.4 ms).  So the work is split by what is cheapest to move:
+
+  device : MinMax -> Dense stack -> |yhat - y| -> row totals (gb200_ff_score); sends back
+           ``model-output`` and the three total columns, plus the rescaled matrices the plan keeps on the device;
+  host   : the per-column rescalings the plan moves off the wire
+           (``anomaly-confidence``, ``tag-anomaly-scaled``, ``tag-anomaly-unscaled`` -- in that order) are
+           written by gb200_host_expand_columns straight into the response buffers while the next
+           chunk is in flight.
+
+``plan`` = how many of those three matrices the host derives (0..3).  One GPU alone is PCIe-bound
+and wants 3; eight ranks sharing two sockets are host-DRAM-bound and want fewer -- ``plan="auto"``
+times each option on the first call (all ranks do so together) and keeps the fastest.
+
+Chunks of Machines flow through three streams (H2D, kernel, D2H) and three device buffer sets, so
+both PCIe directions and the kernel overlap; a host worker thread expands chunk c while c+1 is on the wire.
+"""
+import ctypes as C
+import queue
+import threading
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .fleet import FFFleet, Schedule
+
+MATRIX_COLUMNS = ("model-output", "tag-anomaly-scaled", "tag-anomaly-unscaled", "anomaly-confidence")
+VECTOR_COLUMNS = ("total-anomaly-scaled", "total-anomaly-unscaled", "total-anomaly-confidence")
+# order in which matrices move from the wire to the host threads as the plan grows
+DERIVE_ORDER = ("anomaly-confidence", "tag-anomaly-scaled", "tag-anomaly-unscaled")
+
+
+class FleetAnomalyResult:
+    """Host columns of one ``FleetAnomalyServer.anomaly`` call (views of the server's pinned buffers)."""
+
+    def __init__(self, columns: Dict[str, torch.Tensor], row_off: np.ndarray, x_host: torch.Tensor, tags=None):
+        self.columns = columns
+        self.row_off = row_off
+        self.model_input = x_host
+        self.tags = tags
+
+    def machine(self, m: int) -> Dict[str, np.ndarray]:
+        a, b = int(self.row_off[m]), int(self.row_off[m + 1])
+        out = {"model-input": self.model_input[a:b].numpy()}
+        out.update({k: v[a:b].numpy() for k, v in self.columns.items()})
+        return out
+
+    def frame(self, m: int, index=None, frequency=None, tags: Optional[Sequence] = None):
+        """The reference's anomaly frame for Machine m (model/utils.py:49-165 layout, diff.py:310-458 columns)."""
+        from gordo_b200.machine.model import utils as model_utils
+        c = self.machine(m)
+        T = c["model-input"].shape[1]
+        tags = list(tags if tags is not None else (self.tags[m] if self.tags is not None else range(T)))
+        names_in = model_utils._second_level(c["model-input"], tags)
+        names_out = model_utils._second_level(c["model-output"], tags)
+        tag_names = [model_utils._tag_name(t) for t in tags]
+        groups = [("model-input", c["model-input"], names_in), ("model-output", c["model-output"], names_out),
+                  ("tag-anomaly-scaled", c["tag-anomaly-scaled"], names_out),
+                  ("total-anomaly-scaled", c["total-anomaly-scaled"], None),
+                  ("tag-anomaly-unscaled", c["tag-anomaly-unscaled"], tag_names),
+                  ("total-anomaly-unscaled", c["total-anomaly-unscaled"], None)]
+        if "anomaly-confidence" in c:
+            groups.append(("anomaly-confidence", c["anomaly-confidence"], names_out))
+        if "total-anomaly-confidence" in c:
+            groups.append(("total-anomaly-confidence", c["total-anomaly-confidence"], None))
+        return model_utils.assemble_frame(groups, index, frequency)
+
+
+class FleetAnomalyServer:
+    def __init__(self, fleet: FFFleet, row_counts: Sequence[int], *, precision: str = "bf16", n_chunks: int = 16,
+                 plan="auto", n_threads: Optional[int] = None, tags=None):
+        if fleet.params is None or fleet.err_scale is None:
+            raise ValueError("FleetAnomalyServer needs a fitted fleet (params and error scaler)")
+        rc = np.asarray(row_counts, np.int64)
+        if len(rc) != fleet.M:
+            raise ValueError("row_counts and fleet disagree on the number of Machines")
+        self.fleet, self.precision, self.tags = fleet, fleet.auto_precision(precision), tags
+        self.row_off = np.concatenate([[0], np.cumsum(rc)]).astype(np.int64)
+        self.rows = int(self.row_off[-1])
+        self.M = fleet.M
+        dev = fleet.device
+        T, To = fleet.topo.n_in, fleet.topo.n_out
+        if T != To:
+            raise ValueError("FleetAnomalyServer serves autoencoders (n_features == n_features_out)")
+        self.T = T
+        self.has_feat, self.has_agg = fleet.feat_thr is not None, fleet.agg_thr is not None
+        self.matrices = [c for c in MATRIX_COLUMNS if c != "anomaly-confidence" or self.has_feat]
+        self.vectors = [c for c in VECTOR_COLUMNS if c != "total-anomaly-confidence" or self.has_agg]
+        self.derivable = [c for c in DERIVE_ORDER if c in self.matrices]
+        import os
+        try:
+            n_aff = len(os.sched_getaffinity(0))
+        except Exception:
+            n_aff = os.cpu_count() or 8
+        self.n_threads = int(n_threads) if n_threads else max(1, min(32, n_aff // 2 if n_aff >= 8 else n_aff))
+        # chunks of whole Machines
+        n_chunks = max(1, min(int(n_chunks), self.M))
+        b = np.linspace(0, self.M, n_chunks + 1).astype(int)
+        self.chunks = [(int(a), int(c)) for a, c in zip(b[:-1], b[1:]) if c > a]
+        max_rows = max(int(self.row_off[c] - self.row_off[a]) for a, c in self.chunks)
+        self.n_slots = min(3, len(self.chunks))
+        self.s_h2d, self.s_k, self.s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.dx = [torch.empty((max_rows, T), dtype=torch.float32, device=dev) for _ in range(self.n_slots)]
+        self.dy = None
+        self.dout = [{**{c: torch.empty((max_rows, To), dtype=torch.float32, device=dev) for c in self.matrices},
+                      **{c: torch.empty((max_rows,), dtype=torch.float32, device=dev) for c in self.vectors}}
+                     for _ in range(self.n_slots)]
+        self.host_out: Dict[str, torch.Tensor] = {
+            **{c: torch.empty((self.rows, To), dtype=torch.float32, pin_memory=True) for c in self.matrices},
+            **{c: torch.empty((self.rows,), dtype=torch.float32, pin_memory=True) for c in self.vectors}}
+        # per-chunk fleet views + schedules, host copies of the per-column factors
+        self.views = []
+        for a, c in self.chunks:
+            v = FFFleet(fleet.topo, c - a, dev)
+            v.params = fleet.params[a:c]
+            if self.precision == "bf16":
+                v._packed = fleet.packed()[a:c]; v._packed_version = v._version
+            for name in ("in_scale", "in_min", "err_scale", "feat_thr", "agg_thr"):
+                t = getattr(fleet, name)
+                setattr(v, name, None if t is None else t[a:c])
+            self.views.append((v, Schedule(np.diff(self.row_off[a:c + 1]))))
+        self.h_err_scale = np.ascontiguousarray(fleet.err_scale.cpu().numpy(), np.float32)
+        self.h_feat_thr = None if not self.has_feat else np.ascontiguousarray(fleet.feat_thr.cpu().numpy(), np.float32)
+        self._lock = threading.Lock()             # one request at a time per server (buffers are reused)
+        self._jobs: "queue.Queue" = queue.Queue()
+        self._worker = threading.Thread(target=self._host_worker, daemon=True)
+        self._worker.start()
+        self._stage: Optional[torch.Tensor] = None
+        self.plan_timings: Dict[int, float] = {}
+        if plan == "auto":
+            self.plan: Optional[int] = None
+        else:
+            self.plan = max(0, min(int(plan), len(self.derivable)))
+
+    # ------------------------------------------------------------------ construction from fitted models
+    @classmethod
+    def from_models(cls, models: Sequence, row_counts: Sequence[int], device=None, **kw) -> "FleetAnomalyServer":
+        """
+        From fitted ``DiffBasedAnomalyDetector[Pipeline[MinMaxScaler, KerasAutoEncoder]]`` objects of ONE
+        topology (what FleetModelBuilder / serializer.load hand back).  Use ``group_by_topology`` first for a
+        heterogeneous project.
+        """
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        plans = [m._fused_plan() for m in models]
+        if any(p is None for p in plans):
+            raise ValueError("every model must be the standard fused composition (see DiffBasedAnomalyDetector._fused_plan)")
+        topo = plans[0][1].model.topology
+        if any(p[1].model.topology.key() != topo.key() for p in plans):
+            raise ValueError("models of one FleetAnomalyServer must share a topology")
+        M = len(models)
+        fleet = FFFleet(topo, M, dev)
+        fleet.set_params(torch.as_tensor(np.stack([p[1].model.params for p in plans]), device=dev))
+        f32 = lambda rows: torch.as_tensor(np.stack([np.asarray(r, np.float32) for r in rows]), device=dev)
+        if all(p[0] is not None for p in plans):
+            fleet.in_scale, fleet.in_min = f32([p[0].scale_ for p in plans]), f32([p[0].min_ for p in plans])
+        elif any(p[0] is not None for p in plans):
+            raise ValueError("either every model has an input MinMaxScaler or none")
+        fleet.err_scale = f32([m.scaler.scale_ for m in models])
+        feats = [m.__dict__.get("feature_thresholds_") for m in models]
+        aggs = [m.__dict__.get("aggregate_threshold_") for m in models]
+        if all(f is not None for f in feats):
+            fleet.feat_thr = f32([np.asarray(f, np.float64) for f in feats])
+        if all(a is not None for a in aggs):
+            fleet.agg_thr = torch.as_tensor(np.asarray(aggs, np.float32), device=dev)
+        prec = kw.pop("precision", plans[0][1]._precision)
+        return cls(fleet, row_counts, precision=prec, **kw)
+
+    @staticmethod
+    def group_by_topology(models: Sequence) -> Dict[tuple, List[int]]:
+        groups: Dict[tuple, List[int]] = {}
+        for i, m in enumerate(models):
+            p = m._fused_plan()
+            key = None if p is None else (p[1].model.topology.key(), p[0] is None,
+                                          m.__dict__.get("feature_thresholds_") is None)
+            groups.setdefault(key, []).append(i)
+        return groups
+
+    # ------------------------------------------------------------------ host side
+    def _host_worker(self):
+        lib = N.lib()
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            ev, ci, derive, x_host, y_host, done = job
+            try:
+                ev.synchronize()
+                if derive:
+                    a, c = self.chunks[ci]
+                    r0, r1 = int(self.row_off[a]), int(self.row_off[c])
+                    ro = np.ascontiguousarray(self.row_off[a:c + 1])
+                    hp = lambda name: C.c_void_p(self.host_out[name][r0:r1].data_ptr()) if name in derive else None
+                    rc = lib.gb200_host_expand_columns(
+                        c - a, ro.ctypes.data_as(C.c_void_p), self.T,
+                        C.c_void_p(self.host_out["model-output"][r0:r1].data_ptr()), C.c_void_p(y_host[r0:r1].data_ptr()),
+                        self.h_err_scale[a:c].ctypes.data_as(C.c_void_p),
+                        None if self.h_feat_thr is None else self.h_feat_thr[a:c].ctypes.data_as(C.c_void_p),
+                        hp("tag-anomaly-unscaled"), hp("tag-anomaly-scaled"), hp("anomaly-confidence"), self.n_threads)
+                    if rc != 0:
+                        raise RuntimeError("gb200_host_expand_columns: " + lib.gb200_last_error().decode())
+                done.append(None)
+            except Exception as e:       # surfaced by anomaly()
+                done.append(e)
+            finally:
+                self._jobs.task_done()
+
+    def _as_pinned(self, X) -> torch.Tensor:
+        """The request's samples as ONE pinned float32 [rows, T] matrix (no copy when it already is one)."""
+        if isinstance(X, torch.Tensor):
+            if X.dtype == torch.float32 and X.is_pinned() and X.is_contiguous() and tuple(X.shape) == (self.rows, self.T):
+                return X
+            X = X.numpy()
+        if self._stage is None:
+            self._stage = torch.empty((self.rows, self.T), dtype=torch.float32, pin_memory=True)
+        st = self._stage.numpy()
+        if isinstance(X, (list, tuple)):
+            if len(X) != self.M:
+                raise ValueError(f"expected {self.M} Machines, got {len(X)}")
+            for m, xm in enumerate(X):
+                a, b = int(self.row_off[m]), int(self.row_off[m + 1])
+                xv = np.asarray(getattr(xm, "values", xm))
+                if xv.shape != (b - a, self.T):
+                    raise ValueError(f"Machine {m}: expected {(b - a, self.T)}, got {xv.shape}")
+                st[a:b] = xv
+        else:
+            xv = np.asarray(getattr(X, "values", X))
+            if xv.shape != (self.rows, self.T):
+                raise ValueError(f"expected {(self.rows, self.T)}, got {xv.shape}")
+            st[:] = xv
+        return self._stage
+
+    # ------------------------------------------------------------------ the call
+    def anomaly(self, X, y=None) -> FleetAnomalyResult:
+        """
+        X: pinned float32 [rows_total, T] (zero-copy), or an array / list of per-Machine arrays or frames
+        (staged into pinned memory first).  y defaults to X (autoencoder).  Blocks until every host column
+        is complete.
+        """
+        with self._lock:
+            x_host = self._as_pinned(X)
+            if y is not None and y is not X:
+                raise NotImplementedError("FleetAnomalyServer: separate targets are served per Machine (model.anomaly)")
+            if self.plan is None:
+                self._calibrate(x_host)
+            self._run(x_host, x_host, self.plan)
+            return FleetAnomalyResult(self.host_out, self.row_off, x_host, self.tags)
+
+    def _calibrate(self, x_host):
+        best, best_t = 0, None
+        for k in range(len(self.derivable), -1, -1):
+            self._run(x_host, x_host, k)            # warm
+            t0 = time.perf_counter()
+            self._run(x_host, x_host, k)
+            dt = time.perf_counter() - t0
+            self.plan_timings[k] = dt
+            if best_t is None or dt < best_t * 0.97:     # prefer more host derivation on ties (less PCIe)
+                best, best_t = k, dt
+        self.plan = best
+
+    def _run(self, x_host, y_host, k: int):
+        derive = tuple(self.derivable[:k])
+        dev_cols = tuple(c for c in self.matrices if c not in derive) + tuple(self.vectors)
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event(); start.record(cur)
+        for s in (self.s_h2d, self.s_k, self.s_d2h):
+            s.wait_event(start)
+        ev_k: List[Optional[torch.cuda.Event]] = [None] * len(self.chunks)
+        ev_d: List[Optional[torch.cuda.Event]] = [None] * len(self.chunks)
+        done: List = []
+        for ci, ((a, c), (view, vs)) in enumerate(zip(self.chunks, self.views)):
+            slot = ci % self.n_slots
+            r0, r1 = int(self.row_off[a]), int(self.row_off[c])
+            n = r1 - r0
+            dx = self.dx[slot][:n]
+            with torch.cuda.stream(self.s_h2d):
+                if ci >= self.n_slots:
+                    self.s_h2d.wait_event(ev_k[ci - self.n_slots])        # the slot's previous kernel has read dx
+                dx.copy_(x_host[r0:r1], non_blocking=True)
+                e_h = torch.cuda.Event(); e_h.record(self.s_h2d)
+            out = {cname: self.dout[slot][cname][:n] for cname in dev_cols}
+            with torch.cuda.stream(self.s_k):
+                self.s_k.wait_event(e_h)
+                if ci >= self.n_slots:
+                    self.s_k.wait_event(ev_d[ci - self.n_slots])          # the slot's previous results left the device
+                view.score(vs, dx, precision=self.precision, columns=dev_cols, out=out)
+                ev_k[ci] = torch.cuda.Event(); ev_k[ci].record(self.s_k)
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(ev_k[ci])
+                for cname in dev_cols:
+                    self.host_out[cname][r0:r1].copy_(out[cname], non_blocking=True)
+                ev_d[ci] = torch.cuda.Event(); ev_d[ci].record(self.s_d2h)
+            self._jobs.put((ev_d[ci], ci, derive, x_host, y_host, done))
+        self._jobs.join()                       # every chunk copied out and expanded
+        for s in (self.s_h2d, self.s_k, self.s_d2h):
+            e = torch.cuda.Event(); e.record(s); cur.wait_event(e)
+        errs = [e for e in done if e is not None]
+        if errs:
+            raise errs[0]
+
+    # ------------------------------------------------------------------ accounting
+    def bytes_per_call(self, k: Optional[int] = None) -> Dict[str, int]:
+        k = self.plan if k is None else k
+        k = len(self.derivable) if k is None else k
+        n_mat_dev = len(self.matrices) - k
+        return {"h2d": self.rows * self.T * 4,
+                "d2h": self.rows * (n_mat_dev * self.T + len(self.vectors)) * 4,
+                "host_derived_bytes": self.rows * k * self.T * 4}
+
+    def kernel_launches_per_call(self) -> int:
+        return len(self.chunks)
+
+    def close(self):
+        self._jobs.put(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -239,6 +239,28 @@ int gb200_score_outputs(int32_t n_machines, const int64_t* out_row_off,
                         float* tag_scaled, float* tag_unscaled, float* total_scaled,
                         float* total_unscaled, float* conf, float* total_conf, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host half of the fleet response path (pointers here are HOST pointers, no stream).
+ *
+ * gb200_host_expand_columns: the per-column rescalings of DiffBasedAnomalyDetector.anomaly
+ * (gordo/machine/model/anomaly/diff.py:366-375 tag-anomaly-unscaled, :350-364 tag-anomaly-scaled,
+ * :417-426 anomaly-confidence) written from the model output the device sent back, for the
+ * n_machines Machines whose rows are [row_off_host[m], row_off_host[m+1]) RELATIVE to the data
+ * pointers' first row (row_off_host[0] is that first row's absolute index and is subtracted).
+ * Any of the three outputs may be NULL.  err_scale / feat_thr: [n_machines, T] float32.
+ * Rows are split over n_threads host threads (non-temporal stores); the threads inherit the
+ * caller's CPU affinity.  This is the host side of a PCIe-bound transfer plan, not a fallback:
+ * model output and row totals always come from gb200_ff_score. */
+int gb200_host_expand_columns(int32_t n_machines, const int64_t* row_off_host, int32_t T,
+                              const float* yhat_host, const float* y_host,
+                              const float* err_scale_host, const float* feat_thr_host,
+                              float* tag_unscaled_host, float* tag_scaled_host, float* conf_host,
+                              int32_t n_threads);
+/* Host memory streaming probe (dst = src * c, non-temporal stores, best of reps): seconds per pass.
+ * Lets the fleet server weigh PCIe bytes against host DRAM bytes on the box it runs on. */
+double gb200_host_stream_seconds(float* dst_host, const float* src_host, int64_t n_floats,
+                                 int32_t n_threads, int32_t reps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -203,7 +203,7 @@ def test_fleet_builder_bucketing_rules():
     """Which Machines share a batched launch (host logic only: no device needed)."""
     import pandas as pd
     from gordo_b200 import serializer
-    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.builder import FleetBuild, FleetMachine, FleetModelBuilder
 
     def machine(detector="DiffBasedAnomalyDetector", det_kw=None, est="KerasAutoEncoder", est_kw=None, tags=4, evaluation=None):
         kw = {"kind": "feedforward_hourglass" if est == "KerasAutoEncoder" else "lstm_hourglass"}
@@ -213,7 +213,7 @@ def test_fleet_builder_bucketing_rules():
                                                     {f"gordo_b200.machine.model.models.{est}": kw}]}})}
         return FleetMachine("m", pd.DataFrame(np.zeros((50, tags))), model=d, evaluation=evaluation or {})
 
-    b = FleetModelBuilder([])
+    b = FleetBuild([])
     key = lambda mc: b._bucket_key(serializer.from_definition(mc.definition()), mc)
     base = key(machine())
     assert base is not None and base == key(machine())                       # same topology + fit settings: one bucket

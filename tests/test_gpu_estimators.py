@@ -21,6 +21,19 @@ from oracle.scaler import MinMaxScaler as OMinMax, time_series_split
 pytestmark = pytest.mark.gpu
 
 
+
+def _builder_init(init_fn, seed, n_machines, per):
+    """The initial weights FleetBuild gives job i of every Machine: its own generator, seeded like the per-Machine path."""
+    from gordo_b200.builder import job_seeds
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev)
+    rows = []
+    for _ in range(n_machines):
+        for sd in job_seeds(seed, per):
+            gen.manual_seed(sd)
+            rows.append(init_fn(1, gen, dev)[0].cpu().numpy())
+    return np.stack(rows)
+
 def _data(seed, n, T):
     rng = np.random.default_rng(seed)
     Z = np.cumsum(rng.normal(size=(n, 2)), axis=0) * 0.05
@@ -166,7 +179,7 @@ def test_smoothing_columns_and_kfcv_detector():
 
 def test_fleet_builder_matches_oracle_full_build():
     """FleetModelBuilder (batched CV + fit + thresholds for a bucket of Machines) vs the oracle."""
-    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.builder import FleetBuild, FleetMachine, FleetModelBuilder
     from gordo_b200.fleet import FFTopology
     T, rows = 6, [512, 480, 333]
     Xs = [_data(20 + i, n, T) for i, n in enumerate(rows)]
@@ -175,12 +188,11 @@ def test_fleet_builder_matches_oracle_full_build():
             {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "shuffle": False}}]}}}}
     mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=[f"t{j}" for j in range(T)]), model=defn,
                         evaluation={"seed": 5}) for i, X in enumerate(Xs)]
-    builder = FleetModelBuilder(mcs)
+    builder = FleetBuild(mcs)
     built = builder.build()
     spec = factories.feedforward_hourglass(T)
     topo = FFTopology(spec["widths"], spec["acts"], spec["l1"])
-    gen = torch.Generator(device="cuda:0"); gen.manual_seed(5)
-    init = topo.glorot_init(len(rows) * 4, gen, torch.device("cuda:0")).cpu().numpy()     # same draw as the builder
+    init = _builder_init(topo.glorot_init, 5, len(rows), 4)
     for m, ((model, meta), X) in enumerate(zip(built, Xs)):
         Xd = X.astype(np.float64)
         det = DiffDetector(lambda tag, m=m: FFBase(spec, dense.ff_unflatten(
@@ -206,11 +218,11 @@ def test_fleet_builder_cv_scores_match_sklearn_scorers():
     """The four builder metrics (build_model.py:377-446) per tag / averaged / per fold, from gb200_cv_sums."""
     from sklearn import metrics as skm
     from sklearn.preprocessing import MinMaxScaler as SkMinMax
-    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.builder import FleetBuild, FleetMachine, FleetModelBuilder
     from gordo_b200.machine.model.utils import metric_wrapper
     T, n = 5, 400
     X = pd.DataFrame(_data(31, n, T), columns=[f"tag {j}" for j in range(T)])
-    built = FleetModelBuilder([FleetMachine("m0", X, evaluation={"seed": 3})]).build()
+    built = FleetBuild([FleetMachine("m0", X, evaluation={"seed": 3})]).build()
     model, meta = built[0]
     scores = meta["cross_validation"]["scores"]
     assert set(scores["r2-score"]) == {"fold-mean", "fold-std", "fold-max", "fold-min", "fold-1", "fold-2", "fold-3"}
@@ -275,7 +287,7 @@ def test_validation_split_val_loss_and_early_stopping():
 
 def test_fleet_builder_smooth_thresholds_with_window():
     """Detectors with ``window`` stay in the batched build: smooth thresholds = rolling(window).min().max() of the fold errors."""
-    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.builder import FleetBuild, FleetMachine, FleetModelBuilder
     from gordo_b200.fleet import FFTopology
     T, rows, W = 5, [420, 377], 12
     Xs = [_data(50 + i, n, T) for i, n in enumerate(rows)]
@@ -284,11 +296,10 @@ def test_fleet_builder_smooth_thresholds_with_window():
             {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "shuffle": False}}]}}}}
     mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=[f"t{j}" for j in range(T)]), model=defn,
                         evaluation={"seed": 9}) for i, X in enumerate(Xs)]
-    built = FleetModelBuilder(mcs).build()
+    built = FleetBuild(mcs).build()
     spec = factories.feedforward_hourglass(T)
     topo = FFTopology(spec["widths"], spec["acts"], spec["l1"])
-    gen = torch.Generator(device="cuda:0"); gen.manual_seed(9)
-    init = topo.glorot_init(len(rows) * 4, gen, torch.device("cuda:0")).cpu().numpy()
+    init = _builder_init(topo.glorot_init, 9, len(rows), 4)
     for m, ((model, meta), X) in enumerate(zip(built, Xs)):
         assert meta["fleet"]["machines_in_launch"] == 2               # batched, not the per-Machine fallback
         Xd = X.astype(np.float64)
@@ -334,7 +345,7 @@ def test_serving_cache_follows_the_model():
 def test_fleet_builder_batches_kfcv_detectors():
     """DiffBasedKFCVAnomalyDetector Machines in the batched build: builder folds (TimeSeriesSplit), thresholds =
     percentile of the smoothed errors over all rows, uncovered rows keeping zero predictions (diff.py:580-635)."""
-    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.builder import FleetBuild, FleetMachine, FleetModelBuilder
     from gordo_b200.fleet import FFTopology
     from gordo_b200.machine.model.anomaly.diff import DiffBasedKFCVAnomalyDetector
     from oracle.anomaly import KFCVDetector
@@ -346,11 +357,10 @@ def test_fleet_builder_batches_kfcv_detectors():
             {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "shuffle": False}}]}}}}
     mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=[f"t{j}" for j in range(T)]), model=defn,
                         evaluation={"seed": 4}) for i, X in enumerate(Xs)]
-    built = FleetModelBuilder(mcs).build()
+    built = FleetBuild(mcs).build()
     spec = factories.feedforward_hourglass(T)
     topo = FFTopology(spec["widths"], spec["acts"], spec["l1"])
-    gen = torch.Generator(device="cuda:0"); gen.manual_seed(4)
-    init = topo.glorot_init(len(rows) * 4, gen, torch.device("cuda:0")).cpu().numpy()
+    init = _builder_init(topo.glorot_init, 4, len(rows), 4)
     for m, ((model, meta), X) in enumerate(zip(built, Xs)):
         assert type(model) is DiffBasedKFCVAnomalyDetector and meta["fleet"]["machines_in_launch"] == 2
         Xd = X.astype(np.float64)

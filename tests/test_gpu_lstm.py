@@ -207,7 +207,7 @@ def test_lstm_detector_fused_scoring_matches_generic_path():
 
 def test_fleet_builder_lstm_bucket_matches_oracle():
     """Batched LSTM build (all folds + final fits in one gb200_lstm_fit, fold scoring on the device) vs the oracle."""
-    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    from gordo_b200.builder import FleetBuild, FleetMachine, FleetModelBuilder
     from gordo_b200.lstm import LSTMTopology
     from oracle.anomaly import DiffDetector, LSTMBase
     T, L, rows = 3, 4, [120, 96]
@@ -218,11 +218,11 @@ def test_fleet_builder_lstm_bucket_matches_oracle():
             {"gordo_b200.machine.model.models.KerasLSTMAutoEncoder": {
                 "kind": "lstm_symmetric", "lookback_window": L, "batch_size": 16, "dims": [4], "funcs": ["tanh"]}}]}}}}
     mcs = [FleetMachine(f"m{i}", pd.DataFrame(X, columns=list("abc")), model=defn, evaluation={"seed": 9}) for i, X in enumerate(Xs)]
-    built = FleetModelBuilder(mcs).build()
+    built = FleetBuild(mcs).build()
     spec = factories.lstm_symmetric(T, lookback_window=L, dims=(4,), funcs=("tanh",))
     topo = LSTMTopology(T, T, spec["units"], spec["acts"], "linear", L)
-    gen = torch.Generator(device=DEV); gen.manual_seed(9)
-    init = topo.init_params(len(rows) * 4, gen, torch.device(DEV)).cpu().numpy()
+    from tests.test_gpu_estimators import _builder_init
+    init = _builder_init(topo.init_params, 9, len(rows), 4)
     for m, ((model, meta), X) in enumerate(zip(built, Xs)):
         Xd = X.astype(np.float64)
         det = DiffDetector(lambda tag, m=m: LSTMBase(spec, olstm.lstm_unflatten(
