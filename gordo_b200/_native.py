@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgordo_b200.so")
 
 MAX_LAYERS = 16
 ACT_CODES = {"linear": 0, "tanh": 1, "relu": 2, "sigmoid": 3, "elu": 4, "softplus": 5}
-PREC_F32, PREC_BF16_TC = 0, 1
+PREC_F32, PREC_BF16_TC, PREC_F16X3_TC = 0, 1, 2
+PREC_CODES = {"f32": PREC_F32, "bf16": PREC_BF16_TC, "f16x3": PREC_F16X3_TC}
 
 
 class FFArch(C.Structure):
@@ -43,6 +44,8 @@ SIGNATURES = {
     "gb200_ff_score": (C.c_int, [_P, C.POINTER(FFArch), C.c_int] + [_P] * 18),
     "gb200_ff_packed_bytes": (_I64, [C.POINTER(FFArch)]),
     "gb200_ff_pack_bf16": (C.c_int, [C.POINTER(FFArch), _I32, _P, _P, _P]),
+    "gb200_ff_packed_bytes_prec": (_I64, [C.POINTER(FFArch), C.c_int]),
+    "gb200_ff_pack": (C.c_int, [C.POINTER(FFArch), C.c_int, _I32, _P, _P, _P]),
     "gb200_ff_param_count": (_I64, [C.POINTER(FFArch)]),
     "gb200_minmax_fit": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _P, _P]),
     "gb200_rolling_min_max": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _P, _P]),

@@ -488,7 +488,7 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
         vf = LSTMFleet(topo, M * k, lookahead, dev)
         vf.set_params(params[sel]); vf.in_scale = in_scale[sel].contiguous(); vf.in_min = in_min[sel].contiguous()
         vs = Schedule(rows_lo=te_lo, rows_hi=te_hi, rows_total=int(off[-1]))
-        prec = est0.kwargs.get("precision", "f32") if vf.tc_eligible() else "f32"
+        prec = "bf16" if (est0.kwargs.get("precision", "f32") == "bf16" and vf.tc_eligible()) else "f32"
         out, out_off = vf.predict(vs, xd, precision=prec)
         n_out = np.diff(out_off)
         y_off = np.asarray(te_hi, np.int64) - n_out                     # align to the LAST len(output) rows

@@ -119,17 +119,30 @@ int64_t gb200_ff_param_count(const gb200_ff_arch* a) {
     return n;
 }
 
+static int is_tc_prec(int precision) { return precision == GB200_PREC_BF16_TC || precision == GB200_PREC_F16X3_TC; }
+
 int64_t gb200_ff_packed_bytes(const gb200_ff_arch* arch) {
     if (check_ff_arch(arch)) return 0;
-    return gb_ff_packed_bytes(arch);
+    return gb_ff_packed_bytes(arch, GB200_PREC_BF16_TC);
+}
+
+int64_t gb200_ff_packed_bytes_prec(const gb200_ff_arch* arch, int precision) {
+    if (check_ff_arch(arch) || !is_tc_prec(precision)) return 0;
+    return gb_ff_packed_bytes(arch, precision);
 }
 
 int gb200_ff_pack_bf16(const gb200_ff_arch* arch, int32_t n_machines, const float* params,
                        void* packed_bf16, void* stream) {
+    return gb200_ff_pack(arch, GB200_PREC_BF16_TC, n_machines, params, packed_bf16, stream);
+}
+
+int gb200_ff_pack(const gb200_ff_arch* arch, int precision, int32_t n_machines, const float* params,
+                  void* packed, void* stream) {
     int rc = check_ff_arch(arch); if (rc) return rc;
-    GB_REQUIRE(params && packed_bf16, "params / packed_bf16 is NULL");
-    GB_REQUIRE(gb_ff_packed_bytes(arch) > 0, "topology is not eligible for the tensor-core path");
-    return gb_launch_ff_pack_bf16(arch, n_machines, params, packed_bf16, (cudaStream_t)stream);
+    GB_REQUIRE(is_tc_prec(precision), "gb200_ff_pack: precision %d has no operand image", precision);
+    GB_REQUIRE(params && packed, "params / packed is NULL");
+    GB_REQUIRE(gb_ff_packed_bytes(arch, precision) > 0, "topology is not eligible for this tensor-core path");
+    return gb_launch_ff_pack(arch, precision, n_machines, params, packed, (cudaStream_t)stream);
 }
 
 int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
@@ -152,11 +165,11 @@ int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
                                       model_out, tag_scaled, tag_unscaled, total_scaled, total_unscaled,
                                       conf, total_conf, activity_l1, (cudaStream_t)stream);
     }
-    if (precision == GB200_PREC_BF16_TC) {
+    if (is_tc_prec(precision)) {
         GB_REQUIRE(activity_l1 == nullptr, "activity_l1 is only produced by GB200_PREC_F32");
-        GB_REQUIRE(packed_bf16 != nullptr, "packed_bf16 is NULL (call gb200_ff_pack_bf16 first)");
-        GB_REQUIRE(gb_ff_packed_bytes(arch) > 0, "topology is not eligible for the tensor-core path");
-        return gb_launch_ff_score_tc(f, arch, packed_bf16, in_scale, in_min, err_scale, feat_thr, agg_thr, x, y,
+        GB_REQUIRE(packed_bf16 != nullptr, "the operand image is NULL (call gb200_ff_pack first)");
+        GB_REQUIRE(gb_ff_packed_bytes(arch, precision) > 0, "topology is not eligible for this tensor-core path");
+        return gb_launch_ff_score_tc(f, arch, precision, packed_bf16, in_scale, in_min, err_scale, feat_thr, agg_thr, x, y,
                                      model_out, tag_scaled, tag_unscaled, total_scaled, total_unscaled,
                                      conf, total_conf, (cudaStream_t)stream);
     }

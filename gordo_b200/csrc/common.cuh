@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -12,6 +13,17 @@
 // process-global, and two host threads launching the same kernel for different topologies on
 // different streams would otherwise race on it.
 #define GB_SMEM_OPTIN_MAX 232448
+
+// raise a kernel's dynamic shared-memory limit to everything the SM offers it: the opt-in maximum minus the
+// kernel's own static shared memory (the attribute counts dynamic bytes only)
+template <typename K>
+static inline cudaError_t gb_allow_max_smem(K kern) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(kern));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GB_SMEM_OPTIN_MAX - (int)fa.sharedSizeBytes);
+}
 
 #define GB_OK 0
 #define GB_ERR_ARG -1
@@ -81,15 +93,15 @@ int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, cons
                            float* model_out, float* tag_scaled, float* tag_unscaled,
                            float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
                            float* activity, cudaStream_t stream);
-int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const void* packed,
+int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, int prec, const void* packed,
                           const float* in_scale, const float* in_min, const float* err_scale,
                           const float* feat_thr, const float* agg_thr, const float* x, const float* y,
                           float* model_out, float* tag_scaled, float* tag_unscaled,
                           float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
                           cudaStream_t stream);
-int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch);
-int gb_launch_ff_pack_bf16(const gb200_ff_arch* arch, int n_machines, const float* params, void* packed,
-                           cudaStream_t stream);
+int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch, int prec);
+int gb_launch_ff_pack(const gb200_ff_arch* arch, int prec, int n_machines, const float* params, void* packed,
+                      cudaStream_t stream);
 int gb_launch_minmax_fit(int n_jobs, const int64_t* lo, const int64_t* hi, const float* x, int n_tags,
                          float* scale, float* min_, cudaStream_t stream);
 int gb_launch_rolling_min_max(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v,

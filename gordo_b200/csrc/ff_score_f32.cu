@@ -241,7 +241,7 @@ int gb_launch_ff_score_f32(const gb200_fleet* f, const gb200_ff_arch* arch, cons
     void (*kern)(ScoreArgs) = !smem_w ? ff_score_f32_kernel<false, 128>
                             : nt == 128 ? ff_score_f32_kernel<true, 128>
                             : nt == 64 ? ff_score_f32_kernel<true, 64> : ff_score_f32_kernel<true, 32>;
-    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
+    GB_CUDA_CHECK(gb_allow_max_smem(kern));
     int per_sm = 1;
     GB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem));
     if (per_sm < 1) per_sm = 1;

@@ -1,4 +1,13 @@
-// ff_score_tc: the Blackwell-native scorer (GB200_PREC_BF16_TC).
+// ff_score_tc: the Blackwell-native scorer (GB200_PREC_BF16_TC and GB200_PREC_F16X3_TC).
+//
+// Two operand precisions share one kernel template:
+//   BF16   bf16 operands, fp32 accumulate: 1 MMA per K step, tanh.approx -- the fastest path (~8e-3 typical error on yhat);
+//   F16X3  fp32-grade: every fp32 operand is split into hi + lo fp16 halves (x = hi + lo + O(2^-22 x)) while it is
+//          staged, and A_hi.B_hi + A_hi.B_lo + A_lo.B_hi is accumulated in fp32 in tensor memory (3 MMAs per K step,
+//          the tensor pipe has the room); activations through ex2/rcp instead of tanh.approx.  Product error < 2^-20,
+//          results agree with the fp32 FMA path to ~1e-6.  Needs bounded hidden activations (tanh / sigmoid): fp16
+//          overflows at 65 504, so the scaled INPUT is clamped to +-6e4 (a first tanh layer saturates identically)
+//          and hidden activations must stay in [-1, 1].
 //
 //   MinMax-scale -> 2E+1 chained Dense layers on tcgen05 tensor cores -> anomaly columns,
 // one 128-row tile of one Machine at a time per warpgroup, everything between the HBM read of the
@@ -37,12 +46,13 @@ constexpr int MAX_WG = 5;
 struct PackLayout {
     int n_layers;
     int Kp[GB200_MAX_LAYERS], Np[GB200_MAX_LAYERS];
-    int w_off[GB200_MAX_LAYERS];     // byte offset of layer l's B operand
+    int w_off[GB200_MAX_LAYERS];     // byte offset of layer l's B operand (the hi half for F16X3)
+    int w_lo[GB200_MAX_LAYERS];      // F16X3: byte offset of the lo half
     int total_bytes;                 // multiple of 16
     int max_Kp, max_Np;
 };
 
-PackLayout make_layout(const gb200_ff_arch* a) {
+PackLayout make_layout(const gb200_ff_arch* a, int prec = GB200_PREC_BF16_TC) {
     PackLayout p{};
     p.n_layers = a->n_layers;
     int off = 0;
@@ -50,6 +60,7 @@ PackLayout make_layout(const gb200_ff_arch* a) {
         p.Kp[l] = gb_round_up(a->widths[l] + 1, 16);      // +1: the bias row (A carries a ones column)
         p.Np[l] = gb_round_up(a->widths[l + 1], 16);
         p.w_off[l] = off; off += p.Kp[l] * p.Np[l] * 2;
+        if (prec == GB200_PREC_F16X3_TC) { p.w_lo[l] = off; off += p.Kp[l] * p.Np[l] * 2; }
         if (p.Kp[l] > p.max_Kp) p.max_Kp = p.Kp[l];
         if (p.Np[l] > p.max_Np) p.max_Np = p.Np[l];
     }
@@ -57,8 +68,9 @@ PackLayout make_layout(const gb200_ff_arch* a) {
     return p;
 }
 
-__global__ void pack_bf16_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_params,
-                                 const float* __restrict__ params, uint8_t* __restrict__ packed) {
+template <int PREC>
+__global__ void pack_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_params,
+                            const float* __restrict__ params, uint8_t* __restrict__ packed) {
     const int m = blockIdx.x;
     const float* P = params + (size_t)m * n_params;
     uint8_t* out = packed + (size_t)m * lay.total_bytes;
@@ -67,6 +79,8 @@ __global__ void pack_bf16_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_p
         const int win = arch.widths[l], wout = arch.widths[l + 1];
         const int Kp = lay.Kp[l], Np = lay.Np[l];
         __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(out + lay.w_off[l]);
+        __half* Bh = reinterpret_cast<__half*>(out + lay.w_off[l]);
+        __half* Bl = reinterpret_cast<__half*>(out + lay.w_lo[l]);
         // canonical K-major, no swizzle: element (n, k) at
         //   (k/8) * (Np/8)*64 + (n/8)*64 + (n%8)*8 + (k%8)      [bf16 elements]
         for (int i = threadIdx.x; i < Kp * Np; i += blockDim.x) {
@@ -76,7 +90,13 @@ __global__ void pack_bf16_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_p
                 if (k < win) w = P[go + (int64_t)k * wout + n];
                 else if (k == win) w = P[go + (int64_t)win * wout + n];      // bias row, multiplied by A's ones column
             }
-            B[(k >> 3) * (Np >> 3) * 64 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(w);
+            const int at = (k >> 3) * (Np >> 3) * 64 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7);
+            if (PREC == GB200_PREC_F16X3_TC) {
+                const __half hi = __float2half_rn(w);
+                Bh[at] = hi; Bl[at] = __float2half_rn(w - __half2float(hi));
+            } else {
+                B[at] = __float2bfloat16_rn(w);
+            }
         }
         go += (int64_t)win * wout + wout;
     }
@@ -84,9 +104,14 @@ __global__ void pack_bf16_kernel(gb200_ff_arch arch, PackLayout lay, int64_t n_p
 
 using namespace gbptx;
 
-template <int ACT>
+// ACC: the fp32-grade path cannot use tanh.approx (2^-11 relative error): tanh(z) = 1 - 2 / (1 + e^(2z))
+// through ex2.approx + rcp.approx, absolute error ~2e-7, exact limits at +-inf, NaN propagates.
+template <int ACT, bool ACC = false>
 __device__ __forceinline__ float act_t(float z) {
-    if (ACT == GB200_ACT_TANH) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z)); return r; }
+    if (ACT == GB200_ACT_TANH) {
+        if (ACC) return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
+        float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(z)); return r;
+    }
     if (ACT == GB200_ACT_RELU) return fmaxf(z, 0.0f);
     if (ACT == GB200_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-z));
     if (ACT == GB200_ACT_ELU) return z > 0.0f ? z : __expf(z) - 1.0f;
@@ -121,7 +146,8 @@ struct TcArgs {
     int tmem_cols_total;     // power of two >= 32
     int xtile_bytes;         // 128*T_in*4 rounded to 128
     int ytile_bytes;         // 0 when y aliases x
-    int tmem_a_off;          // column offset of the bf16 A operand inside a warpgroup's TMEM slice
+    int tmem_a_off;          // column offset of the 16-bit A operand inside a warpgroup's TMEM slice
+    int tmem_a_lo;           // F16X3: column distance from the hi half of A to its lo half
     int vp;                  // padded length of each per-Machine vector (multiple of 16 floats)
 };
 
@@ -135,16 +161,45 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
-// 8 activations -> 4 TMEM columns of the A operand (this thread's lane = its row)
-__device__ __forceinline__ void store_a8(uint32_t taddr, const float* v) {
-    uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
-    tmem_st4(taddr, pk);
+// fp32 pair -> fp16 hi pair + fp16 lo pair (x = hi + lo + O(2^-22 |x|))
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void store_a16(uint32_t taddr, const float* v) {
-    uint32_t pk[8];
-    #pragma unroll
-    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-    tmem_st8(taddr, pk);
+// 8 activations -> 4 TMEM columns of the A operand (this thread's lane = its row); F16X3: 4 hi + 4 lo columns
+template <int PREC>
+__device__ __forceinline__ void store_a8(uint32_t taddr, int lo_delta, const float* v) {
+    if (PREC == GB200_PREC_F16X3_TC) {
+        uint32_t hi[4], lo[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+        tmem_st4(taddr, hi); tmem_st4(taddr + lo_delta, lo);
+    } else {
+        uint32_t pk[4] = {pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])};
+        tmem_st4(taddr, pk);
+    }
+}
+template <int PREC>
+__device__ __forceinline__ void store_a16(uint32_t taddr, int lo_delta, const float* v) {
+    if (PREC == GB200_PREC_F16X3_TC) {
+        uint32_t hi[8], lo[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+        tmem_st8(taddr, hi); tmem_st8(taddr + lo_delta, lo);
+    } else {
+        uint32_t pk[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        tmem_st8(taddr, pk);
+    }
+}
+// F16X3: the scaled input is clamped into fp16 range (NaN passes through); see the header note
+template <int PREC>
+__device__ __forceinline__ float clamp_in(float v) {
+    if (PREC == GB200_PREC_F16X3_TC) return fabsf(v) > 6.0e4f ? copysignf(6.0e4f, v) : v;
+    return v;
 }
 __device__ __forceinline__ void load16_bcast(const float* p, float* o) {       // 16-byte aligned broadcast loads
     #pragma unroll
@@ -189,32 +244,33 @@ __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const flo
 // hidden layer: accumulator (TMEM, bias already inside the GEMM) -> activation -> bf16 A operand of
 // the next layer, written straight back to TENSOR MEMORY (tcgen05.st): activations never touch
 // shared memory.  Column `wout` of the next A is the ones column that carries the next bias.
-template <int ACT>
+template <int ACT, int PREC>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane, int n_chunks, int wout, int kp_next,
-                                                uint32_t tmem_a_lane) {
+                                                uint32_t tmem_a_lane, int lo_delta) {
+    constexpr bool ACC = PREC == GB200_PREC_F16X3_TC;
     const int c_one = wout >> 4, j_one = wout & 15;
     for (int c = 0; c < n_chunks; ++c) {
         float v[16];
         tmem_ld16(tmem_lane + c * 16, v);
         #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT, ACC>(v[j]);
         if (c == c_one) {
             #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (j == j_one) ? 1.0f : v[j];
         }
-        store_a16(tmem_a_lane + c * 8, v);
+        store_a16<PREC>(tmem_a_lane + c * 8, lo_delta, v);
     }
     if (kp_next > n_chunks * 16) {                     // wout is a multiple of 16: the ones column opens a new chunk
         float v[16];
         #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = (j == j_one) ? 1.0f : 0.0f;
-        store_a16(tmem_a_lane + n_chunks * 8, v);
+        store_a16<PREC>(tmem_a_lane + n_chunks * 8, lo_delta, v);
     }
     tmem_wait_st();
 }
 
 // final layer, pass 1: d = |yhat - y| written in place over the y tile; returns the two row sums
-template <int ACT, bool EVEN>
+template <int ACT, bool EVEN, bool ACC>
 __device__ __forceinline__ void final_pass1(uint32_t tmem_lane,
                                             const float* __restrict__ v_es, float* __restrict__ yrow,
                                             int T_out, float& su_out, float& ss_out) {
@@ -236,7 +292,7 @@ __device__ __forceinline__ void final_pass1(uint32_t tmem_lane,
         }
         #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float d = fabsf(act_t<ACT>(v[j]) - yv[j]);
+            const float d = fabsf(act_t<ACT, ACC>(v[j]) - yv[j]);
             const float s = d * e[j];
             su = fmaf(d, d, su); ss = fmaf(s, s, ss);
             yv[j] = d;
@@ -258,7 +314,7 @@ __device__ __forceinline__ void final_pass1(uint32_t tmem_lane,
         for (int j = 0; j < 16; ++j) {
             const int n = n0 + j;
             if (n < T_out) {
-                const float d = fabsf(act_t<ACT>(v[j]) - yrow[n]);
+                const float d = fabsf(act_t<ACT, ACC>(v[j]) - yrow[n]);
                 const float s = d * v_es[n];
                 su = fmaf(d, d, su); ss = fmaf(s, s, ss);
                 yrow[n] = d;
@@ -269,14 +325,14 @@ __device__ __forceinline__ void final_pass1(uint32_t tmem_lane,
 }
 
 // final layer, pass 2: yhat overwrites the tile
-template <int ACT, bool EVEN>
+template <int ACT, bool EVEN, bool ACC>
 __device__ __forceinline__ void final_pass2(uint32_t tmem_lane, float* __restrict__ yrow, int T_out) {
     const int full = T_out >> 4;
     for (int c = 0; c < full; ++c) {
         float v[16];
         tmem_ld16(tmem_lane + c * 16, v);
         #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT>(v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT, ACC>(v[j]);
         if (EVEN) {
             #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -292,12 +348,14 @@ __device__ __forceinline__ void final_pass2(uint32_t tmem_lane, float* __restric
         tmem_ld16(tmem_lane + n0, v);
         #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (n0 + j < T_out) yrow[n0 + j] = act_t<ACT>(v[j]);
+            if (n0 + j < T_out) yrow[n0 + j] = act_t<ACT, ACC>(v[j]);
     }
 }
 
+template <int PREC>
 __global__ void __launch_bounds__(MAX_WG * WG_THREADS, 1)
 ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
+    constexpr bool ACC = PREC == GB200_PREC_F16X3_TC;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t w_bar;
     __shared__ __align__(8) uint64_t x_bar[MAX_WG];
@@ -335,7 +393,8 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
     tc_fence_after();
     const uint32_t tmem_acc = s_tmem_base + (uint32_t)(wg * a.tmem_cols_wg);          // column offset
     const uint32_t tmem_lane = tmem_acc + ((uint32_t)(warp_in_wg * 32) << 16);        // this warp's lanes
-    const uint32_t tmem_a = tmem_acc + (uint32_t)a.tmem_a_off;                        // bf16 A operand columns
+    const uint32_t tmem_a = tmem_acc + (uint32_t)a.tmem_a_off;                        // 16-bit A operand columns
+    const int lo_delta = a.tmem_a_lo;
     const uint32_t tmem_a_lane = tmem_a + ((uint32_t)(warp_in_wg * 32) << 16);
 
     const int per_cta = (a.tiles_total + gridDim.x - 1) / gridDim.x;
@@ -408,14 +467,18 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                         const float4 m0 = *reinterpret_cast<const float4*>(v_min + c * 8), m1 = *reinterpret_cast<const float4*>(v_min + c * 8 + 4);
                         v[0] = fmaf(v[0], s0.x, m0.x); v[1] = fmaf(v[1], s0.y, m0.y); v[2] = fmaf(v[2], s0.z, m0.z); v[3] = fmaf(v[3], s0.w, m0.w);
                         v[4] = fmaf(v[4], s1.x, m1.x); v[5] = fmaf(v[5], s1.y, m1.y); v[6] = fmaf(v[6], s1.z, m1.z); v[7] = fmaf(v[7], s1.w, m1.w);
-                        store_a8(tmem_a_lane + c * 4, v);
+                        if (ACC) {
+                            #pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = clamp_in<PREC>(v[j]);
+                        }
+                        store_a8<PREC>(tmem_a_lane + c * 4, lo_delta, v);
                     }
                 } else {
                     for (int c = 0; c < full; ++c) {
                         float v[8];
                         #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = fmaf(xr[c * 8 + j], v_scale[c * 8 + j], v_min[c * 8 + j]);
-                        store_a8(tmem_a_lane + c * 4, v);
+                        for (int j = 0; j < 8; ++j) v[j] = clamp_in<PREC>(fmaf(xr[c * 8 + j], v_scale[c * 8 + j], v_min[c * 8 + j]));
+                        store_a8<PREC>(tmem_a_lane + c * 4, lo_delta, v);
                     }
                 }
                 // the chunk holding column T_in (the ones column that carries the first bias), then zero padding
@@ -424,9 +487,9 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                     #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = c * 8 + j;
-                        v[j] = k < T_in ? fmaf(xr[k], v_scale[k], v_min[k]) : (k == T_in ? 1.0f : 0.0f);
+                        v[j] = k < T_in ? clamp_in<PREC>(fmaf(xr[k], v_scale[k], v_min[k])) : (k == T_in ? 1.0f : 0.0f);
                     }
-                    store_a8(tmem_a_lane + c * 4, v);
+                    store_a8<PREC>(tmem_a_lane + c * 4, lo_delta, v);
                 }
                 tmem_wait_st();
             }
@@ -437,27 +500,33 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                 named_bar_sync(1 + wg, WG_THREADS);
                 if (wtid == 0) {
                     tc_fence_after();
-                    const uint32_t idesc = make_idesc(TILE, Np);
+                    const uint32_t idesc = ACC ? make_idesc_f16(TILE, Np) : make_idesc(TILE, Np);
                     const uint32_t b_addr = smem_u32(w_img + a.lay.w_off[l]);
+                    const uint32_t b_lo_addr = smem_u32(w_img + a.lay.w_lo[l]);
                     const uint32_t b_lbo = (uint32_t)(Np / 8) * 128;
                     for (int ks = 0; ks < Kp / 16; ++ks) {
                         const uint64_t db = make_desc(b_addr + ks * 2 * b_lbo, b_lbo, 128);
-                        umma_bf16_ts(tmem_acc, tmem_a + ks * 8, db, idesc, ks > 0 ? 1u : 0u);      // K=16 bf16 = 8 columns of A
+                        umma_bf16_ts(tmem_acc, tmem_a + ks * 8, db, idesc, ks > 0 ? 1u : 0u);      // K=16 halves = 8 columns of A
+                        if (ACC) {                          // + A_hi.B_lo + A_lo.B_hi: the fp32-grade split product
+                            const uint64_t dl = make_desc(b_lo_addr + ks * 2 * b_lbo, b_lbo, 128);
+                            umma_bf16_ts(tmem_acc, tmem_a + ks * 8, dl, idesc, 1u);
+                            umma_bf16_ts(tmem_acc, tmem_a + lo_delta + ks * 8, db, idesc, 1u);
+                        }
                     }
                     umma_commit(&mma_bar[wg]);
                 }
                 mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
                 tc_fence_after();
                 if (l == L - 1) break;
-                GB_DISPATCH_ACT(a.arch.acts[l], hidden_epilogue<ACT>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], tmem_a_lane));
+                GB_DISPATCH_ACT(a.arch.acts[l], (hidden_epilogue<ACT, PREC>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], tmem_a_lane, lo_delta)));
             }
             // ---- final epilogue
             const int code = a.arch.acts[L - 1];
             float* yrow = ybuf + wtid * T_out;
             const bool even = (T_out & 1) == 0;
             float su, ss;
-            if (even) { GB_DISPATCH_ACT(code, (final_pass1<ACT, true>(tmem_lane, v_es, yrow, T_out, su, ss))); }
-            else      { GB_DISPATCH_ACT(code, (final_pass1<ACT, false>(tmem_lane, v_es, yrow, T_out, su, ss))); }
+            if (even) { GB_DISPATCH_ACT(code, (final_pass1<ACT, true, ACC>(tmem_lane, v_es, yrow, T_out, su, ss))); }
+            else      { GB_DISPATCH_ACT(code, (final_pass1<ACT, false, ACC>(tmem_lane, v_es, yrow, T_out, su, ss))); }
             if (wtid < nrows) {
                 const int64_t row = row0 + wtid;
                 const float ts = ss * inv_T;
@@ -481,8 +550,8 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                 }
                 __syncwarp();
                 if (a.model_out) {
-                    if (even) { GB_DISPATCH_ACT(code, (final_pass2<ACT, true>(tmem_lane, yrow, T_out))); }
-                    else      { GB_DISPATCH_ACT(code, (final_pass2<ACT, false>(tmem_lane, yrow, T_out))); }
+                    if (even) { GB_DISPATCH_ACT(code, (final_pass2<ACT, true, ACC>(tmem_lane, yrow, T_out))); }
+                    else      { GB_DISPATCH_ACT(code, (final_pass2<ACT, false, ACC>(tmem_lane, yrow, T_out))); }
                     __syncwarp();
                     if (cnt > 0) warp_copy_out<0>(a.model_out + goff, src, cnt, T_out, nullptr, lane, v16);
                 }
@@ -503,35 +572,45 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
 
 }  // namespace
 
-int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch) {
-    PackLayout lay = make_layout(arch);
+int64_t gb_ff_packed_bytes(const gb200_ff_arch* arch, int prec) {
+    PackLayout lay = make_layout(arch, prec);
     // eligible when the image + one warpgroup's buffers fit the 227 KB shared-memory window and
     // a layer fits one UMMA (N <= 256) and one accumulator slice (<= 512 TMEM columns)
     if (lay.max_Np > 256 || lay.max_Kp > 256) return 0;
     const int T_in = arch->widths[0], T_out = arch->widths[arch->n_layers];
     const int64_t per_wg = gb_round_up(TILE * T_in * 4, 128) + gb_round_up(TILE * T_out * 4, 128);
     if (lay.total_bytes + 4096 + per_wg > 227 * 1024 - 2048) return 0;
+    if (prec == GB200_PREC_F16X3_TC) {
+        // fp16 operands: hidden activations must be bounded (see the header note), and there must be one
+        if (arch->n_layers < 2 || lay.max_Np + lay.max_Kp > 512) return 0;
+        for (int l = 0; l + 1 < arch->n_layers; ++l)
+            if (arch->acts[l] != GB200_ACT_TANH && arch->acts[l] != GB200_ACT_SIGMOID) return 0;
+    }
     return lay.total_bytes;
 }
 
-int gb_launch_ff_pack_bf16(const gb200_ff_arch* arch, int n_machines, const float* params, void* packed,
-                           cudaStream_t stream) {
+int gb_launch_ff_pack(const gb200_ff_arch* arch, int prec, int n_machines, const float* params, void* packed,
+                      cudaStream_t stream) {
     if (n_machines <= 0) return GB_OK;
-    PackLayout lay = make_layout(arch);
-    pack_bf16_kernel<<<n_machines, 256, 0, stream>>>(*arch, lay, gb200_ff_param_count(arch), params, (uint8_t*)packed);
+    PackLayout lay = make_layout(arch, prec);
+    if (prec == GB200_PREC_F16X3_TC)
+        pack_kernel<GB200_PREC_F16X3_TC><<<n_machines, 256, 0, stream>>>(*arch, lay, gb200_ff_param_count(arch), params, (uint8_t*)packed);
+    else
+        pack_kernel<GB200_PREC_BF16_TC><<<n_machines, 256, 0, stream>>>(*arch, lay, gb200_ff_param_count(arch), params, (uint8_t*)packed);
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
 }
 
-int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const void* packed,
+int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, int prec, const void* packed,
                           const float* in_scale, const float* in_min, const float* err_scale,
                           const float* feat_thr, const float* agg_thr, const float* x, const float* y,
                           float* model_out, float* tag_scaled, float* tag_unscaled,
                           float* total_scaled, float* total_unscaled, float* conf, float* total_conf,
                           cudaStream_t stream) {
     if (f->tiles_total == 0) return GB_OK;
+    const bool x3 = prec == GB200_PREC_F16X3_TC;
     TcArgs a{};
-    a.arch = *arch; a.lay = make_layout(arch);
+    a.arch = *arch; a.lay = make_layout(arch, prec);
     a.row_lo = f->d_row_lo; a.row_hi = f->d_row_hi; a.tile_off = f->d_tile_off;
     a.n_machines = f->n_machines; a.tiles_total = f->tiles_total;
     a.packed = (const uint8_t*)packed;
@@ -543,9 +622,10 @@ int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const
     a.xtile_bytes = gb_round_up(TILE * T_in * 4, 128);
     a.ytile_bytes = a.y ? gb_round_up(TILE * T_out * 4, 128) : 0;
     a.vp = gb_round_up((T_in > T_out ? T_in : T_out) + 4, 16);
-    // TMEM slice of a warpgroup: fp32 accumulator (max_Np columns) + bf16 A operand (max_Kp/2 columns)
+    // TMEM slice of a warpgroup: fp32 accumulator (max_Np columns) + 16-bit A operand (max_Kp/2 columns, twice for hi + lo)
     a.tmem_a_off = a.lay.max_Np;
-    const int cols = a.lay.max_Np + a.lay.max_Kp / 2;
+    a.tmem_a_lo = x3 ? a.lay.max_Kp / 2 : 0;
+    const int cols = a.lay.max_Np + (x3 ? a.lay.max_Kp : a.lay.max_Kp / 2);
     a.tmem_cols_wg = cols;
     const size_t cap = 227 * 1024 - 1024;
     const size_t fixed = (size_t)a.lay.total_bytes + (size_t)(5 * a.vp + 32) * 4;
@@ -553,18 +633,19 @@ int gb_launch_ff_score_tc(const gb200_fleet* f, const gb200_ff_arch* arch, const
     int nwg = MAX_WG;
     { const char* e = getenv("GB200_FF_NWG"); if (e && atoi(e) >= 1 && atoi(e) <= MAX_WG) nwg = atoi(e); }   // tuning knob
     while (nwg > 1 && (fixed + nwg * per_wg > cap || nwg * cols > 512)) --nwg;
-    GB_REQUIRE(fixed + nwg * per_wg <= cap, "ff_score_tc: topology does not fit in shared memory");
+    GB_REQUIRE(fixed + nwg * per_wg <= cap && nwg * cols <= 512, "ff_score_tc: topology does not fit in shared / tensor memory");
     a.nwg = nwg;
     int tot = 32; while (tot < nwg * cols) tot <<= 1;
     a.tmem_cols_total = tot;
     const size_t smem = fixed + nwg * per_wg;
-    GB_CUDA_CHECK(cudaFuncSetAttribute(ff_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
+    auto* kern = x3 ? ff_score_tc_kernel<GB200_PREC_F16X3_TC> : ff_score_tc_kernel<GB200_PREC_BF16_TC>;
+    GB_CUDA_CHECK(gb_allow_max_smem(kern));
     int grid = f->sm_count;
     const int min_tiles_per_cta = nwg;            // keep every warpgroup of a CTA busy
     const int max_grid = (f->tiles_total + min_tiles_per_cta - 1) / min_tiles_per_cta;
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
-    ff_score_tc_kernel<<<grid, nwg * WG_THREADS, smem, stream>>>(a);
+    kern<<<grid, nwg * WG_THREADS, smem, stream>>>(a);
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
 }

@@ -1016,7 +1016,7 @@ static int launch_rec(bool fwd, const RecPlan& rp, RecArgs& a, int J, cudaStream
     a.width = fwd ? rp.width_f : rp.width_b; a.NG = fwd ? rp.ng_f : rp.ng_b;
     const size_t smem = fwd ? rp.smem_f : rp.smem_b;
     auto* kern = fwd ? lstm_rec_fwd_kernel : lstm_rec_bwd_kernel;
-    GB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
+    GB_CUDA_CHECK(gb_allow_max_smem(kern));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(rp.CL, 1, J); cfg.blockDim = dim3(a.width * a.NG, 1, 1);
     cfg.dynamicSmemBytes = smem; cfg.stream = stream;

@@ -485,7 +485,7 @@ int gb_lstm_predict_tc(const gb200_fleet* f, const gb200_lstm_arch* arch, const 
                 }
                 a.stage_bytes = stage; a.a_bytes = abytes;
                 const size_t smem = (size_t)abytes + (size_t)B_STAGES_HOST * stage;
-                GB_CUDA_CHECK(cudaFuncSetAttribute(lstm_persist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
+                GB_CUDA_CHECK(gb_allow_max_smem(lstm_persist_tc_kernel));
                 lstm_persist_tc_kernel<<<tiles, PERSIST_THREADS, smem, stream>>>(a);
             }
             const TcLayer& yl = p.ly[p.n_layers - 1];

@@ -89,7 +89,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
+// same with fp16 operands (A/B format code 0)
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // kind::tf32: 32-bit operands (10-bit mantissa used), K = 8 per instruction; A/B format code 2
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {

@@ -315,7 +315,7 @@ int gb_launch_smooth(int n_jobs, const int64_t* lo, const int64_t* hi, const flo
     const int64_t rows_per_block = (int64_t)nsub * S;
     dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), n_jobs, (n_cols + nt - 1) / nt);
     if (smem > 48 * 1024)
-        GB_CUDA_CHECK(cudaFuncSetAttribute(smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_OPTIN_MAX));
+        GB_CUDA_CHECK(gb_allow_max_smem(smooth_kernel));
     smooth_kernel<<<grid, nt, smem, stream>>>(a);
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;

@@ -148,8 +148,10 @@ class FFFleet:
         self.params: Optional[torch.Tensor] = None
         self.in_scale = self.in_min = self.err_scale = None
         self.feat_thr = self.agg_thr = None
-        self._packed = None
+        self._packed = None                 # bf16 operand image (kept under this name: chunk views alias it)
         self._packed_version = -1
+        self._packed_x3 = None              # f16x3 operand image
+        self._packed_x3_version = -1
         self._version = 0
         self._pack_lock = threading.Lock()
 
@@ -169,33 +171,38 @@ class FFFleet:
         g = torch.Generator(device=self.device); g.manual_seed(int(seed))
         self.set_params(self.topo.glorot_init(self.M, g, self.device))
 
-    def tc_eligible(self) -> bool:
-        return N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch)) > 0
+    def tc_eligible(self, precision: str = "bf16") -> bool:
+        return N.lib().gb200_ff_packed_bytes_prec(C.byref(self.topo.arch), N.PREC_CODES[precision]) > 0
 
     def auto_precision(self, requested: str = "bf16") -> str:
         """
-        The scorer to launch for a caller that asked for ``requested``: the tcgen05 path when the
-        topology is eligible and wide enough to profit -- with every layer at most 8 wide (5-tag
-        Machines) the exact fp32 kernel is both faster and exact (profiles/README.md r1g).
+        The scorer to launch for a caller that asked for ``requested``:
+        "bf16"  -> the bf16 tcgen05 path when the topology is eligible and wide enough to profit -- with every
+                   layer at most 8 wide (5-tag Machines) the exact fp32 kernel is both faster and exact
+                   (profiles/README.md r1g);
+        "f16x3" -> the fp32-grade tcgen05 path (split fp16 operands) when eligible (tanh / sigmoid hidden layers);
+        anything else, or not eligible -> the exact fp32 kernel.
         """
-        if requested == "bf16" and self.tc_eligible() and max(self.topo.widths) > 8:
-            return "bf16"
+        if requested in ("bf16", "f16x3") and self.tc_eligible(requested) and max(self.topo.widths) > 8:
+            return requested
         return "f32"
 
-    def packed(self) -> torch.Tensor:
-        """bf16 tcgen05 operand image of the current weights (re-packed when they change)."""
+    def packed(self, precision: str = "bf16") -> torch.Tensor:
+        """tcgen05 operand image of the current weights for ``precision`` (re-packed when they change)."""
+        attr, vattr = ("_packed", "_packed_version") if precision == "bf16" else ("_packed_x3", "_packed_x3_version")
         with self._pack_lock:
-            if self._packed is None or self._packed_version != self._version:
-                nbytes = N.lib().gb200_ff_packed_bytes(C.byref(self.topo.arch))
+            if getattr(self, attr) is None or getattr(self, vattr) != self._version:
+                code = N.PREC_CODES[precision]
+                nbytes = N.lib().gb200_ff_packed_bytes_prec(C.byref(self.topo.arch), code)
                 if nbytes <= 0:
-                    raise ValueError("topology is not eligible for the tensor-core path")
+                    raise ValueError(f"topology is not eligible for the {precision} tensor-core path")
                 packed = torch.empty((self.M, nbytes), dtype=torch.uint8, device=self.device)
-                N.check(N.lib().gb200_ff_pack_bf16(C.byref(self.topo.arch), self.M, N.ptr(self.params),
-                                                   N.ptr(packed), _stream_ptr()), "gb200_ff_pack_bf16")
+                N.check(N.lib().gb200_ff_pack(C.byref(self.topo.arch), code, self.M, N.ptr(self.params),
+                                              N.ptr(packed), _stream_ptr()), "gb200_ff_pack")
                 if torch.cuda.current_stream() != torch.cuda.default_stream():
                     torch.cuda.current_stream().synchronize()      # another thread / stream may read it next
-                self._packed, self._packed_version = packed, self._version
-            return self._packed
+                setattr(self, attr, packed); setattr(self, vattr, self._version)
+            return getattr(self, attr)
 
     # ------------------------------------------------------------------ scalers / thresholds
     @staticmethod
@@ -346,12 +353,12 @@ class FFFleet:
         ttu = buf("total-anomaly-unscaled", (R,)); cf = buf("anomaly-confidence", (R, To))
         tcf = buf("total-anomaly-confidence", (R,))
         act = buf("activity-l1", (R,)) if precision == "f32" else None
-        if precision == "bf16":
-            prec, packed = N.PREC_BF16_TC, self.packed()
+        if precision in ("bf16", "f16x3"):
+            prec, packed = N.PREC_CODES[precision], self.packed(precision)
         elif precision == "f32":
             prec, packed = N.PREC_F32, None
         else:
-            raise ValueError("precision must be 'bf16' or 'f32'")
+            raise ValueError("precision must be 'bf16', 'f16x3' or 'f32'")
         N.check(N.lib().gb200_ff_score(
             sched.handle, C.byref(self.topo.arch), prec, N.ptr(self.params), N.ptr(packed),
             N.ptr(self.in_scale), N.ptr(self.in_min), N.ptr(self.err_scale),

@@ -16,6 +16,38 @@ import os
 from typing import Dict, List, Optional
 
 
+def cpu_quota() -> Optional[float]:
+    """CPUs' worth of time the cgroup grants this container (cpu.max / cfs quota), None when unlimited."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                     # cgroup v2
+            q, per = f.read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:                                                              # cgroup v1
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            q = float(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            per = float(f.read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
+def effective_cpus() -> int:
+    """Host threads worth starting: the affinity mask capped by the cgroup CPU quota (a GPU lease is a
+    container: it can see 128 CPUs and still be granted the time of a handful)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    q = cpu_quota()
+    if q:
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))     # the quota is shared by the ranks of the box
+        n = min(n, max(1, int(q / ranks + 0.5)))
+    return max(1, n)
+
+
 def _parse_cpulist(text: str) -> List[int]:
     out: List[int] = []
     for part in text.strip().split(","):
@@ -113,7 +145,7 @@ def slice_cpus(cpus: List[int], part: int, parts: int) -> List[int]:
 
 def bind_to_gpu(index: int, local_rank: int = 0, local_world: int = 1, n_gpus_visible: Optional[int] = None) -> Dict:
     """Returns what was done: {"node", "cpus", "n_cpus", "mempolicy", "source"}."""
-    info: Dict = {"node": None, "cpus": None, "n_cpus": None, "mempolicy": False, "source": None}
+    info: Dict = {"node": None, "cpus": None, "n_cpus": None, "mempolicy": False, "source": None, "cpu_quota": cpu_quota()}
     try:
         avail = sorted(os.sched_getaffinity(0))
     except Exception:

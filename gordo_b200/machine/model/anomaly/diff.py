@@ -336,7 +336,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
                 self.__dict__["_gb200_serving_lstm"] = (key, fleet)
         xd = torch.as_tensor(np.ascontiguousarray(Xv, np.float32), device=dev)
         yd = torch.as_tensor(np.ascontiguousarray(yv, np.float32), device=dev)
-        prec = est._precision if fleet.tc_eligible() else "f32"
+        prec = "bf16" if (est._precision == "bf16" and fleet.tc_eligible()) else "f32"
         out, off = fleet.predict(Schedule.single(len(Xv)), xd, precision=prec)
         n_out = int(off[-1])
         feat = self.__dict__.get("feature_thresholds_"); agg = self.__dict__.get("aggregate_threshold_")

@@ -148,7 +148,7 @@ class KerasBaseEstimator(BaseEstimator, GordoBase):
         kind: a registered factory name, a dotted path to a factory, or a factory callable
         (registered on the fly) -- models.py:53-94.  kwargs: factory arguments and/or fit
         arguments (epochs, batch_size, shuffle, validation_split ...), plus ``precision``
-        ("f32" default | "bf16": tensor-core inference) and ``l1_batch_norm`` ("sum" default, as
+        ("f32" default | "bf16": tensor-core inference | "f16x3": fp32-grade tensor-core inference) and ``l1_batch_norm`` ("sum" default, as
         Keras 3.3.3 | "mean").
         """
         self.kind = self.load_kind(kind)
@@ -263,8 +263,8 @@ class KerasBaseEstimator(BaseEstimator, GordoBase):
     @property
     def _precision(self) -> str:
         p = self.kwargs.get("precision", "f32")
-        if p not in ("f32", "bf16"):
-            raise ValueError("precision must be 'f32' or 'bf16'")
+        if p not in ("f32", "bf16", "f16x3"):
+            raise ValueError("precision must be 'f32', 'bf16' or 'f16x3'")
         return p
 
     def get_metadata(self):
@@ -476,7 +476,7 @@ class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin):
                 fleet.set_params(torch.as_tensor(self.model.params[None], device=dev))
                 self.__dict__["_gb200_serving"] = (key, fleet)
         xd = torch.as_tensor(np.ascontiguousarray(X, np.float32), device=dev)
-        prec = self._precision if fleet.tc_eligible() else "f32"       # "bf16": tcgen05 step kernel
+        prec = "bf16" if (self._precision == "bf16" and fleet.tc_eligible()) else "f32"       # "bf16": tcgen05 step kernel
         out, _ = fleet.predict(Schedule.single(len(X)), xd, precision=prec)
         return out.cpu().numpy()
 

@@ -58,8 +58,8 @@ class FleetAnomalyResult:
         out.update({k: v[a:b].numpy() for k, v in self.columns.items()})
         return out
 
-    def frame(self, m: int, index=None, frequency=None, tags: Optional[Sequence] = None):
-        """The reference's anomaly frame for Machine m (model/utils.py:49-165 layout, diff.py:310-458 columns)."""
+    def groups(self, m: int, tags: Optional[Sequence] = None):
+        """Machine m's columns as ``assemble_frame`` groups, in the reference's column order (diff.py:310-458)."""
         from gordo_b200.machine.model import utils as model_utils
         c = self.machine(m)
         T = c["model-input"].shape[1]
@@ -76,7 +76,22 @@ class FleetAnomalyResult:
             groups.append(("anomaly-confidence", c["anomaly-confidence"], names_out))
         if "total-anomaly-confidence" in c:
             groups.append(("total-anomaly-confidence", c["total-anomaly-confidence"], None))
-        return model_utils.assemble_frame(groups, index, frequency)
+        return groups
+
+    def frame(self, m: int, index=None, frequency=None, tags: Optional[Sequence] = None):
+        """The reference's anomaly frame for Machine m (model/utils.py:49-165 layout, diff.py:310-458 columns)."""
+        from gordo_b200.machine.model import utils as model_utils
+        return model_utils.assemble_frame(self.groups(m, tags), index, frequency)
+
+    def parquet_bytes(self, m: int, index=None, frequency=None, tags: Optional[Sequence] = None, compression="snappy") -> bytes:
+        """The ``?format=parquet`` response body of server/blueprints/anomaly.py:64-68 for Machine m, straight from the columns."""
+        from gordo_b200.server.utils import columns_into_parquet_bytes
+        return columns_into_parquet_bytes(self.groups(m, tags), index, frequency, compression)
+
+    def to_dict(self, m: int, index=None, frequency=None, tags: Optional[Sequence] = None) -> dict:
+        """The ``data`` member of the JSON response (server/blueprints/anomaly.py:70-72, server/utils.py:88-142)."""
+        from gordo_b200.server.utils import columns_to_dict
+        return columns_to_dict(self.groups(m, tags), index, frequency)
 
 
 class FleetAnomalyServer:
@@ -100,12 +115,9 @@ class FleetAnomalyServer:
         self.matrices = [c for c in MATRIX_COLUMNS if c != "anomaly-confidence" or self.has_feat]
         self.vectors = [c for c in VECTOR_COLUMNS if c != "total-anomaly-confidence" or self.has_agg]
         self.derivable = [c for c in DERIVE_ORDER if c in self.matrices]
-        import os
-        try:
-            n_aff = len(os.sched_getaffinity(0))
-        except Exception:
-            n_aff = os.cpu_count() or 8
-        self.n_threads = int(n_threads) if n_threads else max(1, min(32, n_aff // 2 if n_aff >= 8 else n_aff))
+        from .hostbind import effective_cpus
+        n_eff = effective_cpus()                 # affinity mask capped by the container's CPU quota
+        self.n_threads = int(n_threads) if n_threads else max(1, min(32, n_eff // 2 if n_eff >= 16 else n_eff))
         # chunks of whole Machines
         n_chunks = max(1, min(int(n_chunks), self.M))
         b = np.linspace(0, self.M, n_chunks + 1).astype(int)
@@ -127,7 +139,9 @@ class FleetAnomalyServer:
             v = FFFleet(fleet.topo, c - a, dev)
             v.params = fleet.params[a:c]
             if self.precision == "bf16":
-                v._packed = fleet.packed()[a:c]; v._packed_version = v._version
+                v._packed = fleet.packed("bf16")[a:c]; v._packed_version = v._version
+            elif self.precision == "f16x3":
+                v._packed_x3 = fleet.packed("f16x3")[a:c]; v._packed_x3_version = v._version
             for name in ("in_scale", "in_min", "err_scale", "feat_thr", "agg_thr"):
                 t = getattr(fleet, name)
                 setattr(v, name, None if t is None else t[a:c])

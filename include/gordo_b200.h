@@ -39,7 +39,9 @@ enum { GB200_ACT_LINEAR = 0, GB200_ACT_TANH = 1, GB200_ACT_RELU = 2, GB200_ACT_S
 
 /* precision of the dense stacks */
 enum { GB200_PREC_F32 = 0,      /* fp32 FMA, bit-faithful ordering of the reference ops   */
-       GB200_PREC_BF16_TC = 1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */ };
+       GB200_PREC_BF16_TC = 1,  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate */
+       GB200_PREC_F16X3_TC = 2  /* fp32-grade on tcgen05: operands split into hi + lo fp16, 3 MMAs per K step,
+                                   fp32 accumulate; feed-forward scorer only, tanh / sigmoid hidden layers  */ };
 
 /* Feed-forward topology: what gordo/machine/model/factories/feedforward_autoencoder.py:15-104
  * builds as a Keras Sequential of Dense layers. */
@@ -96,7 +98,8 @@ void gb200_fleet_destroy(gb200_fleet* f);
  *   total_anomaly_conf     = total_anomaly_scaled / agg_thr    (diff.py:438-444)
  * Any output pointer may be NULL (skipped).  y == NULL means y aliases x (autoencoder).
  * params       : [M, P] fp32 (GB200_PREC_F32) -- always required
- * packed_bf16  : [M, gb200_ff_packed_bytes()] from gb200_ff_pack_bf16 (GB200_PREC_BF16_TC), else NULL
+ * packed_bf16  : the operand image of the tensor-core precisions: [M, gb200_ff_packed_bytes_prec()] from
+ *                gb200_ff_pack (GB200_PREC_BF16_TC / GB200_PREC_F16X3_TC), else NULL
  * in_scale/in_min : [M, T_in] fp32 (NULL = identity); err_scale : [M, T_out] fp32 (NULL = 1)
  * feat_thr : [M, T_out] or NULL; agg_thr : [M] or NULL
  * activity_l1 : optional [rows] (GB200_PREC_F32 only): sum_l l1[l]*sum_j|h_l[j]| per row -- the activity-
@@ -116,6 +119,10 @@ int gb200_ff_score(gb200_fleet* f, const gb200_ff_arch* arch, int precision,
 int64_t gb200_ff_packed_bytes(const gb200_ff_arch* arch);
 int gb200_ff_pack_bf16(const gb200_ff_arch* arch, int32_t n_machines, const float* params,
                        void* packed_bf16, void* stream);
+/* the same for either tensor-core precision (the F16X3 image holds a hi and a lo fp16 copy of every layer) */
+int64_t gb200_ff_packed_bytes_prec(const gb200_ff_arch* arch, int precision);
+int gb200_ff_pack(const gb200_ff_arch* arch, int precision, int32_t n_machines, const float* params,
+                  void* packed, void* stream);
 int64_t gb200_ff_param_count(const gb200_ff_arch* arch);
 
 /* ---------------------------------------------------------------------------------------------
