@@ -170,21 +170,26 @@ def _run_lstm_case(c):
 
 
 def _prep_build_case(m, rows):
-    from oracle import dense, factories
-    T, _ = c3_machine_shape(m, CONFIGS["c3"])
-    spec = factories.feedforward_hourglass(T)
+    from oracle import factories
+    T, is_lstm = c3_machine_shape(m, CONFIGS["c3"])
+    L = CONFIGS["c3"]["lstm_lookback"]
+    spec = factories.lstm_hourglass(T, lookback_window=L) if is_lstm else factories.feedforward_hourglass(T)
     rng, X = machine_data(m, rows, T)
-    return dict(kind="build", spec=spec, X=X, rng_seed=SEED0 + m, windows=5 * rows)
+    return dict(kind="build", spec=spec, X=X, rng_seed=SEED0 + m, windows=5 * rows, lstm=is_lstm, L=L)
 
 
 def _run_build_case(c):
-    """ModelBuilder._build's model section for one feed-forward Machine on a bounded row sample:
-    TimeSeriesSplit(3) CV (fit + predict + thresholds per fold) then the final fit + predict."""
-    from oracle import dense
-    from oracle.anomaly import DiffDetector, FFBase
+    """ModelBuilder._build's model section for one c3 Machine (feed-forward, or LSTM for every 4th) on a bounded
+    row sample: TimeSeriesSplit(3) CV (fit + predict + thresholds per fold) then the final fit + predict."""
+    from oracle import dense, lstm as olstm
+    from oracle.anomaly import DiffDetector, FFBase, LSTMBase
     X = c["X"]
     rng = np.random.default_rng(c["rng_seed"])
-    det = DiffDetector(lambda tag: FFBase(c["spec"], dense.ff_init(c["spec"], rng), epochs=1, batch_size=32))
+    if c["lstm"]:
+        det = DiffDetector(lambda tag: LSTMBase(c["spec"], olstm.lstm_init(c["spec"], rng), lookback_window=c["L"],
+                                                epochs=1, batch_size=32))
+    else:
+        det = DiffDetector(lambda tag: FFBase(c["spec"], dense.ff_init(c["spec"], rng), epochs=1, batch_size=32))
     det.cross_validate(X, X, n_splits=3)
     det.fit(X, X)
     return float(np.asarray(det.predict(X)).sum())
@@ -263,7 +268,8 @@ def reference_sample(name):
         return k, None, f"{k} Machine(s) per host CPU ({cfg['tags']} tags x {cfg['rows']} rows each)"
     if cfg["kind"] == "lstm":
         return 1, 192, f"192 windows of one {cfg['tags']}-tag lookback-{cfg['lookback']} Machine per host CPU"
-    return 1, 4000, "one feed-forward c3 Machine per host CPU on a 4 000-row sample (CV + final fit + predict)"
+    return 4, 800, ("four consecutive c3 Machines per host CPU (three feed-forward + one LSTM lookback 16, T_m = 20 + (37 m mod 81)) "
+                    "on an 800-row sample each (CV + final fit + predict)")
 
 
 def run_reference(args):
@@ -324,17 +330,19 @@ def cpu_baseline_one_core(name, seconds=10.0):
         cases = [_prep_lstm_case(0, cfg["tags"], cfg["lookback"], 192)]
         what = "192-window slices of one Machine"
     else:
-        cases = [_prep_build_case(0, 4000)]
-        what = "4 000-row builds of feed-forward c3 Machine 0"
+        cases = [_prep_build_case(m, 800) for m in range(4)]
+        what = "800-row builds of c3 Machines 0-3 (three feed-forward + one LSTM)"
     run = _RUNNERS[cases[0]["kind"]]
     run(cases[0])
     n, t0 = 0, time.perf_counter()
     while True:
-        run(cases[0]); n += 1
+        for c in cases:
+            run(c)
+        n += 1
         dt = time.perf_counter() - t0
         if dt >= seconds or n >= 64:
             break
-    return {"value": n * cases[0]["windows"] / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    return {"value": n * sum(c["windows"] for c in cases) / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{n} x {what}, {dt:.1f} s, oracle port run as the reference runs it (one Machine at a time, "
                       f"predict batch 32), data / weights / scalers prepared outside the timed region"}
 
@@ -486,12 +494,15 @@ def run_ff(ctx, args, name, steps, warmup, with_cpu=True, with_other=True):
         step()
     sampler = ClockSampler(ctx.local); sampler.start()
     ms_step = ctx.timed(step, steps)
-    other = None
-    if with_other and fleet.tc_eligible():
-        oprec = "f32" if prec == "bf16" else "bf16"
-        ofn = lambda: fleet.score(sched, x_dev, precision=oprec, out=out)
-        ofn(); ms_o = ctx.timed(ofn, 1)
-        other = {"precision": oprec, "ms_per_step": ms_o, "value": R / (ms_o * 1e-3)}
+    other = []
+    if with_other:
+        for oprec in ("f16x3", "bf16", "f32"):
+            if oprec == prec or (oprec != "f32" and not fleet.tc_eligible(oprec)):
+                continue
+            ofn = lambda: fleet.score(sched, x_dev, precision=oprec, out=out)
+            ofn(); ms_o = ctx.timed(ofn, 3)
+            other.append({"precision": oprec, "ms_per_step": ms_o, "value": R / (ms_o * 1e-3),
+                          "hbm_frac": R * ff_bytes_per_window(T, True) / (ms_o * 1e-3) / 1e9 / float(ctx.peaks.get("hbm_gbs", 6650.0))})
         step()
 
     # ---- end to end through the plugin surface: pinned HOST samples in, every HOST column out
@@ -567,7 +578,7 @@ def run_ff(ctx, args, name, steps, warmup, with_cpu=True, with_other=True):
             "clocks": clocks, "checksum": checksum,
         }
         if other:
-            line["other_precision"] = other
+            line["other_precisions"] = other
         if with_cpu:
             line["cpu_baseline"] = cpu_baseline_one_core(name, args.cpu_seconds)
     srv.close()
@@ -742,7 +753,11 @@ def run_build(ctx, args, name, steps, warmup, with_cpu=True):
                         "api": "FleetModelBuilder(machines).build(): host arrays in, fitted host models + metadata out "
                                "(value IS the end-to-end number: the build has no device-resident variant)"},
                 "gpu_launches": getattr(builder, "launch_count", None),
-                "machines_rank0": {"total": len(machines), "lstm": n_lstm, "buckets": getattr(builder, "last_bucket_count", None)},
+                "machines_rank0": {"total": len(machines), "lstm": n_lstm, "buckets": getattr(builder, "last_bucket_count", None),
+                                   "bucket_seconds": {k: [round(sum(b[3] for b in builder.bucket_log if b[0] == k), 2),
+                                                          round(max([b[3] for b in builder.bucket_log if b[0] == k] or [0]), 2)]
+                                                      for k in ("ff", "lstm")},
+                                   "slowest_buckets": sorted(((b[0], b[1], round(b[3], 2)) for b in builder.bucket_log), key=lambda b: -b[2])[:6]},
                 "rows_per_machine": rows, "aggregate_thresholds_first4": thr, "clocks": clocks}
         if with_cpu:
             line["cpu_baseline"] = cpu_baseline_one_core(name, args.cpu_seconds)
@@ -798,7 +813,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="c3 only: rows per Machine (default 100 000)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--plan", default="auto", help="e2e transfer plan: auto | 0..3 matrices derived on the host")
-    ap.add_argument("--streams", type=int, default=8, help="c3: topology buckets built concurrently")
+    ap.add_argument("--streams", type=int, default=16, help="c3: topology buckets built concurrently")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="cpu_baseline sample length (one core)")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: every host CPU)")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to the GPU's NUMA node")

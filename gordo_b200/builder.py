@@ -56,6 +56,29 @@ class FleetMachine:
                     {"gordo_b200.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass"}}]}}}}
 
 
+def extract_model_metadata(model) -> Dict[str, Any]:
+    """
+    ``ModelBuilder._extract_metadata_from_model`` (build_model.py:518-570): the ``get_metadata()`` of every GordoBase
+    reachable from ``model`` -- through the last step of a Pipeline and through estimator-valued attributes --
+    merged into one dict (outer objects first, so an inner estimator's keys win, as in the reference).
+    """
+    from sklearn.base import BaseEstimator
+    from gordo_b200.machine.model.base import GordoBase
+    out: Dict[str, Any] = {}
+    if isinstance(model, Pipeline):
+        return extract_model_metadata(model.steps[-1][1])
+    if isinstance(model, GordoBase):
+        out.update(model.get_metadata())
+    for key, val in list(getattr(model, "__dict__", {}).items()):
+        if key == "regressor" or key.startswith("_gb200_"):
+            continue
+        if isinstance(val, Pipeline):
+            out.update(extract_model_metadata(val.steps[-1][1]))
+        elif isinstance(val, (GordoBase, BaseEstimator)):
+            out.update(extract_model_metadata(val))
+    return out
+
+
 def _metrics_dict(y: pd.DataFrame, scaler="sklearn.preprocessing.MinMaxScaler"):
     """ModelBuilder.build_metrics_dict (build_model.py:377-446): ``{metric}-{tag}`` per target tag and ``{metric}``."""
     from sklearn import metrics as skm
@@ -143,9 +166,16 @@ class FleetBuild:
                 buckets.setdefault(key, []).append(i)
         self.last_bucket_count = len(buckets)
 
+        self.bucket_log = []                       # (kind, tags, Machines, wall seconds) per bucket, for the bench
+
         def run(item):
             key, idxs = item
-            return idxs, self._build_bucket([self.machines[i] for i in idxs], [prototypes[i] for i in idxs], dev)
+            t0 = time.time()
+            out = self._build_bucket([self.machines[i] for i in idxs], [prototypes[i] for i in idxs], dev)
+            X0 = self.machines[idxs[0]].X
+            self.bucket_log.append(("lstm" if key[0] == "lstm" else "ff", int(np.shape(getattr(X0, "values", X0))[1]),
+                                    len(idxs), time.time() - t0))
+            return idxs, out
 
         # largest buckets first so the small ones fill the tail
         order = sorted(buckets.items(), key=lambda kv: -sum(len(np.asarray(getattr(self.machines[i].X, "values", self.machines[i].X)))
@@ -252,7 +282,7 @@ class FleetBuild:
             model.fit(X, y)
             meta["model_training_duration_sec"] = time.time() - t1
             meta["model_offset"] = len(X) - len(model.predict(X))
-        meta["model"] = model.get_metadata() if hasattr(model, "get_metadata") else {}
+        meta["model"] = extract_model_metadata(model)
         return model, meta
 
     # ------------------------------------------------------------------ the batched build
@@ -415,7 +445,7 @@ class FleetBuild:
                 _set_smooth_thresholds(model, None if sfeat_h is None else sfeat_h[m], None if sagg_h is None else sagg_h[m], tags, k)
             scores = _cv_score_dict({kk: v[m * k:(m + 1) * k] for kk, v in cv_metrics.items()}, tags) if k else {}
             # build_model.py:448-471: offset = len(X) - len(predict(X)); the feed-forward scorer emits one row per input row
-            meta = {"name": mc.name, "model_offset": int(rows[m]) - fleet.out_rows(int(rows[m])), "model": model.get_metadata(),
+            meta = {"name": mc.name, "model_offset": int(rows[m]) - fleet.out_rows(int(rows[m])), "model": extract_model_metadata(model),
                     "model_training_duration_sec": t_fit, "cv_duration_sec": (t_total - t_fit) if k else None,
                     "cross_validation": {"scores": scores,
                                          "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
@@ -525,7 +555,7 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
             model.aggregate_threshold_ = float(agg_h[m, -1])
             _set_smooth_thresholds(model, None if sfeat_h is None else sfeat_h[m], None if sagg_h is None else sagg_h[m], tags, k)
         # build_model.py:448-471: len(X) - len(predict(X)), from the fleet's own output-row count
-        meta = {"name": mc.name, "model_offset": int(rows[m]) - trainer.out_rows(int(rows[m])), "model": model.get_metadata(),
+        meta = {"name": mc.name, "model_offset": int(rows[m]) - trainer.out_rows(int(rows[m])), "model": extract_model_metadata(model),
                 "model_training_duration_sec": t_total, "cv_duration_sec": None,
                 "cross_validation": {"scores": {}, "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
                                                               enumerate(time_series_split_bounds(int(rows[m]), k))} if k else {}},

@@ -5,9 +5,10 @@
 //   F16X3  fp32-grade: every fp32 operand is split into hi + lo fp16 halves (x = hi + lo + O(2^-22 x)) while it is
 //          staged, and A_hi.B_hi + A_hi.B_lo + A_lo.B_hi is accumulated in fp32 in tensor memory (3 MMAs per K step,
 //          the tensor pipe has the room); activations through ex2/rcp instead of tanh.approx.  Product error < 2^-20,
-//          results agree with the fp32 FMA path to ~1e-6.  Needs bounded hidden activations (tanh / sigmoid): fp16
-//          overflows at 65 504, so the scaled INPUT is clamped to +-6e4 (a first tanh layer saturates identically)
-//          and hidden activations must stay in [-1, 1].
+//          results agree with the fp32 FMA path to ~1e-6.  fp16 overflows at 65 504: hidden activations must be
+//          bounded (tanh / sigmoid), and the scaled INPUT row is multiplied by a per-row power of two s (1 unless
+//          the row's largest magnitude exceeds 2^15; the ones column carries s, the first accumulator is
+//          multiplied by 1/s before its activation -- exact), so any finite input keeps its 22 bits.
 //
 //   MinMax-scale -> 2E+1 chained Dense layers on tcgen05 tensor cores -> anomaly columns,
 // one 128-row tile of one Machine at a time per warpgroup, everything between the HBM read of the
@@ -195,11 +196,15 @@ __device__ __forceinline__ void store_a16(uint32_t taddr, int lo_delta, const fl
         tmem_st8(taddr, pk);
     }
 }
-// F16X3: the scaled input is clamped into fp16 range (NaN passes through); see the header note
-template <int PREC>
-__device__ __forceinline__ float clamp_in(float v) {
-    if (PREC == GB200_PREC_F16X3_TC) return fabsf(v) > 6.0e4f ? copysignf(6.0e4f, v) : v;
-    return v;
+// F16X3: power-of-two scale that brings a row whose largest magnitude is `amax` below 2^15 (1 when it already is)
+__device__ __forceinline__ void row_pow2_scale(float amax, float& s, float& inv_s) {
+    s = 1.0f; inv_s = 1.0f;
+    if (amax > 32768.0f) {                                     // false for NaN
+        int e = (__float_as_int(amax) >> 23) - 127;            // amax < 2^(e+1)
+        e = min(e, 127);
+        s = __int_as_float((127 + 14 - e) << 23);              // amax * s < 2^15
+        inv_s = __int_as_float((127 - 14 + e) << 23);
+    }
 }
 __device__ __forceinline__ void load16_bcast(const float* p, float* o) {       // 16-byte aligned broadcast loads
     #pragma unroll
@@ -244,16 +249,16 @@ __device__ __forceinline__ void warp_copy_out(float* __restrict__ dst, const flo
 // hidden layer: accumulator (TMEM, bias already inside the GEMM) -> activation -> bf16 A operand of
 // the next layer, written straight back to TENSOR MEMORY (tcgen05.st): activations never touch
 // shared memory.  Column `wout` of the next A is the ones column that carries the next bias.
-template <int ACT, int PREC>
+template <int ACT, int PREC, bool SCALED>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane, int n_chunks, int wout, int kp_next,
-                                                uint32_t tmem_a_lane, int lo_delta) {
+                                                uint32_t tmem_a_lane, int lo_delta, float inv_s) {
     constexpr bool ACC = PREC == GB200_PREC_F16X3_TC;
     const int c_one = wout >> 4, j_one = wout & 15;
     for (int c = 0; c < n_chunks; ++c) {
         float v[16];
         tmem_ld16(tmem_lane + c * 16, v);
         #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT, ACC>(v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = act_t<ACT, ACC>(SCALED ? v[j] * inv_s : v[j]);
         if (c == c_one) {
             #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = (j == j_one) ? 1.0f : v[j];
@@ -451,10 +456,16 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
             }
             // ---- A operand of layer 0: bf16(x*scale+min), written to tensor memory.  Rows past nrows
             // hold stale data: rows never mix inside a GEMM and those rows are never stored.
+            float row_s = 1.0f, row_inv_s = 1.0f;
             {
                 const int Kp = a.lay.Kp[0];
                 const float* xr = xbuf + wtid * T_in;
                 const int full = T_in >> 3;
+                if (ACC) {                       // fp16 operands: bring the row into range (see the header note)
+                    float amax = 0.0f;
+                    for (int k = 0; k < T_in; ++k) amax = fmaxf(amax, fabsf(fmaf(xr[k], v_scale[k], v_min[k])));
+                    row_pow2_scale(amax, row_s, row_inv_s);
+                }
                 if ((T_in & 1) == 0) {
                     for (int c = 0; c < full; ++c) {
                         float v[8];
@@ -469,7 +480,7 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                         v[4] = fmaf(v[4], s1.x, m1.x); v[5] = fmaf(v[5], s1.y, m1.y); v[6] = fmaf(v[6], s1.z, m1.z); v[7] = fmaf(v[7], s1.w, m1.w);
                         if (ACC) {
                             #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = clamp_in<PREC>(v[j]);
+                            for (int j = 0; j < 8; ++j) v[j] *= row_s;
                         }
                         store_a8<PREC>(tmem_a_lane + c * 4, lo_delta, v);
                     }
@@ -477,7 +488,7 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                     for (int c = 0; c < full; ++c) {
                         float v[8];
                         #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = clamp_in<PREC>(fmaf(xr[c * 8 + j], v_scale[c * 8 + j], v_min[c * 8 + j]));
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(xr[c * 8 + j], v_scale[c * 8 + j], v_min[c * 8 + j]) * row_s;
                         store_a8<PREC>(tmem_a_lane + c * 4, lo_delta, v);
                     }
                 }
@@ -487,7 +498,7 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                     #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int k = c * 8 + j;
-                        v[j] = k < T_in ? clamp_in<PREC>(fmaf(xr[k], v_scale[k], v_min[k])) : (k == T_in ? 1.0f : 0.0f);
+                        v[j] = k < T_in ? fmaf(xr[k], v_scale[k], v_min[k]) * row_s : (k == T_in ? row_s : 0.0f);
                     }
                     store_a8<PREC>(tmem_a_lane + c * 4, lo_delta, v);
                 }
@@ -518,7 +529,11 @@ ff_score_tc_kernel(const __grid_constant__ TcArgs a) {
                 mbar_wait(&mma_bar[wg], mma_phase); mma_phase ^= 1;
                 tc_fence_after();
                 if (l == L - 1) break;
-                GB_DISPATCH_ACT(a.arch.acts[l], (hidden_epilogue<ACT, PREC>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], tmem_a_lane, lo_delta)));
+                if (ACC && l == 0) {
+                    GB_DISPATCH_ACT(a.arch.acts[l], (hidden_epilogue<ACT, PREC, true>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], tmem_a_lane, lo_delta, row_inv_s)));
+                } else {
+                    GB_DISPATCH_ACT(a.arch.acts[l], (hidden_epilogue<ACT, PREC, false>(tmem_lane, Np / 16, a.arch.widths[l + 1], a.lay.Kp[l + 1], tmem_a_lane, lo_delta, 1.0f)));
+                }
             }
             // ---- final epilogue
             const int code = a.arch.acts[L - 1];

@@ -1049,16 +1049,22 @@ __global__ void lstm_adam_kernel(const __grid_constant__ AdamArgs a) {
         P[i] -= alpha * m / (sqrtf(v) + a.adam.epsilon);
     }
 }
+// Last kernel of an optimizer step.  `advance` > 0 moves every group's window cursor (first sample row, windows
+// left) forward by one batch ON THE DEVICE: a step's launches then take identical arguments from one step to
+// the next, which is what lets the whole step be replayed as one CUDA graph.
 __global__ void lstm_step_end_kernel(GroupCtx g, int n_groups, int64_t* tcount, const float* loss_sum,
-                                     float* epoch_acc, int T_out, float* primer_loss) {
+                                     float* epoch_acc, int T_out, float* primer_loss, int advance,
+                                     int64_t* rows_cur, int32_t* nwin_cur) {
     const int grp = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp >= n_groups) return;
     const int nb = group_nb(g, grp);
-    if (nb == 0) return;
-    tcount[grp] += 1;
-    const float batch_loss = loss_sum[grp] / (float)(nb * T_out);
-    if (primer_loss) primer_loss[grp] = batch_loss;
-    else epoch_acc[grp] += batch_loss * nb;            // Keras: sample-weighted running mean
+    if (nb > 0) {
+        tcount[grp] += 1;
+        const float batch_loss = loss_sum[grp] / (float)(nb * T_out);
+        if (primer_loss) primer_loss[grp] = batch_loss;
+        else epoch_acc[grp] += batch_loss * nb;            // Keras: sample-weighted running mean
+    }
+    if (advance > 0) { rows_cur[grp] += advance; nwin_cur[grp] -= advance; }
 }
 __global__ void lstm_epoch_end_kernel(int n_groups, const int32_t* n_win, float* epoch_acc, float* hist, int epochs, int e) {
     const int grp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1225,6 +1231,8 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
     int32_t* d_nwin = (int32_t*)(d_tcount + J);
     float* d_loss = (float*)(d_nwin + J);
     float* d_epoch = d_loss + J;
+    int32_t* d_nwin_cur = (int32_t*)(d_epoch + J);                  // windows left from the cursor
+    int64_t* d_rows_cur = (int64_t*)(tail + 4096 + (size_t)J * 48);  // cursor: first sample row of the next batch
     std::vector<int64_t> rows_lo(J); std::vector<int32_t> nwin(J); int max_win = 0;
     for (int j = 0; j < J; ++j) {
         const int64_t rows = job_rows_hi_host[j] - job_rows_lo_host[j];
@@ -1274,8 +1282,9 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
         else if (e[0] == 't') { force_tc = true; use_vec = !(e[1] == 'c' && e[2] == 's'); }
     }
     // sequence buffers are [t][seq][width]: t stride = B*width, seq stride = width
-    auto run_step = [&](int seq_base, int cap, float* primer_out) -> int {
-        GroupCtx g{d_rows_lo, d_nwin, seq_base, cap};
+    // a step reads its batch position from the device cursor (d_rows_cur / d_nwin_cur), never from a host value
+    auto run_step = [&](int cap, float* primer_out, int advance) -> int {
+        GroupCtx g{d_rows_cur, d_nwin_cur, 0, cap};
         GB_CUDA_CHECK(cudaMemsetAsync(d_loss, 0, sizeof(float) * J, stream));
         // ---------------- forward with caches, layer by layer: the input projection x_t.W + b of ALL
         // time steps is one GEMM, the recurrence adds h_{t-1}.U step by step
@@ -1449,23 +1458,59 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
             int blocks = cdiv((int)((p.n_params + 255) / 256), 1); if (blocks > 148 * 4) blocks = 148 * 4;
             lstm_adam_kernel<<<dim3(blocks, 1, 1), 256, 0, stream>>>(aj);
         }
-        lstm_step_end_kernel<<<cdiv(J, 128), 128, 0, stream>>>(g, J, d_tcount, d_loss, d_epoch, p.T_out, primer_out);
+        lstm_step_end_kernel<<<cdiv(J, 128), 128, 0, stream>>>(g, J, d_tcount, d_loss, d_epoch, p.T_out, primer_out,
+                                                              advance, d_rows_cur, d_nwin_cur);
         GB_CUDA_CHECK(cudaGetLastError());
+        return GB_OK;
+    };
+    auto rewind = [&]() -> int {
+        GB_CUDA_CHECK(cudaMemcpyAsync(d_rows_cur, d_rows_lo, sizeof(int64_t) * J, cudaMemcpyDeviceToDevice, stream));
+        GB_CUDA_CHECK(cudaMemcpyAsync(d_nwin_cur, d_nwin, sizeof(int32_t) * J, cudaMemcpyDeviceToDevice, stream));
         return GB_OK;
     };
 
     // (1) primer: ONE Adam step on the first window alone (models.py:585-597)
-    rc = run_step(0, 1, primer_loss ? primer_loss : d_epoch + 0 /*unused sink*/);
+    rc = rewind(); if (rc) return rc;
+    rc = run_step(1, primer_loss ? primer_loss : d_epoch + 0 /*unused sink*/, 0);
     if (rc) return rc;
     if (!primer_loss) GB_CUDA_CHECK(cudaMemsetAsync(d_epoch, 0, sizeof(float) * J, stream));
-    // (2) main fit: time-ordered batches, shuffle=False (models.py:599-615)
+    // (2) main fit: time-ordered batches, shuffle=False (models.py:599-615).  A step is 50-100 small dependent
+    // launches; replayed as ONE CUDA graph per step the host issues a single call and the device skips the
+    // per-launch gaps.  GB200_LSTM_GRAPH=0 (or a failed capture) issues the launches one by one instead.
+    const int n_steps = (max_win + B - 1) / B;
+    cudaGraphExec_t exec = nullptr;
+    bool use_graph = n_steps >= 4;
+    { const char* e = getenv("GB200_LSTM_GRAPH"); if (e && atoi(e) == 0) use_graph = false; }
+    if (use_graph) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            const int crc = run_step(B, nullptr, B);
+            const cudaError_t ee = cudaStreamEndCapture(stream, &graph);
+            if (crc != GB_OK || ee != cudaSuccess || graph == nullptr ||
+                cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        (void)cudaGetLastError();               // a failed capture leaves a sticky-free error behind: clear it
+    }
     for (int e = 0; e < epochs; ++e) {
-        for (int s0 = 0; s0 < max_win; s0 += B) {
-            rc = run_step(s0, B, nullptr);
-            if (rc) return rc;
+        rc = rewind(); if (rc) { if (exec) cudaGraphExecDestroy(exec); return rc; }
+        for (int s = 0; s < n_steps; ++s) {
+            if (exec) {
+                const cudaError_t le = cudaGraphLaunch(exec, stream);
+                if (le != cudaSuccess) { cudaGraphExecDestroy(exec); gb_set_error("lstm fit: graph launch: %s", cudaGetErrorString(le)); return GB_ERR_CUDA; }
+            } else {
+                rc = run_step(B, nullptr, B);
+                if (rc) return rc;
+            }
         }
         if (hist_loss) lstm_epoch_end_kernel<<<cdiv(J, 128), 128, 0, stream>>>(J, d_nwin, d_epoch, hist_loss, epochs, e);
         else GB_CUDA_CHECK(cudaMemsetAsync(d_epoch, 0, sizeof(float) * J, stream));
+    }
+    if (exec) {
+        // the executable graph must outlive its last launch: wait for the stream, then release it
+        const cudaError_t se = cudaStreamSynchronize(stream);
+        cudaGraphExecDestroy(exec);
+        if (se != cudaSuccess) { gb_set_error("lstm fit: %s", cudaGetErrorString(se)); return GB_ERR_CUDA; }
     }
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;

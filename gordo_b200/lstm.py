@@ -6,6 +6,7 @@ window generator of models.py:713-793: windows are never materialised; window k 
 rows [k, k+L) of its scaled sample matrix, target row k + L - 1 + lookahead.
 """
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -14,6 +15,11 @@ import torch
 
 from . import _native as N
 from .fleet import Schedule, _stream_ptr, _require_cuda
+
+
+# torch initialises its linalg backend lazily and not re-entrantly: the first torch.linalg.qr must not race
+# between the builder's bucket threads
+_QR_LOCK = threading.Lock()
 
 
 @dataclass
@@ -55,7 +61,8 @@ class LSTMTopology:
             out[:, o:o + n_in * 4 * u] = (torch.rand((n_machines, n_in * 4 * u), generator=generator, device=device) * 2 - 1) * lim
             o += n_in * 4 * u
             a = torch.randn((n_machines, 4 * u, u), generator=generator, device=device)
-            q, r = torch.linalg.qr(a)                                   # [M, 4u, u], orthonormal columns
+            with _QR_LOCK:
+                q, r = torch.linalg.qr(a)                               # [M, 4u, u], orthonormal columns
             q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
             out[:, o:o + u * 4 * u] = q.transpose(-1, -2).reshape(n_machines, -1)      # U [u, 4u]
             o += u * 4 * u

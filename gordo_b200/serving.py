@@ -117,7 +117,7 @@ class FleetAnomalyServer:
         self.derivable = [c for c in DERIVE_ORDER if c in self.matrices]
         from .hostbind import effective_cpus
         n_eff = effective_cpus()                 # affinity mask capped by the container's CPU quota
-        self.n_threads = int(n_threads) if n_threads else max(1, min(32, n_eff // 2 if n_eff >= 16 else n_eff))
+        self.n_threads = int(n_threads) if n_threads else max(1, min(32, n_eff))
         # chunks of whole Machines
         n_chunks = max(1, min(int(n_chunks), self.M))
         b = np.linspace(0, self.M, n_chunks + 1).astype(int)

@@ -65,7 +65,10 @@ def test_ff_fit_topologies_beyond_shared_memory_match_oracle(kind, T, batch, kw)
                                perm_pool=pool, perm_off=_i64(lo))
     torch.cuda.synchronize()
     for j in range(len(rows)):
-        np.testing.assert_allclose(params[j].cpu().numpy(), want[j], rtol=0, atol=3e-4, err_msg=f"job {j}")
+        # Adam normalises every gradient to ~lr: a near-zero gradient whose fp32 summation order differs moves a weight
+        # by a visible fraction of lr per step; a handful of 37 422 weights lands between 3e-4 and 6e-4
+        np.testing.assert_allclose(params[j].cpu().numpy(), want[j], rtol=0, atol=6e-4, err_msg=f"job {j}")
+        assert float(np.mean(np.abs(params[j].cpu().numpy() - want[j]))) < 2e-5
         np.testing.assert_allclose(hl[j].cpu().numpy(), want_h[j]["loss"], rtol=3e-4)
         np.testing.assert_allclose(ha[j].cpu().numpy(), want_h[j]["accuracy"], atol=2.0 / rows[j])
 
@@ -305,7 +308,7 @@ X3_CASES = {
     "c2_shape_3x50": dict(seed=3, row_counts=[4096, 1003, 2500], T=50),
     "sigmoid_T33_E2": dict(seed=6, row_counts=[513], T=33, func="sigmoid", encoding_layers=2),
     "separate_y_T12_to_4": dict(seed=7, row_counts=[400, 333], T=12, T_out=4),
-    "T100_two_engines": dict(seed=12, row_counts=[700, 300], T=100),
+    "T64": dict(seed=12, row_counts=[700, 300], T=64),
     "no_thresholds_T20": dict(seed=13, row_counts=[640, 64], T=20, thresholds=False),
 }
 
@@ -320,7 +323,7 @@ def test_ff_score_f16x3_is_fp32_grade(name):
     assert fl.tc_eligible("f16x3") and fl.auto_precision("f16x3") == "f16x3"
     res = fl.score(sched, X, Y, precision="f16x3")
     torch.cuda.synchronize()
-    _compare(res, case, None, 2e-5 if X3_CASES[name]["T"] < 100 else 5e-5, 2e-4, 2e-6)
+    _compare(res, case, None, 2e-5, 2e-4, 2e-6)
     r32 = fl.score(sched, X, Y, precision="f32")
     e = (res["model-output"] - r32["model-output"]).abs()
     if e.numel():
@@ -333,8 +336,11 @@ def test_ff_score_f16x3_eligibility_and_input_range():
     relu = make_fleet_case(seed=5, row_counts=[64], T=20, func="relu")
     fl, _, _, _ = fleet_from_case(relu)
     assert not fl.tc_eligible("f16x3") and fl.auto_precision("f16x3") == "f32" and fl.tc_eligible("bf16")
-    # inputs far outside fp16 range and NaNs: finite rows stay finite and equal the fp32 kernel where the first
-    # tanh layer saturates the same way; a NaN input poisons its own row only
+    wide = make_fleet_case(seed=5, row_counts=[64], T=100)          # hi + lo images of 100 tags exceed shared memory
+    fw, _, _, _ = fleet_from_case(wide)
+    assert not fw.tc_eligible("f16x3") and fw.auto_precision("f16x3") == "f32" and fw.tc_eligible("bf16")
+    # inputs far outside fp16 range and NaNs: the per-row power-of-two scale keeps every finite row equal to the
+    # fp32 kernel; a NaN input poisons its own row only
     case = make_fleet_case(seed=21, row_counts=[256], T=10)
     fl, sched, X, Y = fleet_from_case(case)
     Xb = X.clone()
@@ -344,7 +350,11 @@ def test_ff_score_f16x3_eligibility_and_input_range():
     ok = torch.ones(256, dtype=torch.bool, device=X.device); ok[[3, 7, 11]] = False
     np.testing.assert_allclose(a[ok].cpu().numpy(), b[ok].cpu().numpy(), rtol=0, atol=2e-5)
     assert bool(torch.isnan(a[7]).all()) and bool(torch.isfinite(a[3]).all()) and bool(torch.isfinite(a[11]).all())
-    np.testing.assert_allclose(a[[3, 11]].cpu().numpy(), b[[3, 11]].cpu().numpy(), rtol=0, atol=1e-3)
+    np.testing.assert_allclose(a[[3, 11]].cpu().numpy(), b[[3, 11]].cpu().numpy(), rtol=0, atol=2e-5)
+    Xc = X.clone(); Xc[5] *= 4e5; Xc[9, 3] = 7e4                    # just past fp16's range, mixed magnitudes in one row
+    a2 = fl.score(sched, Xc, None, precision="f16x3")["model-output"]
+    b2 = fl.score(sched, Xc, None, precision="f32")["model-output"]
+    np.testing.assert_allclose(a2.cpu().numpy(), b2.cpu().numpy(), rtol=0, atol=2e-5)
 
 
 def test_estimator_and_detector_with_f16x3_precision():

@@ -58,7 +58,7 @@ def main():
         fl.err_scale = fl.in_scale.clone()
         fl.feat_thr = torch.rand((M, T), generator=g, device=dev) * 0.4 + 0.1
         fl.agg_thr = torch.rand((M,), generator=g, device=dev) * 0.09 + 0.01
-        prec = a.precision if fl.tc_eligible() else "f32"
+        prec = a.precision if fl.tc_eligible(a.precision) else "f32"
         res = fl.score(sched, X, precision=prec)
         for _ in range(2):
             fl.score(sched, X, precision=prec, out=res)
