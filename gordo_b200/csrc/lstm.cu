@@ -786,9 +786,23 @@ __global__ void lstm_colsum_kernel(GroupCtx g, int B, int rows, int N, const flo
     const int lane_r = threadIdx.x >> 5;                 // 8 row lanes
     __shared__ float part[8][33];
     float acc = 0.0f;
-    if (n < N)
-        for (int r = lane_r; r < rows; r += 8)
-            if ((r % B) < nb) acc += dz[(size_t)grp * dz_grp + (size_t)r * N + n];
+    if (n < N) {
+        // four independent partial sums: the loads of a thread's 4 rows are in flight together (one dependent
+        // add per load made this kernel 30 us for 400 KB: pure load latency)
+        const float* base = dz + (size_t)grp * dz_grp + n;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        int r = lane_r;
+        for (; r + 24 < rows; r += 32) {
+            const float v0 = ((r % B) < nb) ? base[(size_t)r * N] : 0.0f;
+            const float v1 = (((r + 8) % B) < nb) ? base[(size_t)(r + 8) * N] : 0.0f;
+            const float v2 = (((r + 16) % B) < nb) ? base[(size_t)(r + 16) * N] : 0.0f;
+            const float v3 = (((r + 24) % B) < nb) ? base[(size_t)(r + 24) * N] : 0.0f;
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+        for (; r < rows; r += 8)
+            if ((r % B) < nb) a0 += base[(size_t)r * N];
+        acc = (a0 + a1) + (a2 + a3);
+    }
     part[lane_r][threadIdx.x & 31] = acc;
     __syncthreads();
     if (lane_r == 0 && n < N) {
@@ -995,10 +1009,10 @@ __global__ void lstm_rec_bwd_kernel(const __grid_constant__ RecArgs a) {
 }
 
 struct RecPlan { bool ok; int CL, us, nc, BP, width_f, ng_f, width_b, ng_b; size_t smem_f, smem_b; };
-static RecPlan make_rec_plan(int u, int B) {
+static RecPlan make_rec_plan_cl(int u, int B, int CL) {
     RecPlan r{};
     r.BP = (B + REC_SG - 1) / REC_SG * REC_SG;
-    r.CL = u > 64 ? 8 : (u > 32 ? 4 : (u > 16 ? 2 : 1));
+    r.CL = CL;
     r.us = (u + r.CL - 1) / r.CL;
     r.nc = 4 * r.us;
     r.width_f = (r.nc + 31) / 32 * 32;
@@ -1009,6 +1023,24 @@ static RecPlan make_rec_plan(int u, int B) {
     r.smem_f = sizeof(float) * ((size_t)u * r.nc + (size_t)2 * u * r.BP + (size_t)r.nc * (r.BP + 1) + (size_t)r.us * r.BP);
     r.smem_b = sizeof(float) * ((size_t)r.nc * u + (size_t)r.nc * r.BP + (size_t)2 * r.CL * r.us * r.BP + (size_t)r.us * r.BP);
     r.ok = u <= 256 && r.ng_f >= 1 && r.ng_b >= 1 && r.smem_f <= 200 * 1024 && r.smem_b <= 200 * 1024;
+    return r;
+}
+// Cluster size of the recurrence: a time step costs (B * u * 4u / CL) FMAs per CTA plus one cluster barrier + DSMEM
+// hand-over.  The per-CTA FMA loop, not the barrier, is the longer part: measured on a 4-job fit (r2, lookback 16,
+// profiles/README.md r2c) at 60 tags (u = 30-50) 1 / 2 / 4 / 8 CTAs per job = 388 / 264 / 206 / 174 ms, at 30 tags
+// 208 (2-4 CTAs) vs 138 ms (8) -- so every layer with >= 3 units per CTA gets the full portable cluster of 8.
+// The first size >= the rule whose slices fit in shared memory wins (large batches need more CTAs).
+static RecPlan make_rec_plan(int u, int B) {
+    int min_cl = u >= 24 ? 8 : (u >= 12 ? 4 : (u >= 6 ? 2 : 1));
+    if (const char* e = getenv("GB200_LSTM_REC_CL")) {              // tuning knob: smallest cluster size to try
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) min_cl = v;
+    }
+    RecPlan r{};
+    for (int cl = min_cl; cl <= 8; cl <<= 1) {
+        r = make_rec_plan_cl(u, B, cl);
+        if (r.ok) return r;
+    }
     return r;
 }
 static int launch_rec(bool fwd, const RecPlan& rp, RecArgs& a, int J, cudaStream_t stream) {
@@ -1452,7 +1484,7 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
         // (kernel indexes grad + grp*n_params): launch per job instead
         for (int j = 0; j < J; ++j) {
             AdamArgs aj = ad;
-            aj.g.rows_lo = d_rows_lo + j; aj.g.n_win = d_nwin + j;
+            aj.g.rows_lo = d_rows_cur + j; aj.g.n_win = d_nwin_cur + j;      // the cursor: a finished job takes no step
             aj.params = params + (size_t)j * p.n_params; aj.grad = S + (size_t)j * per_job + grad_o;
             aj.mv = S + (size_t)j * per_job + mv_o; aj.tcount = d_tcount + j;
             int blocks = cdiv((int)((p.n_params + 255) / 256), 1); if (blocks > 148 * 4) blocks = 148 * 4;
@@ -1475,12 +1507,14 @@ int gb200_lstm_fit(const gb200_lstm_arch* arch, const gb200_adam* adam, int32_t 
     if (rc) return rc;
     if (!primer_loss) GB_CUDA_CHECK(cudaMemsetAsync(d_epoch, 0, sizeof(float) * J, stream));
     // (2) main fit: time-ordered batches, shuffle=False (models.py:599-615).  A step is 50-100 small dependent
-    // launches; replayed as ONE CUDA graph per step the host issues a single call and the device skips the
-    // per-launch gaps.  GB200_LSTM_GRAPH=0 (or a failed capture) issues the launches one by one instead.
+    // launches with identical arguments from step to step (the batch position lives on the device), so it can be
+    // replayed as ONE CUDA graph per step: GB200_LSTM_GRAPH=1.  Off by default -- on the c3 build (many concurrent
+    // streams, steps bound by the cluster recurrence kernels, not by launches) the replay measured slower than
+    // stream launches (profiles/README.md r2c); a legacy-default-stream caller cannot capture at all.
     const int n_steps = (max_win + B - 1) / B;
     cudaGraphExec_t exec = nullptr;
-    bool use_graph = n_steps >= 4;
-    { const char* e = getenv("GB200_LSTM_GRAPH"); if (e && atoi(e) == 0) use_graph = false; }
+    bool use_graph = false;
+    { const char* e = getenv("GB200_LSTM_GRAPH"); if (e && atoi(e) == 1 && n_steps >= 4) use_graph = true; }
     if (use_graph) {
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {

@@ -237,3 +237,34 @@ def test_fleet_builder_lstm_bucket_matches_oracle():
         want = det.anomaly(Xd, Xd)
         assert len(f) == rows[m] - L + 1
         np.testing.assert_allclose(f["total-anomaly-confidence"].to_numpy().ravel(), want["total-anomaly-confidence"], rtol=2e-2, atol=1e-4)
+
+
+def test_lstm_fit_graph_replay_on_a_side_stream_equals_stream_launches(monkeypatch):
+    """GB200_LSTM_GRAPH=1: an optimizer step replayed as one CUDA graph (the batch cursor lives on the device) must
+    give bit-identical weights to the launch-by-launch path; jobs of different lengths stop stepping when they run out."""
+    from gordo_b200.lstm import LSTMFleet
+    rng = np.random.default_rng(15)
+    T, L, B = 4, 5, 8
+    spec = _spec(T, L, enc=(6,), dec=(5,), funcs=("tanh",))
+    rows = [120, 61, 90]
+    X = torch.from_numpy(rng.random((sum(rows), T)).astype(np.float32)).to(DEV)
+    lo = np.concatenate([[0], np.cumsum(rows)[:-1]]); hi = np.cumsum(rows)
+    init = torch.from_numpy(np.stack([olstm.lstm_flatten(olstm.lstm_init(spec, rng)) for _ in rows])).to(DEV)
+    fl = LSTMFleet(_topo(spec), 3, 0, DEV)
+    outs = {}
+    side = torch.cuda.Stream()
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GB200_LSTM_GRAPH", mode)
+        p = init.clone()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            hl, pl = fl.fit_jobs(X, X, lo, hi, p, epochs=2, batch_size=B)
+        side.synchronize()
+        outs[mode] = (p.cpu().numpy(), hl.cpu().numpy())
+    np.testing.assert_array_equal(outs["0"][0], outs["1"][0])
+    np.testing.assert_array_equal(outs["0"][1], outs["1"][1])
+    # and both equal the oracle for the shortest job (it must not keep stepping after its last batch)
+    pj = olstm.lstm_unflatten(init[1].cpu().numpy(), spec)
+    Xj = X[lo[1]:hi[1]].cpu().numpy()
+    olstm.lstm_fit(spec, pj, Xj, Xj, lookback_window=L, lookahead=0, batch_size=B, epochs=2)
+    np.testing.assert_allclose(outs["1"][0][1], olstm.lstm_flatten(pj), atol=3e-4)
