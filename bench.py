@@ -282,7 +282,8 @@ def run_reference(args):
     # one worker per CPU the container may actually use: a GPU lease can SEE every CPU of the host while its
     # cgroup grants the time of a few (round 1: 128 processes delivered 5x one core) -- oversubscribing the quota
     # only adds context switches.  Workers are spread over physical cores (stride over the sorted list).
-    n_workers = args.ref_procs or effective_cpus()
+    q = cpu_quota()                                     # the whole quota: the other ranks of a torchrun launch exit at once
+    n_workers = args.ref_procs or (max(1, min(len(cpus), int(q + 0.5))) if q else len(cpus))
     stride = max(1, len(cpus) // n_workers)
     cpus = cpus[::stride][:n_workers]
     k, arg, what = reference_sample(name)

@@ -186,10 +186,18 @@ quantile_kernel(const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, 
                 if (x == x) {
                     const uint32_t k = f2key(x);
                     if ((k & s_mask[j]) == s_prefix[j]) {
-                        // scores cluster in a few bins: lanes that hit the same bin add once, together
+                        // scores cluster in a few bins (one exponent): when every active lane hits the SAME bin one
+                        // lane adds the count (a shuffle + a vote; MATCH.ANY per element was the kernel's bottleneck),
+                        // otherwise the lanes are spread and plain shared-memory atomics rarely collide
                         const int bin = (int)((k >> shifts[p]) & (nb - 1));
-                        const unsigned peers = __match_any_sync(__activemask(), bin);
-                        if (lane == __ffs(peers) - 1) atomicAdd(&qhist[j * Q_BINS + bin], __popc(peers));
+                        const unsigned act = __activemask();
+                        const int leader = __ffs(act) - 1;
+                        const int lead_bin = __shfl_sync(act, bin, leader);
+                        if (__all_sync(act, bin == lead_bin)) {
+                            if (lane == leader) atomicAdd(&qhist[j * Q_BINS + bin], __popc(act));
+                        } else {
+                            atomicAdd(&qhist[j * Q_BINS + bin], 1);
+                        }
                     }
                 }
             }
