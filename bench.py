@@ -591,7 +591,7 @@ def run_ff(ctx, args, name, steps, warmup, with_cpu=True, with_other=True):
         }
         if other:
             line["other_precisions"] = other
-        if with_cpu:
+        if with_cpu and ctx.world == 1:          # rank 0 at N = 1 only (the contract); --impl reference is the N-way CPU arm
             line["cpu_baseline"] = cpu_baseline_one_core(name, args.cpu_seconds)
     srv.close()
     del srv, fleet, x_dev, x_host, res, chk
@@ -695,7 +695,7 @@ def run_lstm(ctx, args, name, steps, warmup, with_cpu=True):
                              "kernel": "lstm_persist_tc_kernel" if prec == "bf16" else "lstm_step_kernel",
                              "algorithmic_flops_per_window": fpw},
                 "shards_rank0": mine, "clocks": clocks}
-        if with_cpu:
+        if with_cpu and ctx.world == 1:          # rank 0 at N = 1 only (the contract); --impl reference is the N-way CPU arm
             line["cpu_baseline"] = cpu_baseline_one_core(name, args.cpu_seconds)
     del fleet, x_dev, x_host
     torch.cuda.empty_cache()
@@ -773,10 +773,47 @@ def run_build(ctx, args, name, steps, warmup, with_cpu=True):
                                                       for k in ("ff", "lstm")},
                                    "slowest_buckets": sorted(((b[0], b[1], round(b[3], 2)) for b in builder.bucket_log), key=lambda b: -b[2])[:6]},
                 "rows_per_machine": rows, "aggregate_thresholds_first4": thr, "clocks": clocks}
-        if with_cpu:
+        if with_cpu and ctx.world == 1:          # rank 0 at N = 1 only (the contract); --impl reference is the N-way CPU arm
             line["cpu_baseline"] = cpu_baseline_one_core(name, args.cpu_seconds)
-            line["cpu_baseline"]["unit"] = "rows/s"
+            if "cpu_baseline" in line:
+                line["cpu_baseline"]["unit"] = "rows/s"
     return line
+
+
+def run_request(ctx, rounds=100):
+    """
+    The reference's own benchmark shape (benchmarks/test_ml_server.py:21-44: 100 rounds of one POST of 100 rows x 4
+    tags to /anomaly/prediction): a fitted Machine, `model.anomaly(X, y, frequency)` host frame in -> host frame out
+    (server/blueprints/anomaly.py:50) plus the response body in both wire formats (server/utils.py:47-142), per request.
+    """
+    import pandas as pd
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import MinMaxScaler
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_b200.machine.model.models import KerasAutoEncoder
+    from gordo_b200.server import utils as server_utils
+    rng = np.random.default_rng(SEED0)
+    tags = [f"tag-{i}" for i in range(4)]
+    Xtrain = pd.DataFrame(rng.random((1000, 4)), columns=tags, index=pd.date_range("2019-01-01", periods=1000, freq="10min", tz="UTC"))
+    det = DiffBasedAnomalyDetector(base_estimator=Pipeline([("s", MinMaxScaler()), ("m", KerasAutoEncoder(kind="feedforward_hourglass"))]))
+    det.cross_validate(X=Xtrain, y=Xtrain)
+    det.fit(Xtrain, Xtrain)
+    X = Xtrain.iloc[:100]
+    freq = pd.Timedelta("10min")
+    out = {}
+    for name, fn in (("anomaly_frame", lambda: det.anomaly(X, X, frequency=freq)),
+                     ("anomaly_parquet", lambda: server_utils.dataframe_into_parquet_bytes(det.anomaly(X, X, frequency=freq))),
+                     ("anomaly_json_dict", lambda: server_utils.dataframe_to_dict(det.anomaly(X, X, frequency=freq)))):
+        for _ in range(10):
+            fn()
+        ctx.torch.cuda.synchronize()
+        ts = []
+        for _ in range(rounds):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        ts = np.array(ts) * 1e3
+        out[name] = {"ms_median": float(np.median(ts)), "ms_p95": float(np.percentile(ts, 95))}
+    out["shape"] = "100 rows x 4 tags, 100 rounds (benchmarks/test_ml_server.py:21-44); the reference documents 160-190 ms per request (docs/general/endpoints.rst:223)"
+    return out
 
 
 def run_ours(args):
@@ -817,6 +854,11 @@ def run_ours(args):
                 except Exception:
                     pass
             elapsed += time.perf_counter() - t_x
+        if ctx.rank == 0 and elapsed <= args.extras_budget:
+            try:
+                mine["request"] = run_request(ctx)
+            except Exception as e:
+                mine["request"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         ctx.collective = True
         gathered = [mine]
         if ctx.world > 1:
@@ -840,6 +882,8 @@ def run_ours(args):
                 e["timing"] = "per-rank CUDA events, no barrier inside the side measurement; max over ranks"
                 e.pop("_raw", None)
                 extras[other] = e
+            if "request" in gathered[0]:
+                extras["request_latency"] = gathered[0]["request"]
     if ctx.rank == 0:
         line.pop("_raw", None)
         if extras:

@@ -231,3 +231,90 @@ def test_fleet_builder_bucketing_rules():
     lstm = key(machine(est="KerasLSTMAutoEncoder", est_kw={"lookback_window": 4}))
     assert lstm is not None and lstm[0] == "lstm"
     assert key(machine(detector="DiffBasedKFCVAnomalyDetector", est="KerasLSTMAutoEncoder", est_kw={"lookback_window": 4})) is None
+
+
+# ----------------------------------------------------------------------------- round 2 host logic (no device needed)
+def test_job_seeds_are_the_per_machine_path_draws():
+    """FleetBuild seeds fit job i of a Machine with the i-th draw the per-Machine path makes after np.random.seed(seed)."""
+    from gordo_b200.builder import job_seeds
+    np.random.seed(7)
+    want = [int(np.random.randint(0, 2 ** 31 - 1)) for _ in range(4)]
+    assert job_seeds(7, 4) == want and job_seeds(7, 2) == want[:2] and job_seeds(8, 4) != want
+
+
+def test_redirect_definition_and_build_metadata_layout():
+    from gordo_b200.builder import build_metadata_dict, redirect_definition
+    d = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {
+        "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler",
+            {"gordo.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass"}}]}}}}
+    r = redirect_definition(d)
+    assert list(r) == ["gordo_b200.machine.model.anomaly.diff.DiffBasedAnomalyDetector"]
+    steps = r[list(r)[0]]["base_estimator"]["sklearn.pipeline.Pipeline"]["steps"]
+    assert steps[0] == "sklearn.preprocessing.MinMaxScaler" and list(steps[1]) == ["gordo_b200.machine.model.models.KerasAutoEncoder"]
+    assert "gordo.machine" in list(d)[0]                           # the input is not modified
+    assert redirect_definition(d, enable=False) is d
+    bm = build_metadata_dict({"model_offset": 3, "model_training_duration_sec": 1.5, "cv_duration_sec": 2.5,
+                              "cross_validation": {"scores": {"r2-score": {"fold-mean": 0.5}}, "splits": {"fold-1-n-train": 10}},
+                              "model": {"history": {"loss": [1.0]}}})
+    # gordo/machine/metadata/metadata.py:17-56
+    assert set(bm) == {"model", "dataset"} and bm["model"]["model_offset"] == 3
+    assert set(bm["model"]) == {"model_offset", "model_creation_date", "model_builder_version", "model_training_duration_sec",
+                                "cross_validation", "model_meta"}
+    assert bm["model"]["cross_validation"] == {"cv_duration_sec": 2.5, "scores": {"r2-score": {"fold-mean": 0.5}},
+                                               "splits": {"fold-1-n-train": 10}}
+    assert set(bm["dataset"]) == {"query_duration_sec", "dataset_meta"}
+
+
+def test_extract_model_metadata_digs_through_pipelines_like_the_reference():
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import MinMaxScaler
+    from gordo_b200.builder import extract_model_metadata
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    from gordo_b200.machine.model.models import History, KerasAutoEncoder
+    est = KerasAutoEncoder(kind="feedforward_hourglass")
+    est._history = History({"loss": [0.5], "accuracy": [0.1]}, {"epochs": 1}, [0])
+    det = DiffBasedAnomalyDetector(base_estimator=Pipeline([("s", MinMaxScaler()), ("m", est)]))
+    det.aggregate_threshold_ = 0.25
+    meta = extract_model_metadata(det)                             # build_model.py:518-570
+    assert meta["history"]["loss"] == [0.5] and meta["aggregate-threshold"] == 0.25
+    assert extract_model_metadata(Pipeline([("s", MinMaxScaler()), ("m", est)]))["history"]["params"] == {"epochs": 1}
+
+
+def test_hostbind_cpu_slicing_and_quota(monkeypatch, tmp_path):
+    from gordo_b200 import hostbind
+    assert hostbind._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    # 8 cores with hyper-thread siblings c, c + 8: four ranks get two cores (+ siblings) each, nothing shared
+    monkeypatch.setattr(hostbind, "_siblings", lambda c: [c % 8, c % 8 + 8])
+    cpus = list(range(16))
+    parts = [hostbind.slice_cpus(cpus, r, 4) for r in range(4)]
+    assert parts[0] == [0, 1, 8, 9] and parts[3] == [6, 7, 14, 15]
+    assert sorted(c for p in parts for c in p) == cpus
+    assert hostbind.slice_cpus(cpus, 0, 1) == cpus
+    monkeypatch.setattr(hostbind, "cpu_quota", lambda: 6.0)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    assert hostbind.effective_cpus() <= 3                          # the quota is shared by the ranks of the box
+    monkeypatch.setattr(hostbind, "cpu_quota", lambda: None)
+    assert hostbind.effective_cpus() >= 1
+
+
+def test_fleet_anomaly_result_response_methods_without_a_device():
+    """FleetAnomalyResult is host-only: frame / parquet / dict of one Machine from the column buffers."""
+    import torch
+    from gordo_b200.serving import FleetAnomalyResult
+    from gordo_b200.server import utils as su
+    rng = np.random.default_rng(0)
+    R, T = 30, 3
+    cols = {k: torch.from_numpy(rng.random((R, T)).astype(np.float32)) for k in
+            ("model-output", "tag-anomaly-scaled", "tag-anomaly-unscaled", "anomaly-confidence")}
+    cols.update({k: torch.from_numpy(rng.random(R).astype(np.float32)) for k in
+                 ("total-anomaly-scaled", "total-anomaly-unscaled", "total-anomaly-confidence")})
+    x = torch.from_numpy(rng.random((R, T)).astype(np.float32))
+    res = FleetAnomalyResult(cols, np.array([0, 10, 30]), x, tags=[["a", "b", "c"], ["d", "e", "f"]])
+    idx = pd.date_range("2021-01-01", periods=20, freq="10min", tz="UTC")
+    frame = res.frame(1, idx, pd.Timedelta("10min"))
+    assert len(frame) == 20 and ("anomaly-confidence", "e") in frame.columns and frame.columns[0] == ("start", "")
+    np.testing.assert_allclose(frame["model-output"].to_numpy(), cols["model-output"][10:30].numpy())
+    back = su.dataframe_from_parquet_bytes(res.parquet_bytes(1, idx, pd.Timedelta("10min")))
+    pd.testing.assert_frame_equal(back, frame, check_freq=False)
+    d = res.to_dict(0)
+    assert set(d["model-input"]) == {"a", "b", "c"} and len(d["total-anomaly-scaled"]["total-anomaly-scaled"]) == 10
