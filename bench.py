@@ -803,7 +803,10 @@ def run_request(ctx, rounds=100):
     out = {}
     for name, fn in (("anomaly_frame", lambda: det.anomaly(X, X, frequency=freq)),
                      ("anomaly_parquet", lambda: server_utils.dataframe_into_parquet_bytes(det.anomaly(X, X, frequency=freq))),
-                     ("anomaly_json_dict", lambda: server_utils.dataframe_to_dict(det.anomaly(X, X, frequency=freq)))):
+                     ("anomaly_json_dict", lambda: server_utils.dataframe_to_dict(det.anomaly(X, X, frequency=freq))),
+                     # the same response bodies straight from the column groups (no DataFrame pivot)
+                     ("response_parquet_from_columns", lambda: det.anomaly_response(X, X, frequency=freq, fmt="parquet")),
+                     ("response_json_from_columns", lambda: det.anomaly_response(X, X, frequency=freq, fmt="json"))):
         for _ in range(10):
             fn()
         ctx.torch.cuda.synchronize()

@@ -353,6 +353,29 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
         ``total-anomaly-scaled``, ``tag-anomaly-unscaled``, ``total-anomaly-unscaled``, optional
         ``smooth-*``, ``anomaly-confidence``, ``total-anomaly-confidence`` (diff.py:310-458).
         """
+        return model_utils.assemble_frame(self.anomaly_groups(X, y), getattr(X, "index", None), frequency)
+
+    def anomaly_response(self, X: pd.DataFrame, y: pd.DataFrame, frequency: Optional[timedelta] = None,
+                         fmt: str = "parquet", all_columns: bool = False):
+        """
+        The body of the server's anomaly response (gordo/server/blueprints/anomaly.py:57-72) straight from the column
+        groups, without the DataFrame pivot: ``fmt="parquet"`` -> the bytes of ``dataframe_into_parquet_bytes(frame)``,
+        ``fmt="json"`` -> the dict of ``dataframe_to_dict(frame)`` (the ``data`` member).  ``all_columns=False`` drops the
+        smooth-* groups as the view does (anomaly.py:17-22, 57-62).
+        """
+        from gordo_b200.server import utils as server_utils
+        groups = self.anomaly_groups(X, y)
+        if not all_columns:
+            groups = [g for g in groups if not g[0].startswith("smooth-")]
+        index = getattr(X, "index", None)
+        if fmt == "parquet":
+            return server_utils.columns_into_parquet_bytes(groups, index, frequency)
+        if fmt == "json":
+            return server_utils.columns_to_dict(groups, index, frequency)
+        raise ValueError("fmt must be 'parquet' or 'json'")
+
+    def anomaly_groups(self, X: pd.DataFrame, y: pd.DataFrame):
+        """The frame's column groups [(top-level name, values, second-level names)], in the reference's order."""
         if not hasattr(X, "values"):
             raise ValueError("Unable to find X.values property")
         has_feat = self.__dict__.get("feature_thresholds_") is not None
@@ -408,7 +431,7 @@ class DiffBasedAnomalyDetector(AnomalyDetectorBase):
             groups.append(("anomaly-confidence", conf, out_names))
         if tconf is not None:
             groups.append(("total-anomaly-confidence", tconf, None))
-        return model_utils.assemble_frame(groups, getattr(X, "index", None), frequency)
+        return groups
 
 
 def _n_in(est):

@@ -18,9 +18,10 @@ Gen5 x16 link moves 1e5 x 50 float32 rows in 0.4 ms).  So the work is split by w
            written by gb200_host_expand_columns straight into the response buffers while the next
            chunk is in flight.
 
-``plan`` = how many of those three matrices the host derives (0..3).  One GPU alone is PCIe-bound
-and wants 3; eight ranks sharing two sockets are host-DRAM-bound and want fewer -- ``plan="auto"``
-times each option on the first call (all ranks do so together) and keeps the fastest.
+``plan`` = how many of those three matrices the host derives (0..3; x.5 = alternate chunks use x and x+1, which
+splits the load between the PCIe link and the host threads more finely).  One GPU alone is PCIe-bound and wants
+about 3; eight ranks sharing two sockets are host-DRAM-bound and want 0 -- ``plan="auto"`` times the options on
+the first call (all ranks do so together) and keeps the fastest.
 
 Chunks of Machines flow through three streams (H2D, kernel, D2H) and three device buffer sets, so
 both PCIe directions and the kernel overlap; a host worker thread expands chunk c while c+1 is on the wire.
@@ -155,9 +156,9 @@ class FleetAnomalyServer:
         self._stage: Optional[torch.Tensor] = None
         self.plan_timings: Dict[int, float] = {}
         if plan == "auto":
-            self.plan: Optional[int] = None
+            self.plan: Optional[float] = None
         else:
-            self.plan = max(0, min(int(plan), len(self.derivable)))
+            self.plan = self._clamp_plan(float(plan))
 
     # ------------------------------------------------------------------ construction from fitted models
     @classmethod
@@ -272,21 +273,41 @@ class FleetAnomalyServer:
             self._run(x_host, x_host, self.plan)
             return FleetAnomalyResult(self.host_out, self.row_off, x_host, self.tags)
 
+    def _clamp_plan(self, p: float) -> float:
+        p = max(0.0, min(float(p), float(len(self.derivable))))
+        return round(p * 2) / 2.0                     # whole or half steps
+
+    def _chunk_k(self, plan: float, ci: int) -> int:
+        """Matrices chunk ``ci`` derives on the host under ``plan`` (x.5: odd chunks take one more)."""
+        k = int(plan)
+        if plan - k >= 0.5 and (ci & 1):
+            k += 1
+        return min(k, len(self.derivable))
+
+    def _time_plan(self, x_host, p: float) -> float:
+        self._run(x_host, x_host, p)                # warm
+        t0 = time.perf_counter()
+        self._run(x_host, x_host, p)
+        dt = time.perf_counter() - t0
+        self.plan_timings[p] = dt
+        return dt
+
     def _calibrate(self, x_host):
-        best, best_t = 0, None
+        # whole plans first (most host derivation first: ties go to less PCIe), then the half steps next to the best
+        best, best_t = 0.0, None
         for k in range(len(self.derivable), -1, -1):
-            self._run(x_host, x_host, k)            # warm
-            t0 = time.perf_counter()
-            self._run(x_host, x_host, k)
-            dt = time.perf_counter() - t0
-            self.plan_timings[k] = dt
-            if best_t is None or dt < best_t * 0.97:     # prefer more host derivation on ties (less PCIe)
-                best, best_t = k, dt
+            dt = self._time_plan(x_host, float(k))
+            if best_t is None or dt < best_t * 0.97:
+                best, best_t = float(k), dt
+        if len(self.chunks) >= 4:
+            for p in (best + 0.5, best - 0.5):
+                if 0.0 <= p <= len(self.derivable):
+                    dt = self._time_plan(x_host, p)
+                    if dt < best_t * 0.97:
+                        best, best_t = p, dt
         self.plan = best
 
-    def _run(self, x_host, y_host, k: int):
-        derive = tuple(self.derivable[:k])
-        dev_cols = tuple(c for c in self.matrices if c not in derive) + tuple(self.vectors)
+    def _run(self, x_host, y_host, plan: float):
         cur = torch.cuda.current_stream()
         start = torch.cuda.Event(); start.record(cur)
         for s in (self.s_h2d, self.s_k, self.s_d2h):
@@ -298,6 +319,8 @@ class FleetAnomalyServer:
             slot = ci % self.n_slots
             r0, r1 = int(self.row_off[a]), int(self.row_off[c])
             n = r1 - r0
+            derive = tuple(self.derivable[:self._chunk_k(plan, ci)])
+            dev_cols = tuple(cn for cn in self.matrices if cn not in derive) + tuple(self.vectors)
             dx = self.dx[slot][:n]
             with torch.cuda.stream(self.s_h2d):
                 if ci >= self.n_slots:
@@ -325,19 +348,28 @@ class FleetAnomalyServer:
             raise errs[0]
 
     # ------------------------------------------------------------------ accounting
-    def bytes_per_call(self, k: Optional[int] = None) -> Dict[str, int]:
-        k = self.plan if k is None else k
-        k = len(self.derivable) if k is None else k
-        n_mat_dev = len(self.matrices) - k
-        return {"h2d": self.rows * self.T * 4,
-                "d2h": self.rows * (n_mat_dev * self.T + len(self.vectors)) * 4,
-                "host_derived_bytes": self.rows * k * self.T * 4}
+    def bytes_per_call(self, plan: Optional[float] = None) -> Dict[str, int]:
+        plan = self.plan if plan is None else plan
+        plan = float(len(self.derivable)) if plan is None else float(plan)
+        d2h = derived = 0
+        for ci, (a, c) in enumerate(self.chunks):
+            rows = int(self.row_off[c] - self.row_off[a])
+            k = self._chunk_k(plan, ci)
+            d2h += rows * ((len(self.matrices) - k) * self.T + len(self.vectors)) * 4
+            derived += rows * k * self.T * 4
+        return {"h2d": self.rows * self.T * 4, "d2h": d2h, "host_derived_bytes": derived}
 
     def kernel_launches_per_call(self) -> int:
         return len(self.chunks)
 
     def close(self):
+        """Stop the host worker thread and wait for it (a thread still inside the library at interpreter shutdown aborts the process)."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
         self._jobs.put(None)
+        if self._worker.is_alive() and threading.current_thread() is not self._worker:
+            self._worker.join(timeout=10)
 
     def __del__(self):
         try:

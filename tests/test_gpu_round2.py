@@ -195,11 +195,11 @@ def test_fleet_anomaly_server_plans_match_per_machine_anomaly():
     want = [mdl.anomaly(pd.DataFrame(X, columns=mc.X.columns), pd.DataFrame(X, columns=mc.X.columns))
             for mdl, mc, X in zip(models, mcs, Xs)]
     assert FleetAnomalyServer.group_by_topology(models).keys().__len__() == 1
-    for plan in (0, 1, 2, 3, "auto"):
+    for plan in (0, 1, 1.5, 2, 3, "auto"):
         srv = FleetAnomalyServer.from_models(models, rows, precision="f32", n_chunks=3, plan=plan, n_threads=3)
         res = srv.anomaly(Xs)                                    # list of per-Machine host arrays (staged to pinned memory)
         if plan == "auto":
-            assert srv.plan in (0, 1, 2, 3) and len(srv.plan_timings) == 4
+            assert 0 <= srv.plan <= 3 and len(srv.plan_timings) >= 4
         for m in range(len(rows)):
             c = res.machine(m)
             for name in ("model-output", "tag-anomaly-scaled", "tag-anomaly-unscaled", "anomaly-confidence"):
@@ -211,7 +211,11 @@ def test_fleet_anomaly_server_plans_match_per_machine_anomaly():
         np.testing.assert_allclose(frame["anomaly-confidence"].to_numpy(), want[1]["anomaly-confidence"].to_numpy(), rtol=2e-5, atol=2e-6)
         by = srv.bytes_per_call()
         k = srv.plan
-        assert by["d2h"] == sum(rows) * ((4 - k) * T + 3) * 4 and by["h2d"] == sum(rows) * T * 4
+        if float(k).is_integer():
+            assert by["d2h"] == sum(rows) * ((4 - int(k)) * T + 3) * 4
+        else:       # x.5: odd chunks derive one matrix more than even ones
+            assert sum(rows) * ((4 - int(k) - 1) * T + 3) * 4 < by["d2h"] < sum(rows) * ((4 - int(k)) * T + 3) * 4
+        assert by["h2d"] == sum(rows) * T * 4 and by["d2h"] + by["host_derived_bytes"] == sum(rows) * (4 * T + 3) * 4
         srv.close()
     # pinned input: zero-copy path, bf16 tensor-core scorer, device columns == host columns
     big = FleetAnomalyServer.from_models(models, rows, precision="bf16", n_chunks=2, plan=3)
@@ -394,3 +398,26 @@ def test_ff_fit_tensor_core_variant_matches_the_default_kernel(T, batch, monkeyp
     np.testing.assert_allclose(res["mma"][1], res["simt"][1], rtol=2e-4)
     np.testing.assert_allclose(res["mma"][2], res["simt"][2], atol=2.0 / min(rows))
     assert float(np.abs(res["mma"][0] - init.cpu().numpy()).max()) > 1e-3
+
+
+def test_anomaly_response_bodies_equal_the_frame_codecs():
+    """model.anomaly_response (column groups -> parquet bytes / JSON dict) == the server codecs applied to model.anomaly's
+    frame (gordo/server/blueprints/anomaly.py:57-72), incl. the smooth-* columns the view drops by default."""
+    import json
+    from gordo_b200.builder import FleetBuild
+    from gordo_b200.server import utils as su
+    from gordo_b200.builder import FleetMachine
+    X = pd.DataFrame(np.random.default_rng(3).random((400, 5)).astype(np.float32), columns=[f"tag {j}" for j in range(5)],
+                     index=pd.date_range("2020-01-01", periods=400, freq="10min", tz="UTC"))
+    model = FleetBuild([FleetMachine("m", X, model=_defn(det_kw={"window": 12}), evaluation={"seed": 1})]).build()[0][0]
+    req = X.iloc[:100]
+    freq = pd.Timedelta("10min")
+    frame = model.anomaly(req, req, frequency=freq)
+    assert any(c[0].startswith("smooth-") for c in frame.columns)
+    dropped = frame.drop(columns=[c for c in frame.columns if c[0].startswith("smooth-")])
+    got = su.dataframe_from_parquet_bytes(model.anomaly_response(req, req, frequency=freq, fmt="parquet"))
+    pd.testing.assert_frame_equal(got, su.dataframe_from_parquet_bytes(su.dataframe_into_parquet_bytes(dropped)))
+    full = su.dataframe_from_parquet_bytes(model.anomaly_response(req, req, frequency=freq, fmt="parquet", all_columns=True))
+    pd.testing.assert_frame_equal(full, su.dataframe_from_parquet_bytes(su.dataframe_into_parquet_bytes(frame)))
+    d = model.anomaly_response(req, req, frequency=freq, fmt="json")
+    assert json.dumps(d, sort_keys=True, default=str) == json.dumps(su.dataframe_to_dict(dropped), sort_keys=True, default=str)
