@@ -109,9 +109,7 @@ class FleetAnomalyServer:
         self.M = fleet.M
         dev = fleet.device
         T, To = fleet.topo.n_in, fleet.topo.n_out
-        if T != To:
-            raise ValueError("FleetAnomalyServer serves autoencoders (n_features == n_features_out)")
-        self.T = T
+        self.T, self.To = T, To
         self.has_feat, self.has_agg = fleet.feat_thr is not None, fleet.agg_thr is not None
         self.matrices = [c for c in MATRIX_COLUMNS if c != "anomaly-confidence" or self.has_feat]
         self.vectors = [c for c in VECTOR_COLUMNS if c != "total-anomaly-confidence" or self.has_agg]
@@ -127,7 +125,8 @@ class FleetAnomalyServer:
         self.n_slots = min(3, len(self.chunks))
         self.s_h2d, self.s_k, self.s_d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
         self.dx = [torch.empty((max_rows, T), dtype=torch.float32, device=dev) for _ in range(self.n_slots)]
-        self.dy = None
+        self.dy = None                  # device targets, allocated on the first call that passes y != X
+        self._max_rows = max_rows
         self.dout = [{**{c: torch.empty((max_rows, To), dtype=torch.float32, device=dev) for c in self.matrices},
                       **{c: torch.empty((max_rows,), dtype=torch.float32, device=dev) for c in self.vectors}}
                      for _ in range(self.n_slots)]
@@ -154,6 +153,7 @@ class FleetAnomalyServer:
         self._worker = threading.Thread(target=self._host_worker, daemon=True)
         self._worker.start()
         self._stage: Optional[torch.Tensor] = None
+        self._stage_y: Optional[torch.Tensor] = None
         self.plan_timings: Dict[int, float] = {}
         if plan == "auto":
             self.plan: Optional[float] = None
@@ -219,7 +219,7 @@ class FleetAnomalyServer:
                     ro = np.ascontiguousarray(self.row_off[a:c + 1])
                     hp = lambda name: C.c_void_p(self.host_out[name][r0:r1].data_ptr()) if name in derive else None
                     rc = lib.gb200_host_expand_columns(
-                        c - a, ro.ctypes.data_as(C.c_void_p), self.T,
+                        c - a, ro.ctypes.data_as(C.c_void_p), self.To,
                         C.c_void_p(self.host_out["model-output"][r0:r1].data_ptr()), C.c_void_p(y_host[r0:r1].data_ptr()),
                         self.h_err_scale[a:c].ctypes.data_as(C.c_void_p),
                         None if self.h_feat_thr is None else self.h_feat_thr[a:c].ctypes.data_as(C.c_void_p),
@@ -232,30 +232,31 @@ class FleetAnomalyServer:
             finally:
                 self._jobs.task_done()
 
-    def _as_pinned(self, X) -> torch.Tensor:
-        """The request's samples as ONE pinned float32 [rows, T] matrix (no copy when it already is one)."""
+    def _as_pinned(self, X, width: Optional[int] = None, which: str = "_stage") -> torch.Tensor:
+        """The request's samples (or targets) as ONE pinned float32 [rows, width] matrix (no copy when it already is one)."""
+        W = self.T if width is None else width
         if isinstance(X, torch.Tensor):
-            if X.dtype == torch.float32 and X.is_pinned() and X.is_contiguous() and tuple(X.shape) == (self.rows, self.T):
+            if X.dtype == torch.float32 and X.is_pinned() and X.is_contiguous() and tuple(X.shape) == (self.rows, W):
                 return X
             X = X.numpy()
-        if self._stage is None:
-            self._stage = torch.empty((self.rows, self.T), dtype=torch.float32, pin_memory=True)
-        st = self._stage.numpy()
+        if getattr(self, which) is None:
+            setattr(self, which, torch.empty((self.rows, W), dtype=torch.float32, pin_memory=True))
+        st = getattr(self, which).numpy()
         if isinstance(X, (list, tuple)):
             if len(X) != self.M:
                 raise ValueError(f"expected {self.M} Machines, got {len(X)}")
             for m, xm in enumerate(X):
                 a, b = int(self.row_off[m]), int(self.row_off[m + 1])
                 xv = np.asarray(getattr(xm, "values", xm))
-                if xv.shape != (b - a, self.T):
-                    raise ValueError(f"Machine {m}: expected {(b - a, self.T)}, got {xv.shape}")
+                if xv.shape != (b - a, W):
+                    raise ValueError(f"Machine {m}: expected {(b - a, W)}, got {xv.shape}")
                 st[a:b] = xv
         else:
             xv = np.asarray(getattr(X, "values", X))
-            if xv.shape != (self.rows, self.T):
-                raise ValueError(f"expected {(self.rows, self.T)}, got {xv.shape}")
+            if xv.shape != (self.rows, W):
+                raise ValueError(f"expected {(self.rows, W)}, got {xv.shape}")
             st[:] = xv
-        return self._stage
+        return getattr(self, which)
 
     # ------------------------------------------------------------------ the call
     def anomaly(self, X, y=None) -> FleetAnomalyResult:
@@ -266,11 +267,18 @@ class FleetAnomalyServer:
         """
         with self._lock:
             x_host = self._as_pinned(X)
-            if y is not None and y is not X:
-                raise NotImplementedError("FleetAnomalyServer: separate targets are served per Machine (model.anomaly)")
+            if y is None or y is X:
+                if self.T != self.To:
+                    raise ValueError("y may default to X only when n_features == n_features_out")
+                y_host = x_host
+            else:                                   # separate targets (model.anomaly(X, y): diff.py:336-344)
+                y_host = self._as_pinned(y, self.To, "_stage_y")
+                if self.dy is None:
+                    self.dy = [torch.empty((self._max_rows, self.To), dtype=torch.float32, device=self.fleet.device)
+                               for _ in range(self.n_slots)]
             if self.plan is None:
-                self._calibrate(x_host)
-            self._run(x_host, x_host, self.plan)
+                self._calibrate(x_host, y_host)
+            self._run(x_host, y_host, self.plan)
             return FleetAnomalyResult(self.host_out, self.row_off, x_host, self.tags)
 
     def _clamp_plan(self, p: float) -> float:
@@ -284,25 +292,25 @@ class FleetAnomalyServer:
             k += 1
         return min(k, len(self.derivable))
 
-    def _time_plan(self, x_host, p: float) -> float:
-        self._run(x_host, x_host, p)                # warm
+    def _time_plan(self, x_host, y_host, p: float) -> float:
+        self._run(x_host, y_host, p)                # warm
         t0 = time.perf_counter()
-        self._run(x_host, x_host, p)
+        self._run(x_host, y_host, p)
         dt = time.perf_counter() - t0
         self.plan_timings[p] = dt
         return dt
 
-    def _calibrate(self, x_host):
+    def _calibrate(self, x_host, y_host):
         # whole plans first (most host derivation first: ties go to less PCIe), then the half steps next to the best
         best, best_t = 0.0, None
         for k in range(len(self.derivable), -1, -1):
-            dt = self._time_plan(x_host, float(k))
+            dt = self._time_plan(x_host, y_host, float(k))
             if best_t is None or dt < best_t * 0.97:
                 best, best_t = float(k), dt
         if len(self.chunks) >= 4:
             for p in (best + 0.5, best - 0.5):
                 if 0.0 <= p <= len(self.derivable):
-                    dt = self._time_plan(x_host, p)
+                    dt = self._time_plan(x_host, y_host, p)
                     if dt < best_t * 0.97:
                         best, best_t = p, dt
         self.plan = best
@@ -326,13 +334,17 @@ class FleetAnomalyServer:
                 if ci >= self.n_slots:
                     self.s_h2d.wait_event(ev_k[ci - self.n_slots])        # the slot's previous kernel has read dx
                 dx.copy_(x_host[r0:r1], non_blocking=True)
+                dy = None
+                if y_host is not x_host:
+                    dy = self.dy[slot][:n]
+                    dy.copy_(y_host[r0:r1], non_blocking=True)
                 e_h = torch.cuda.Event(); e_h.record(self.s_h2d)
             out = {cname: self.dout[slot][cname][:n] for cname in dev_cols}
             with torch.cuda.stream(self.s_k):
                 self.s_k.wait_event(e_h)
                 if ci >= self.n_slots:
                     self.s_k.wait_event(ev_d[ci - self.n_slots])          # the slot's previous results left the device
-                view.score(vs, dx, precision=self.precision, columns=dev_cols, out=out)
+                view.score(vs, dx, dy, precision=self.precision, columns=dev_cols, out=out)
                 ev_k[ci] = torch.cuda.Event(); ev_k[ci].record(self.s_k)
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(ev_k[ci])
@@ -355,9 +367,10 @@ class FleetAnomalyServer:
         for ci, (a, c) in enumerate(self.chunks):
             rows = int(self.row_off[c] - self.row_off[a])
             k = self._chunk_k(plan, ci)
-            d2h += rows * ((len(self.matrices) - k) * self.T + len(self.vectors)) * 4
-            derived += rows * k * self.T * 4
-        return {"h2d": self.rows * self.T * 4, "d2h": d2h, "host_derived_bytes": derived}
+            d2h += rows * ((len(self.matrices) - k) * self.To + len(self.vectors)) * 4
+            derived += rows * k * self.To * 4
+        h2d = self.rows * self.T * 4 + (self.rows * self.To * 4 if self.dy is not None else 0)
+        return {"h2d": h2d, "d2h": d2h, "host_derived_bytes": derived}
 
     def kernel_launches_per_call(self) -> int:
         return len(self.chunks)

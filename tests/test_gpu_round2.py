@@ -421,3 +421,23 @@ def test_anomaly_response_bodies_equal_the_frame_codecs():
     pd.testing.assert_frame_equal(full, su.dataframe_from_parquet_bytes(su.dataframe_into_parquet_bytes(frame)))
     d = model.anomaly_response(req, req, frequency=freq, fmt="json")
     assert json.dumps(d, sort_keys=True, default=str) == json.dumps(su.dataframe_to_dict(dropped), sort_keys=True, default=str)
+
+
+def test_fleet_anomaly_server_with_separate_targets():
+    """model.anomaly(X, y) with y != X (target tags differ from the input tags, T_out != T): host targets are staged and
+    copied per chunk, the host expansion uses them; every plan equals the device-resident columns."""
+    from gordo_b200.serving import FleetAnomalyServer
+    case = make_fleet_case(seed=7, row_counts=[400, 333, 129], T=12, T_out=4)
+    fl, sched, X, Y = fleet_from_case(case)
+    want = fl.score(sched, X, Y, precision="f32")
+    Xh = [x for x in case["X"]]; Yh = [y for y in case["Y"]]
+    for plan in (0, 2, 3):
+        srv = FleetAnomalyServer(fl, case["row_counts"], precision="f32", n_chunks=2, plan=plan, n_threads=2)
+        res = srv.anomaly(Xh, Yh)
+        for k, w in want.items():
+            np.testing.assert_allclose(res.columns[k].numpy(), w.cpu().numpy(), rtol=1e-5, atol=1e-6, err_msg=f"plan {plan} {k}")
+        assert res.machine(1)["model-input"].shape == (333, 12) and res.machine(1)["model-output"].shape == (333, 4)
+        assert srv.bytes_per_call()["h2d"] == sum(case["row_counts"]) * (12 + 4) * 4
+        with pytest.raises(ValueError):
+            srv.anomaly(Xh)                                       # y cannot default to X when the widths differ
+        srv.close()
