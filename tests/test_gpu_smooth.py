@@ -151,6 +151,12 @@ def test_kfcv_detector_matches_real_reference_golden(ci):
                                    rtol=5e-6, atol=1e-9, equal_nan=True)
 
 
+# The offset stand-in estimator (an LSTM-like model whose output is shorter than its input) inherits sklearn's
+# RegressorMixin.score = r2_score(y, predict(X)): with offset > 0 the lengths differ, sklearn's cross_validate catches the
+# ValueError, warns "Scoring failed" and records NaN -- in the reference run that produced the golden as well
+# (tests/golden/make_golden.py uses the same stand-in; the default `score` is never read by diff.py:176-266).  Expected,
+# hence filtered here rather than left to look like an accident.
+@pytest.mark.filterwarnings("ignore:Scoring failed:UserWarning")
 @pytest.mark.parametrize("ci", [3, 4, 5])
 def test_smooth_columns_match_real_reference_golden(ci):
     """smooth-* columns of DiffBasedAnomalyDetector.anomaly (window 12: smm / sma / ewma) vs the real reference."""
