@@ -74,14 +74,16 @@ def _load_params(params: dict, redirect_gordo: bool):
 def into_definition(obj) -> Any:
     """Inverse of from_definition for the objects this package builds."""
     path = f"{obj.__class__.__module__}.{obj.__class__.__name__}"
-    if hasattr(obj, "into_definition"):
+    # looked up on the class: the detectors are transparent into base_estimator (diff.py:78-86), so an instance
+    # lookup would find a bare KerasAutoEncoder's hook and describe the detector with the estimator's parameters
+    if hasattr(type(obj), "into_definition"):
         return {path: obj.into_definition()}
     params = obj.get_params(deep=False) if hasattr(obj, "get_params") else {}
     out = {}
     for k, v in params.items():
         if k == "steps":
             out[k] = [into_definition(s[1]) for s in v]
-        elif hasattr(v, "get_params") or hasattr(v, "into_definition"):
+        elif hasattr(type(v), "get_params") or hasattr(type(v), "into_definition"):
             out[k] = into_definition(v)
         else:
             out[k] = v

@@ -172,6 +172,10 @@ class FleetAnomalyServer:
         plans = [m._fused_plan() for m in models]
         if any(p is None for p in plans):
             raise ValueError("every model must be the standard fused composition (see DiffBasedAnomalyDetector._fused_plan)")
+        from gordo_b200.machine.model.models import KerasLSTMBaseEstimator
+        if any(isinstance(p[1], KerasLSTMBaseEstimator) for p in plans):
+            raise ValueError("FleetAnomalyServer batches feed-forward Machines; LSTM Machines are served per Machine "
+                             "(model.anomaly) or through LSTMFleet.predict + FFFleet.score_outputs")
         topo = plans[0][1].model.topology
         if any(p[1].model.topology.key() != topo.key() for p in plans):
             raise ValueError("models of one FleetAnomalyServer must share a topology")

@@ -318,3 +318,72 @@ def test_fleet_anomaly_result_response_methods_without_a_device():
     pd.testing.assert_frame_equal(back, frame, check_freq=False)
     d = res.to_dict(0)
     assert set(d["model-input"]) == {"a", "b", "c"} and len(d["total-anomaly-scaled"]["total-anomaly-scaled"]) == 10
+
+
+REFERENCE_SERIALIZABILITY_CONFIGS = ["""
+    gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector:
+        base_estimator:
+            sklearn.pipeline.Pipeline:
+                steps:
+                - sklearn.preprocessing.MinMaxScaler
+                - gordo.machine.model.models.KerasAutoEncoder:
+                    kind: feedforward_hourglass
+""", """
+    gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector:
+        base_estimator:
+            gordo.machine.model.models.KerasAutoEncoder:
+                kind: feedforward_hourglass
+""", """
+    gordo.machine.model.anomaly.diff.DiffBasedKFCVAnomalyDetector:
+        base_estimator:
+            sklearn.compose.TransformedTargetRegressor:
+                transformer:
+                    sklearn.preprocessing.MinMaxScaler
+                regressor:
+                    sklearn.pipeline.Pipeline:
+                        steps:
+                        - sklearn.preprocessing.MinMaxScaler
+                        - gordo.machine.model.models.KerasAutoEncoder:
+                            kind: feedforward_hourglass
+                            batch_size: 128
+                            compression_factor: 0.5
+                            encoding_layers: 1
+                            func: tanh
+                            out_func: linear
+                            optimizer: Adam
+                            loss: mse
+                            epochs: 1000
+                            validation_split: 0.1
+                            callbacks:
+                                - tensorflow.keras.callbacks.EarlyStopping:
+                                    monitor: val_loss
+                                    patience: 10
+                                    restore_best_weights: true
+        scaler: sklearn.preprocessing.MinMaxScaler
+        window: 144
+        shuffle: true
+        threshold_percentile: 0.975
+"""]
+
+
+@pytest.mark.parametrize("config", REFERENCE_SERIALIZABILITY_CONFIGS)
+def test_reference_detector_configs_are_serializable(config):
+    """The unmodified YAMLs of tests/gordo/machine/model/anomaly/test_anomaly_detectors.py:480-552 (incl. the
+    TransformedTargetRegressor + EarlyStopping K-fold config): from_definition with the gordo -> gordo_b200 redirect,
+    into_definition and back, pickle round trip -- "should play well with the gordo serializer"."""
+    import pickle
+    import yaml
+    from gordo_b200 import serializer
+    from gordo_b200.machine.model.anomaly.diff import DiffBasedAnomalyDetector
+    model = serializer.from_definition(yaml.safe_load(config), redirect_gordo=True)
+    assert isinstance(model, DiffBasedAnomalyDetector)
+    definition = serializer.into_definition(model)
+    again = serializer.from_definition(definition)
+    assert type(again) is type(model) and again.get_params().keys() == model.get_params().keys()
+    clone = pickle.loads(pickle.dumps(model))
+    assert type(clone) is type(model)
+    if "KFCV" in config:
+        assert model.threshold_percentile == 0.975 and model.window == 144 and model.shuffle is True
+        est = model.base_estimator.regressor.steps[1][1]
+        assert est.kwargs["epochs"] == 1000 and est.kwargs["callbacks"][0] == {
+            "tensorflow.keras.callbacks.EarlyStopping": {"monitor": "val_loss", "patience": 10, "restore_best_weights": True}}

@@ -441,3 +441,75 @@ def test_fleet_anomaly_server_with_separate_targets():
         with pytest.raises(ValueError):
             srv.anomaly(Xh)                                       # y cannot default to X when the widths differ
         srv.close()
+
+
+@pytest.mark.gpu
+def test_kfcv_detector_over_transformed_target_regressor():
+    """The reference's third serializability config (test_anomaly_detectors.py:508-538) run, not just parsed:
+    DiffBasedKFCVAnomalyDetector over TransformedTargetRegressor(MinMaxScaler, Pipeline[MinMaxScaler, KerasAutoEncoder
+    with validation_split + EarlyStopping]).  This composition has no fused route (the target transformer sits outside
+    the Pipeline), so it exercises the generic sklearn path through the GPU estimator: K-fold cross_validate, fit,
+    anomaly() with smoothing + percentile thresholds; the estimator inside must equal a manual composition."""
+    import yaml
+    from sklearn.model_selection import KFold
+    from gordo_b200 import serializer
+    cfg = yaml.safe_load("""
+    gordo.machine.model.anomaly.diff.DiffBasedKFCVAnomalyDetector:
+        base_estimator:
+            sklearn.compose.TransformedTargetRegressor:
+                transformer:
+                    sklearn.preprocessing.MinMaxScaler
+                regressor:
+                    sklearn.pipeline.Pipeline:
+                        steps:
+                        - sklearn.preprocessing.MinMaxScaler
+                        - gordo.machine.model.models.KerasAutoEncoder:
+                            kind: feedforward_hourglass
+                            batch_size: 128
+                            compression_factor: 0.5
+                            encoding_layers: 1
+                            func: tanh
+                            out_func: linear
+                            optimizer: Adam
+                            loss: mse
+                            epochs: 12
+                            validation_split: 0.1
+                            callbacks:
+                                - tensorflow.keras.callbacks.EarlyStopping:
+                                    monitor: val_loss
+                                    patience: 3
+                                    restore_best_weights: true
+        scaler: sklearn.preprocessing.MinMaxScaler
+        window: 24
+        shuffle: true
+        threshold_percentile: 0.975
+    """)
+    rng = np.random.default_rng(5)
+    t = np.arange(1500)[:, None]
+    X = pd.DataFrame((np.sin(t / 50.0 + np.arange(6)) * np.arange(1, 7) + 0.05 * rng.standard_normal((1500, 6))).astype(np.float32),
+                     index=pd.date_range("2020-01-01", periods=1500, freq="10min", tz="UTC"), columns=[f"tag-{i}" for i in range(6)])
+    torch.manual_seed(0); np.random.seed(0)
+    model = serializer.from_definition(cfg, redirect_gordo=True)
+    cv = model.cross_validate(X=X, y=X, cv=KFold(n_splits=3, shuffle=True, random_state=0))
+    assert len(cv["estimator"]) == 3
+    assert np.isfinite(model.aggregate_threshold_) and model.aggregate_threshold_ > 0
+    assert np.asarray(model.feature_thresholds_).shape == (6,) and np.isfinite(np.asarray(model.feature_thresholds_)).all()
+    model.fit(X, X)
+    est = model.base_estimator.regressor_.steps[1][1]
+    hist = est.get_metadata()["history"]
+    assert "val_loss" in hist and 1 <= len(hist["loss"]) <= 12 and hist["loss"][-1] < hist["loss"][0]
+    frame = model.anomaly(X, X)
+    assert {"model-input", "model-output", "tag-anomaly-scaled", "tag-anomaly-unscaled", "total-anomaly-scaled",
+            "total-anomaly-unscaled", "smooth-tag-anomaly-scaled", "smooth-total-anomaly-scaled",
+            "anomaly-confidence", "total-anomaly-confidence"} <= set(frame.columns.get_level_values(0))
+    # the TransformedTargetRegressor inverts the target scaling: model-output lives in the units of y and is the
+    # manual composition of the fitted parts
+    inner = model.base_estimator
+    manual = inner.transformer_.inverse_transform(inner.regressor_.predict(X))
+    np.testing.assert_allclose(frame["model-output"].to_numpy(), manual, rtol=1e-5, atol=1e-5)
+    err = np.abs(frame["model-output"].to_numpy() - X.to_numpy())
+    np.testing.assert_allclose(frame["tag-anomaly-unscaled"].to_numpy(), err, rtol=1e-5, atol=1e-6)
+    assert float(np.mean(err)) < 0.5 * float(np.mean(np.abs(X.to_numpy())))      # it learned the signal
+    conf = frame["total-anomaly-confidence"].to_numpy().ravel()
+    want = frame["smooth-total-anomaly-scaled"].to_numpy().ravel() / model.aggregate_threshold_
+    np.testing.assert_allclose(conf[~np.isnan(want)], want[~np.isnan(want)], rtol=1e-5)
