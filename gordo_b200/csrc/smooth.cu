@@ -9,13 +9,16 @@
 // Smoothing: one thread owns (column, run of S consecutive output rows) and slides its window over
 // the run after warming up on the w-1 rows in front of it; threads of a warp sit on adjacent columns,
 // so a row step of a warp is one contiguous read and one contiguous write.  The moving median keeps
-// the window SORTED in shared memory ([w][threads], conflict-free) and replaces the outgoing value
-// by the incoming one with a single shift pass.  Mean / EWMA carry their state in float64 registers,
-// in the recurrences pandas uses.  Quantile: one CTA per (job, 8 adjacent columns), three-pass radix
-// select (11+11+10 bits of the order-preserving integer image of the float) + one pass for the next order statistic.
+// the window as a ring of integer keys in shared memory and tracks the rank-k element with one uniform
+// pass per output (smm_rank_kernel below; the round-1 sorted-window version stays selectable with
+// GB200_SMM=legacy).  Mean / EWMA carry their state in float64 registers, in the recurrences pandas
+// uses.  NaN and +-inf are missing values for all three, as pandas' `_prep_values` makes them.
+// Quantile: coalesced whole-row reads, 4 x 8-bit radix select passes over global histograms (further down;
+// the round-1 one-CTA-per-8-columns kernel stays selectable with GB200_QUANTILE=legacy).
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -100,7 +103,7 @@ __global__ void smooth_kernel(const __grid_constant__ SmoothArgs a) {
         for (int64_t r = h0; r < o1; ++r) {
             const float x_new = nx, x_old = ox;
             if (r + 1 < o1) { nx = v[(r + 1) * C]; ox = (r + 1 - w >= h0) ? v[(r + 1 - w) * C] : NAN; }
-            const bool vo = x_old == x_old, vn = x_new == x_new;
+            const bool vo = fabsf(x_old) < INFINITY, vn = fabsf(x_new) < INFINITY;   // pandas: NaN and +-inf are missing
             if (vo && vn) sw.replace(x_old, x_new);
             else { if (vo) sw.remove(x_old); if (vn) sw.insert(x_new); }
             if (r >= o0) {
@@ -115,20 +118,25 @@ __global__ void smooth_kernel(const __grid_constant__ SmoothArgs a) {
         const double inv_w = 1.0 / (double)w;
         for (int64_t r = h0; r < o1; ++r) {
             const float x_new = v[r * C];
-            if (x_new == x_new) { sum += (double)x_new; ++nobs; }
-            if (r - w >= h0) { const float x_old = v[(r - w) * C]; if (x_old == x_old) { sum -= (double)x_old; --nobs; } }
+            if (fabsf(x_new) < INFINITY) { sum += (double)x_new; ++nobs; }
+            if (r - w >= h0) { const float x_old = v[(r - w) * C]; if (fabsf(x_old) < INFINITY) { sum -= (double)x_old; --nobs; } }
             if (r >= o0) out[r * C] = nobs == w ? (float)(sum * inv_w) : NAN;
         }
     } else {
         // pandas ewm(span=w, adjust=True, ignore_na=False).mean(): avg <- (old_wt*avg + x)/(old_wt + 1)
         // with old_wt decayed by (1 - alpha) at every row; the history before h0 carries a relative
         // weight below 2^-64 and is dropped
+        // ... counted from the LAST OBSERVED row in front of the run: missing rows carry the average forward unchanged,
+        // so behind a gap longer than the halo the state is whatever the rows before the gap left
         const double decay = 1.0 - a.alpha;
         double avg = NAN, old_wt = 1.0;
-        for (int64_t r = h0; r < o1; ++r) {
+        int64_t last = o0 - 1;
+        while (last >= j0 && !(fabsf(v[last * C]) < INFINITY)) --last;
+        const int64_t e0 = last < j0 ? o0 : max(j0, last - (int64_t)a.halo);
+        for (int64_t r = e0; r < o1; ++r) {
             const float x = v[r * C];
-            const bool obs = x == x;
-            if (r > h0) {
+            const bool obs = fabsf(x) < INFINITY;
+            if (r > e0) {
                 if (avg == avg) {
                     old_wt *= decay;
                     if (obs) {
@@ -152,6 +160,142 @@ __device__ __forceinline__ uint32_t f2key(float x) {
 }
 __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ---------------------------------------------------------------- moving median, rank-tracking version
+// The sorted-window kernel above pays two binary searches (dependent shared-memory loads) and a shift whose length
+// differs per lane -- a warp waits for its slowest lane, ~0.85 w moves on white noise -- per output: 87 ms for the
+// c2-sized matrix at w = 144.  This version keeps the window as an UNSORTED ring of order-preserving integer keys and
+// tracks the median itself: when one value leaves and one enters, every rank moves by at most one, so with
+// r = the previous element of rank k (k = w / 2)
+//      new rank-k element   is one of { pred(r), r, succ(r) },
+//      new rank-(k-1) one   is one of { second largest below r, pred(r), r }            (even windows only),
+// decided by cL = #{x < r} and E = #{x == r}.  One pass over the ring per output -- the same trip count in every lane,
+// 128-bit conflict-free loads, no dependent addressing -- yields pred / second pred / succ and E:
+//      u = key - r (mod 2^32): the keys below r are exactly the ones with u >= 2^32 - r, in key order, so max u = pred
+//      v = r - key (mod 2^32): the keys above r are exactly the ones with v >  r, reversed,            so max v = succ
+//      E = w - sum min(u, 1)
+// cL needs no pass: it is kept up to date from the two values that moved; after r moves DOWN the count below the new r
+// is unknown (its multiplicity is) but the count above is exact (w - old cL), and the other way round after a move UP,
+// so whichever count is known is carried and the other one follows from E after the next pass.  Ties, signed zeros
+// and +-inf (pandas turns them into missing values before any rolling function, window/rolling.py `_prep_values`)
+// therefore cost nothing extra.  A window that held a missing value is re-selected from scratch when the last one
+// leaves (<= k + 1 passes walking up from below the minimum).
+constexpr uint32_t SMM_MISSING = 0xffffffffu;        // the key of a negative-NaN bit pattern: no stored value has it
+
+template <bool EVEN>
+struct RingScan {
+    uint32_t p1 = 0, p2 = 0, s1 = 0, z = 0;
+    __device__ __forceinline__ void add(uint32_t key, uint32_t r) {
+        const uint32_t u = key - r, v = r - key;
+        if (EVEN) p2 = max(p2, min(p1, u));
+        p1 = max(p1, u);
+        s1 = max(s1, v);
+        // min through asm: left to itself the compiler turns `z += min(u, 1)` into a compare, an add and a predicated
+        // move instead of one VIMNMX and a share of an IADD3.  (The loop is bound by the ALU pipe -- 5 min/max/add3 per
+        // key for even windows, 3.5 for odd ones, 80 % busy in profiles/r2h -- but counting through the multiplier,
+        // #{u != 0} = sum(u) - sum(hi32(u * (2^32 - 1))), was slower: IMAD.HI costs more than the VIMNMX it frees.)
+        uint32_t nz;
+        asm("min.u32 %0, %1, 1;" : "=r"(nz) : "r"(u));
+        z += nz;
+    }
+    // ring: this thread's first quad; quads are nt apart
+    __device__ __forceinline__ void run(const uint4* ring, int nt, int w, uint32_t r) {
+        const int nq = w >> 2;
+        #pragma unroll 2
+        for (int q = 0; q < nq; ++q) {
+            const uint4 k4 = ring[(size_t)q * nt];
+            add(k4.x, r); add(k4.y, r); add(k4.z, r); add(k4.w, r);
+        }
+        const int rem = w & 3;
+        if (rem) {
+            const uint4 k4 = ring[(size_t)nq * nt];
+            add(k4.x, r);
+            if (rem > 1) add(k4.y, r);
+            if (rem > 2) add(k4.z, r);
+        }
+    }
+};
+
+template <bool EVEN>
+__global__ void __launch_bounds__(384, 1) smm_rank_kernel(const __grid_constant__ SmoothArgs a) {
+    extern __shared__ uint4 s_ring[];                      // [ceil(w / 4)][threads] quads of keys
+    const int nt = blockDim.x, tid = threadIdx.x;
+    const int job = blockIdx.y;
+    const int c0 = blockIdx.z * nt;
+    const int Cc = min(a.C - c0, nt);
+    const int nsub = nt / Cc;
+    const int sub = tid / Cc, col = c0 + tid - sub * Cc;
+    if (sub >= nsub) return;
+    const int64_t j0 = a.lo[job], j1 = a.hi[job];
+    const int64_t o0 = j0 + ((int64_t)blockIdx.x * nsub + sub) * a.S;
+    const int64_t o1 = min(o0 + (int64_t)a.S, j1);
+    if (o0 >= o1) return;
+    const int64_t h0 = max(j0, o0 - (int64_t)a.halo);
+    const int C = a.C, w = a.window, k = w >> 1;
+    const float* v = a.v + col;
+    float* out = a.out + col;
+    const uint4* ring = s_ring + tid;
+    uint32_t* words = reinterpret_cast<uint32_t*>(s_ring + tid);            // word (i) at words[(i >> 2) * nt * 4 + (i & 3)]
+
+    int pos = 0, n_in = 0, n_missing = 0;
+    bool valid = false, known_lo = true;
+    uint32_t r = 0;                 // key of the current rank-k element
+    int cL = 0, cG = 0;             // #{key < r}, #{key > r}: the one `known_lo` names is exact between passes
+    float nx = v[h0 * C];
+    for (int64_t row = h0; row < o1; ++row) {
+        const float x = nx;
+        if (row + 1 < o1) nx = v[(row + 1) * C];
+        const bool present = fabsf(x) < INFINITY;          // false for NaN and +-inf
+        const uint32_t kn = present ? f2key(x) : SMM_MISSING;
+        uint32_t* slot = words + (size_t)(pos >> 2) * nt * 4 + (pos & 3);
+        const uint32_t ko = *slot;
+        *slot = kn;
+        pos = pos + 1 == w ? 0 : pos + 1;
+        if (n_in == w) n_missing -= (ko == SMM_MISSING); else ++n_in;
+        n_missing += !present;
+        float m = NAN;
+        if (n_in == w) {
+            if (n_missing == 0) {
+                RingScan<EVEN> sc;
+                int E;
+                uint32_t hi, lo;
+                if (!valid) {
+                    r = 0; cL = 0;
+                    for (;;) {
+                        sc = RingScan<EVEN>();
+                        sc.run(ring, nt, w, r);
+                        E = w - (int)sc.z;
+                        if (cL + E > k) break;
+                        cL += E; r -= sc.s1;
+                    }
+                    cG = w - cL - E;
+                    hi = r; lo = cL <= k - 1 ? r : r + sc.p1;
+                    valid = true; known_lo = true;
+                } else {
+                    if (known_lo) cL += (int)(kn < r) - (int)(ko < r);
+                    else          cG += (int)(kn > r) - (int)(ko > r);
+                    sc.run(ring, nt, w, r);
+                    E = w - (int)sc.z;
+                    if (known_lo) cG = w - cL - E; else cL = w - cG - E;
+                    if (cL > k) {                               // rank k slid below r
+                        hi = r + sc.p1; lo = r + sc.p2;
+                        cG = w - cL; known_lo = false; r = hi;
+                    } else if (cL + E <= k) {                   // ... above r
+                        hi = r - sc.s1; lo = E > 0 ? r : r + sc.p1;
+                        cL += E; known_lo = true; r = hi;
+                    } else {
+                        hi = r; lo = cL <= k - 1 ? r : r + sc.p1;
+                        known_lo = true;
+                    }
+                }
+                m = EVEN ? (float)(0.5 * ((double)key2f(lo) + (double)key2f(hi))) : key2f(hi);
+            } else {
+                valid = false;
+            }
+        }
+        if (row >= o0) out[row * C] = m;
+    }
 }
 
 // One CTA = one job x QC adjacent columns: a row's QC values share one or two 32-byte sectors, so the
@@ -298,7 +442,18 @@ int gb_launch_smooth(int n_jobs, const int64_t* lo, const int64_t* hi, const flo
     a.lo = lo; a.hi = hi; a.v = v; a.out = out; a.C = n_cols; a.window = window; a.method = method;
     int nt = 256;
     size_t smem = 0;
-    if (method == GB200_SMOOTH_SMM) {
+    static const bool legacy_smm = [] { const char* e = getenv("GB200_SMM"); return e && !strcmp(e, "legacy"); }();
+    const bool rank_smm = method == GB200_SMOOTH_SMM && !legacy_smm;
+    if (rank_smm) {
+        // ring of ceil(w / 4) key quads per thread; as many threads as the shared memory of one SM holds
+        const size_t per_thread = (size_t)((window + 3) / 4) * sizeof(uint4);
+        nt = 384;
+        while (nt > 32 && (size_t)nt * per_thread > GB_SMEM_OPTIN_MAX) nt -= 32;
+        GB_REQUIRE((size_t)nt * per_thread <= GB_SMEM_OPTIN_MAX, "smooth: moving-median window %d too long (max %d)",
+                   window, (int)(GB_SMEM_OPTIN_MAX / (32 * sizeof(uint4)) * 4));
+        smem = (size_t)nt * per_thread;
+        a.halo = window - 1;
+    } else if (method == GB200_SMOOTH_SMM) {
         // the sorted windows of a block live in shared memory: fewer threads for long windows
         const size_t cap = 200 * 1024;
         while (nt > 32 && (size_t)nt * window * sizeof(float) > cap) nt >>= 1;
@@ -314,14 +469,39 @@ int gb_launch_smooth(int n_jobs, const int64_t* lo, const int64_t* hi, const flo
         const double need = ceil(64.0 * log(2.0) / -log1p(-a.alpha));
         a.halo = need > 1e9 ? 1000000000 : (int)need;
     }
-    // rows per thread: long enough to amortise the warm-up, short enough to fill the GPU
+    // rows per thread: long enough to amortise the warm-up (and, for the rank-tracking median, the selection from
+    // scratch at the first full window: up to w / 2 + 1 passes), short enough to fill the GPU
     int S = a.halo > 512 ? a.halo : 512;
     const int Cc = n_cols < nt ? n_cols : nt;
     const int nsub = nt / Cc;
-    while (S > 64 && S / 2 >= a.halo && ((max_rows + S - 1) / S) * (int64_t)n_jobs * n_cols < 148LL * 2048) S >>= 1;
+    if (rank_smm) {
+        // one CTA per SM and a per-run overhead of halo + ~w/2 selection passes: pick the number of CTAs per job
+        // (j = 1, 2, ...; S = the rows that leaves per thread) that minimises waves x (S + overhead).  With S fixed
+        // at 2048 the c2-sized matrix made 896 CTAs = 6.05 waves of 148.
+        const int64_t zb = (n_cols + nt - 1) / nt, overhead = a.halo + window / 2 + 1;
+        int64_t best = -1;
+        for (int64_t j = 1; j <= 4096; ++j) {
+            const int64_t Sj = (max_rows + nsub * j - 1) / (nsub * j);
+            const int64_t waves = (n_jobs * j * zb + 147) / 148;
+            const int64_t cost = waves * (Sj + overhead);
+            if (best < 0 || cost < best) { best = cost; S = (int)Sj; }
+            if (Sj <= 32) break;
+        }
+    } else {
+        while (S > 64 && S / 2 >= a.halo && ((max_rows + S - 1) / S) * (int64_t)n_jobs * n_cols < 148LL * 2048) S >>= 1;
+    }
     a.S = S;
     const int64_t rows_per_block = (int64_t)nsub * S;
     dim3 grid((unsigned)((max_rows + rows_per_block - 1) / rows_per_block), n_jobs, (n_cols + nt - 1) / nt);
+    if (rank_smm) {
+        auto launch = [&](auto kern) -> int {
+            if (smem > 48 * 1024) GB_CUDA_CHECK(gb_allow_max_smem(kern));
+            kern<<<grid, nt, smem, stream>>>(a);
+            GB_CUDA_CHECK(cudaGetLastError());
+            return GB_OK;
+        };
+        return (window & 1) ? launch(smm_rank_kernel<false>) : launch(smm_rank_kernel<true>);
+    }
     if (smem > 48 * 1024)
         GB_CUDA_CHECK(gb_allow_max_smem(smooth_kernel));
     smooth_kernel<<<grid, nt, smem, stream>>>(a);

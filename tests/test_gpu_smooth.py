@@ -190,3 +190,32 @@ def test_smooth_columns_match_real_reference_golden(ci):
     for grp in case["groups"]:
         np.testing.assert_allclose(frame[grp].to_numpy(float), D[pre + "col_" + grp].reshape(frame[grp].shape),
                                    rtol=5e-6, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("window", [3, 8, 144, 145])
+def test_moving_median_rank_tracking_edge_cases(window):
+    """The rank-tracking moving median (one ring pass per output) on the inputs that stress its bookkeeping: heavy ties
+    (a handful of distinct values, signed zeros), bursts of missing values that force a re-selection, +-inf (pandas
+    turns them into missing values for every rolling / ewm function), runs long enough to cross several thread runs."""
+    from gordo_b200.fleet import FFFleet
+    rng = np.random.default_rng(window)
+    n, c = 40_000, 9
+    V = rng.standard_normal((n, c)).astype(np.float32)
+    V[:, 1] = rng.integers(-2, 3, n)                       # five distinct values
+    V[:, 2] = np.where(rng.random(n) < 0.5, 0.0, -0.0)     # signed zeros only
+    V[:, 3] = 1.25                                         # constant
+    V[:, 4] = np.where(rng.random(n) < 0.01, np.nan, rng.integers(0, 3, n))
+    V[rng.integers(0, n, 40), 5] = np.inf
+    V[rng.integers(0, n, 40), 5] = -np.inf
+    V[5000:5400, 6] = np.nan                               # a burst longer than the window
+    V[:, 7] = np.sort(V[:, 7])                             # monotone: the median moves every step, same direction
+    V[:, 8] = -np.sort(V[:, 8])
+    lo, hi = [0, 25_000], [25_000, n]
+    for method in ("smm", "sma", "ewma"):
+        got = FFFleet.smooth(torch.from_numpy(V).to(DEV), _i64(lo), _i64(hi), method, window).cpu().numpy()
+        for a, b in zip(lo, hi):
+            want = smoothing(V[a:b], method, window)
+            if method == "smm":
+                np.testing.assert_array_equal(got[a:b], want.astype(np.float32))
+            else:
+                np.testing.assert_allclose(got[a:b], want, rtol=2e-6, atol=1e-6, equal_nan=True)
