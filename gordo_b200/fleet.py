@@ -370,12 +370,6 @@ class FFFleet:
     def predict(self, sched: Schedule, x: torch.Tensor, precision: str = "f32") -> torch.Tensor:
         return self.score(sched, x, precision=precision, columns=("model-output",))["model-output"]
 
-    def host_pipeline(self, sched: Schedule, n_chunks: int = 8, precision: str = "bf16", columns=SCORE_COLUMNS,
-                      machines: Optional[int] = None):
-        """Pinned-host-in / pinned-host-out scoring over two streams (see host_pipeline.HostPipeline)."""
-        from .host_pipeline import HostPipeline
-        return HostPipeline(self, sched, n_chunks, precision, columns, machines)
-
     # ------------------------------------------------------------------ training
     def fit_jobs(self, x: torch.Tensor, y: Optional[torch.Tensor], rows_lo: torch.Tensor, rows_hi: torch.Tensor,
                  params: torch.Tensor, *, in_scale=None, in_min=None, scale_slot=None,
