@@ -63,6 +63,11 @@ SIGNATURES = {
     "gb200_score_outputs": (C.c_int, [_I32, _P, _P, _I32] + [_P] * 12),
     "gb200_host_expand_columns": (C.c_int, [_I32, _P, _I32] + [_P] * 7 + [_I32]),
     "gb200_host_stream_seconds": (C.c_double, [_P, _P, _I64, _I32, _I32]),
+    "gb200_resample": (C.c_int, [_I32] + [_P] * 7 + [_I64, _I32, _I64, _I64, _I64, _P, _P]),
+    "gb200_interpolate": (C.c_int, [_I32, _P, _P, _P, _I32, _I64, _P, _P]),
+    "gb200_filter_rows": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _I64, C.POINTER(_I32), C.POINTER(_I32), _I32,
+                                    C.POINTER(C.c_double), _I32, _I32, _P, _P]),
+    "gb200_compact_rows": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

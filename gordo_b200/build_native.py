@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libgordo_b200.so")
-SOURCES = ["abi.cu", "ff_score_f32.cu", "ff_score_tc.cu", "ff_fit.cu", "misc.cu", "smooth.cu", "lstm.cu", "lstm_tc.cu", "host_cols.cu"]
+SOURCES = ["abi.cu", "ff_score_f32.cu", "ff_score_tc.cu", "ff_fit.cu", "misc.cu", "smooth.cu", "lstm.cu", "lstm_tc.cu", "host_cols.cu", "dataset.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

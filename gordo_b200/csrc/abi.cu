@@ -245,4 +245,42 @@ int gb200_score_outputs(int32_t n_machines, const int64_t* out_row_off, const in
                                    conf, total_conf, (cudaStream_t)stream);
 }
 
+int gb200_resample(int32_t n_series, const int64_t* point_off, const int64_t* ts_ns, const double* values,
+                   const int64_t* bin0_ns, const int64_t* n_bins, const int64_t* out_off, const int64_t* out_stride,
+                   int64_t step_ns, int32_t agg, int64_t max_bins, int64_t n_points_total, int64_t total_bins,
+                   double* out, void* stream) {
+    GB_REQUIRE(n_series >= 0, "bad n_series");
+    GB_REQUIRE(n_series == 0 || (point_off && ts_ns && values && bin0_ns && n_bins && out_off && out_stride && out), "NULL argument");
+    return gb_launch_resample(n_series, point_off, ts_ns, values, bin0_ns, n_bins, out_off, out_stride, step_ns, agg,
+                              max_bins, n_points_total, total_bins, out, (cudaStream_t)stream);
+}
+
+int gb200_interpolate(int32_t n_series, const int64_t* n_bins, const int64_t* off, const int64_t* stride,
+                      int32_t method, int64_t limit, double* data, void* stream) {
+    GB_REQUIRE(n_series >= 0, "bad n_series");
+    GB_REQUIRE(n_series == 0 || (n_bins && off && stride && data), "NULL argument");
+    return gb_launch_interpolate(n_series, n_bins, off, stride, method, limit, data, (cudaStream_t)stream);
+}
+
+int gb200_filter_rows(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const double* data,
+                      int32_t n_cols, const int64_t* row_ts_ns, int64_t ts_base_ns,
+                      const int32_t* ops_host, const int32_t* args_host, int32_t n_ops,
+                      const double* consts_host, int32_t n_consts, int32_t buffer_size, uint8_t* keep, void* stream) {
+    GB_REQUIRE(n_jobs >= 0 && n_cols >= 1, "bad n_jobs / n_cols");
+    GB_REQUIRE(rows_lo && rows_hi && data && ops_host && args_host && keep, "NULL argument");
+    GB_REQUIRE(n_consts == 0 || consts_host, "NULL constants");
+    return gb_launch_filter_rows(n_jobs, rows_lo, rows_hi, data, n_cols, row_ts_ns, ts_base_ns, ops_host, args_host, n_ops,
+                                 consts_host, n_consts, buffer_size, keep, (cudaStream_t)stream);
+}
+
+int gb200_compact_rows(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const double* data,
+                       int32_t n_cols, const int64_t* row_ts_ns, const uint8_t* keep, double* out, float* out_f32,
+                       int64_t* out_ts, int64_t* new_rows_lo, int64_t* new_rows_hi, void* stream) {
+    GB_REQUIRE(n_jobs >= 0 && n_cols >= 1, "bad n_jobs / n_cols");
+    GB_REQUIRE(rows_lo && rows_hi && data && keep && out && new_rows_lo && new_rows_hi, "NULL argument");
+    GB_REQUIRE(!out_ts || row_ts_ns, "out_ts needs row_ts_ns");
+    return gb_launch_compact_rows(n_jobs, rows_lo, rows_hi, data, n_cols, row_ts_ns, keep, out, out_f32, out_ts,
+                                  new_rows_lo, new_rows_hi, (cudaStream_t)stream);
+}
+
 }  // extern "C"

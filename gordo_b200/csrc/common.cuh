@@ -116,6 +116,18 @@ int gb_launch_smooth(int n_jobs, const int64_t* lo, const int64_t* hi, const flo
                      int method, int window, float* out, cudaStream_t stream);
 int gb_launch_quantile(int n_jobs, const int64_t* lo, const int64_t* hi, const float* v, int n_cols,
                        double q, double* out, cudaStream_t stream);
+int gb_launch_resample(int n_series, const int64_t* point_off, const int64_t* ts, const double* val,
+                       const int64_t* bin0, const int64_t* n_bins, const int64_t* out_off, const int64_t* out_stride,
+                       int64_t step, int agg, int64_t max_bins, int64_t n_points, int64_t total_bins, double* out,
+                       cudaStream_t stream);
+int gb_launch_interpolate(int n_series, const int64_t* n_bins, const int64_t* off, const int64_t* stride, int method,
+                          int64_t limit, double* data, cudaStream_t stream);
+int gb_launch_filter_rows(int n_jobs, const int64_t* lo, const int64_t* hi, const double* data, int n_cols,
+                          const int64_t* ts, int64_t ts_base, const int32_t* ops, const int32_t* args, int n_ops,
+                          const double* consts, int n_consts, int buffer_size, uint8_t* keep, cudaStream_t stream);
+int gb_launch_compact_rows(int n_jobs, const int64_t* lo, const int64_t* hi, const double* data, int n_cols,
+                           const int64_t* ts, const uint8_t* keep, double* out, float* out_f32, int64_t* out_ts,
+                           int64_t* new_lo, int64_t* new_hi, cudaStream_t stream);
 int gb_launch_cv_sums(int n_jobs, const int64_t* lo, const int64_t* hi, const float* y, const float* yhat,
                       int n_tags, double* out, cudaStream_t stream);
 int64_t gb_lstm_tc_scratch_bytes(const gb200_lstm_arch* arch, int64_t max_windows);

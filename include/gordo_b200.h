@@ -268,6 +268,60 @@ int gb200_host_expand_columns(int32_t n_machines, const int64_t* row_off_host, i
 double gb200_host_stream_seconds(float* dst_host, const float* src_host, int64_t n_floats,
                                  int32_t n_threads, int32_t reps);
 
+/* ---------------------------------------------------------------------------------------------
+ * Upstream of X: the arithmetic of `dataset.get_data()` between the data provider and the matrix
+ * the builder trains on.  Reference call site: gordo/builder/build_model.py:208-213
+ * (`GordoBaseDataset.from_dict(...).get_data()`); the implementation is [3P] gordo-core 0.3.6 (not vendored):
+ * gordo_core/time_series.py `TimeSeriesDataset.join_timeseries` + `get_data`, gordo_core/filters/rows.py
+ * `pandas_filter_rows` + `apply_buffer`.  All pointers are DEVICE pointers unless named *_host.
+ *
+ * gb200_resample: pandas `series.resample(resolution, label="left").agg(method)` of n_series raw series.
+ *   Series s owns points [point_off[s], point_off[s+1]) of ts_ns (int64 ns since the epoch, ascending) / values
+ *   (float64, NaN = missing sample).  Its bin b covers [bin0_ns[s] + b*step_ns, + step_ns) for b < n_bins[s] and is
+ *   written to out[out_off[s] + b*out_stride[s]] (a column of its Machine's row-major [bins, tags] matrix).
+ *   An empty bin is NaN (0 for SUM / COUNT).  max_bins = max n_bins, n_points_total / total_bins size the launch.
+ */
+enum { GB200_AGG_MEAN = 0, GB200_AGG_MIN = 1, GB200_AGG_MAX = 2, GB200_AGG_SUM = 3, GB200_AGG_COUNT = 4,
+       GB200_AGG_FIRST = 5, GB200_AGG_LAST = 6 };
+int gb200_resample(int32_t n_series, const int64_t* point_off, const int64_t* ts_ns, const double* values,
+                   const int64_t* bin0_ns, const int64_t* n_bins, const int64_t* out_off, const int64_t* out_stride,
+                   int64_t step_ns, int32_t agg, int64_t max_bins, int64_t n_points_total, int64_t total_bins,
+                   double* out, void* stream);
+
+/* gb200_interpolate: in place, per series (same addressing as gb200_resample's output):
+ *   GB200_INTERP_LINEAR  pandas `.interpolate(limit=limit)`: linear over bin positions, forward only -- leading NaNs
+ *                        stay, the first `limit` NaNs of a gap are filled, trailing NaNs take the last value
+ *   GB200_INTERP_FFILL   pandas `.fillna(method="ffill", limit=limit)`
+ * limit < 0 = no limit. */
+enum { GB200_INTERP_NONE = 0, GB200_INTERP_LINEAR = 1, GB200_INTERP_FFILL = 2 };
+int gb200_interpolate(int32_t n_series, const int64_t* n_bins, const int64_t* off, const int64_t* stride,
+                      int32_t method, int64_t limit, double* data, void* stream);
+
+/* gb200_filter_rows: keep[r] = predicate(row r) for the rows [rows_lo[j], rows_hi[j]) of every job j of a row-major
+ * [rows_total, n_cols] float64 matrix, then every rejected row also rejects the buffer_size rows on either side of
+ * it inside its job (`apply_buffer`).  The predicate is a postfix program (ops/args/consts are HOST arrays, at most
+ * 96 operations / 48 constants / stack depth 16) compiled by the host side from `row_filter` /
+ * `known_filter_periods` (pandas DataFrame.eval subset) or one of the built-in stages:
+ *   [ALL_NOTNAN]              the dropna() after the inner join of the resampled series
+ *   [ALL_BETWEEN c]           every column inside (consts[c], consts[c+1]): the dataset's low / high thresholds
+ * GB200_OP_INDEX pushes (row_ts_ns[r] - ts_base_ns) as float64; comparisons push 1.0 / 0.0 (NaN compares false). */
+enum { GB200_OP_CONST = 0, GB200_OP_COL = 1, GB200_OP_INDEX = 2, GB200_OP_NEG = 3, GB200_OP_ABS = 4, GB200_OP_NOT = 5,
+       GB200_OP_ADD = 6, GB200_OP_SUB = 7, GB200_OP_MUL = 8, GB200_OP_DIV = 9, GB200_OP_POW = 10,
+       GB200_OP_GT = 11, GB200_OP_GE = 12, GB200_OP_LT = 13, GB200_OP_LE = 14, GB200_OP_EQ = 15, GB200_OP_NE = 16,
+       GB200_OP_AND = 17, GB200_OP_OR = 18, GB200_OP_ALL_FINITE = 19, GB200_OP_ALL_NOTNAN = 20, GB200_OP_ALL_BETWEEN = 21 };
+int gb200_filter_rows(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const double* data,
+                      int32_t n_cols, const int64_t* row_ts_ns, int64_t ts_base_ns,
+                      const int32_t* ops_host, const int32_t* args_host, int32_t n_ops,
+                      const double* consts_host, int32_t n_consts, int32_t buffer_size, uint8_t* keep, void* stream);
+
+/* gb200_compact_rows: what `df[mask]` leaves -- the kept rows of every job packed back to back in job order.
+ * out [<= rows_total, n_cols] float64, out_f32 the same as float32 (the dtype the model consumes; may be NULL),
+ * out_ts the kept rows' timestamps (may be NULL with row_ts_ns), new_rows_lo / new_rows_hi [n_jobs] each job's rows
+ * in the packed matrices. */
+int gb200_compact_rows(int32_t n_jobs, const int64_t* rows_lo, const int64_t* rows_hi, const double* data,
+                       int32_t n_cols, const int64_t* row_ts_ns, const uint8_t* keep, double* out, float* out_f32,
+                       int64_t* out_ts, int64_t* new_rows_lo, int64_t* new_rows_hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
