@@ -17,7 +17,8 @@
 //
 // Layout: a Machine's grid is a row-major [bins, tags] float64 matrix; a series is one of its columns (element offset
 // + stride), so a warp of the per-series kernels sits on adjacent columns.  Resampling: a CTA owns 256 consecutive
-// bins of one series; two binary searches bound its points, one coalesced pass over their timestamps marks where
+// bins of one series (fewer when the series are few); two CTA-wide searches bound its points, one coalesced pass over
+// their timestamps marks where
 // every bin starts (a bin edge is crossed by exactly one adjacent pair of points: no atomics), then groups of G lanes
 // (G chosen on the host from points per bin) reduce one bin each in a fixed order -- results do not depend on
 // scheduling.  Bound: HBM, 16 B per raw point (timestamp + value) + 8 B per bin.
@@ -36,35 +37,56 @@ constexpr int RS_BINS = 256;               // bins per CTA
 struct ResampleArgs {
     const int64_t* point_off; const int64_t* ts; const double* val;
     const int64_t* bin0; const int64_t* n_bins; const int64_t* out_off; const int64_t* out_stride;
-    int64_t step; int agg; int G; double* out;
+    int64_t step; int agg; int G; int bins_per_cta; double* out;
 };
 
-__device__ __forceinline__ int64_t lower_bound_ts(const int64_t* ts, int64_t lo, int64_t hi, int64_t key) {
-    while (lo < hi) {                        // first i in [lo, hi) with ts[i] >= key
-        const int64_t mid = lo + ((hi - lo) >> 1);
-        if (ts[mid] < key) lo = mid + 1; else hi = mid;
+// first i in [lo, hi) with ts[i] >= key, found by the whole CTA: every round probes blockDim.x evenly spaced samples
+// (one coalesced-ish wave of loads instead of one dependent load per halving) and keeps the stretch between the last
+// probe below the key and the first one not below it
+__device__ __forceinline__ int64_t cta_lower_bound(const int64_t* __restrict__ ts, int64_t lo, int64_t hi, int64_t key,
+                                                   int64_t* s_lo, int64_t* s_hi) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    while (hi - lo > nt) {
+        const int64_t span = hi - lo, chunk = (span + nt - 1) / nt;
+        const int64_t p = lo + (int64_t)tid * chunk;                       // probe positions lo, lo+chunk, ...
+        const bool below = p < hi && ts[p] < key;
+        const int64_t pn = p + chunk;
+        const bool next_below = pn < hi && ts[pn] < key;
+        __syncthreads();
+        if (tid == 0 && !below) { *s_lo = lo; *s_hi = lo; }               // ts[lo] >= key: the answer is lo
+        if (below && !next_below) { *s_lo = p + 1; *s_hi = min(pn, hi); }   // exactly one thread sees the crossing
+        __syncthreads();
+        lo = *s_lo; hi = *s_hi;
     }
-    return lo;
+    // final stretch (<= nt candidates): each thread tests one, the smallest index that is not below wins
+    __syncthreads();
+    if (tid == 0) *s_lo = hi;
+    __syncthreads();
+    const int64_t p = lo + tid;
+    if (p < hi && ts[p] >= key && (p == lo || ts[p - 1] < key)) *s_lo = p;
+    __syncthreads();
+    return *s_lo;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_constant__ ResampleArgs a) {
     __shared__ int64_t s_start[RS_BINS + 1];
-    __shared__ int64_t s_range[2];
+    __shared__ int64_t s_range[4];
     const int s = blockIdx.y, tid = threadIdx.x;
     const int64_t nb = a.n_bins[s];
-    const int64_t b0 = (int64_t)blockIdx.x * RS_BINS;
+    const int bpc = a.bins_per_cta;
+    const int64_t b0 = (int64_t)blockIdx.x * bpc;
     if (b0 >= nb) return;
-    const int nbl = (int)min((int64_t)RS_BINS, nb - b0);
+    const int nbl = (int)min((int64_t)bpc, nb - b0);
     const int64_t p0 = a.point_off[s], p1 = a.point_off[s + 1];
     const int64_t edge0 = a.bin0[s] + b0 * a.step;
-    if (tid < 2) s_range[tid] = lower_bound_ts(a.ts, p0, p1, edge0 + (tid ? (int64_t)nbl * a.step : 0));
-    __syncthreads();
-    const int64_t P0 = s_range[0], P1 = s_range[1];
+    const int64_t P0 = cta_lower_bound(a.ts, p0, p1, edge0, &s_range[0], &s_range[1]);
+    const int64_t P1 = cta_lower_bound(a.ts, P0, p1, edge0 + (int64_t)nbl * a.step, &s_range[2], &s_range[3]);
     for (int q = tid; q <= nbl; q += RS_THREADS) s_start[q] = P1;
     __syncthreads();
     // where every bin starts: point i opens all bins in (bin(i-1), bin(i)].  The bin of a point through a reciprocal
-    // multiply and one correction step (offsets inside a CTA's 256 bins are exact in float64); a 64-bit division per
-    // point would make this pass compute-bound
+    // multiply and one correction step (offsets inside a CTA's bins are exact in float64); a 64-bit division per
+    // point would make this pass compute-bound.  Four timestamps per thread are loaded before any of them is used
+    // (one 2 KB request per warp at a time leaves HBM idle); the previous point's timestamp comes from the lane below.
     const double inv_step = 1.0 / (double)a.step;
     auto bin_of = [&](int64_t t) -> int {
         const int64_t dt = t - edge0;
@@ -73,14 +95,26 @@ __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_const
         if (rem < 0) --q; else if (rem >= a.step) ++q;
         return q;
     };
-    // (four independent loads in flight per thread: one 2 KB request per warp and iteration leaves HBM idle)
     const int64_t* __restrict__ tsp = a.ts;
-    #pragma unroll 4
-    for (int64_t i = P0 + tid; i < P1; i += RS_THREADS) {
-        const int64_t t1 = tsp[i], t0 = i == P0 ? 0 : tsp[i - 1];
-        const int bl = bin_of(t1);
-        const int prev = i == P0 ? -1 : bin_of(t0);
-        for (int q = prev + 1; q <= bl; ++q) s_start[q] = i;
+    const int lane = tid & 31;
+    for (int64_t base = P0; base < P1; base += 4 * RS_THREADS) {
+        int64_t t[4];
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + k * RS_THREADS + tid;
+            t[k] = i < P1 ? tsp[i] : 0;
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + k * RS_THREADS + tid;
+            int64_t tp = __shfl_up_sync(0xffffffffu, t[k], 1);
+            if (i < P1) {
+                if (lane == 0 && i > P0) tp = tsp[i - 1];
+                const int bl = bin_of(t[k]);
+                const int prev = i == P0 ? -1 : bin_of(tp);
+                for (int q = prev + 1; q <= bl; ++q) s_start[q] = i;
+            }
+        }
     }
     __syncthreads();
     const int G = a.G, lane_g = tid % G, grp = tid / G, ngrp = RS_THREADS / G;
@@ -372,7 +406,11 @@ int gb_launch_resample(int n_series, const int64_t* point_off, const int64_t* ts
     int G = 1;
     while (G < 32 && (double)G * 4.0 < per_bin) G <<= 1;
     a.G = G;
-    dim3 grid((unsigned)((max_bins + RS_BINS - 1) / RS_BINS), (unsigned)n_series);
+    // bins per CTA: 256 when that already makes several waves of CTAs, fewer (down to 16) when the series are few
+    int bpc = RS_BINS;
+    while (bpc > 16 && (int64_t)n_series * ((max_bins + bpc - 1) / bpc) < 148LL * 8 * 4) bpc >>= 1;
+    a.bins_per_cta = bpc;
+    dim3 grid((unsigned)((max_bins + bpc - 1) / bpc), (unsigned)n_series);
     resample_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
