@@ -195,3 +195,40 @@ def test_time_series_dataset_object_get_data():
     assert dsx.get_metadata()["row_count"] == len(want)
     with pytest.raises(ValueError, match="timezone"):
         ds.TimeSeriesDataset("2020-01-01", "2020-01-02", ["a"])
+
+
+def test_raw_series_to_models_to_anomaly_frames():
+    """The whole chain a project build runs (build_model.py:208-339 per Machine): raw tag series -> get_data on the GPU ->
+    FleetModelBuilder (CV + fit + thresholds) -> model.anomaly on fresh data resampled the same way."""
+    from gordo_b200.builder import FleetMachine, FleetModelBuilder
+    rng = np.random.default_rng(33)
+    start, end = pd.Timestamp("2021-05-01 00:00:00+00:00"), pd.Timestamp("2021-05-04 00:00:00+00:00")
+    model = {"gordo.machine.model.anomaly.diff.DiffBasedAnomalyDetector": {"base_estimator": {
+        "sklearn.pipeline.Pipeline": {"steps": ["sklearn.preprocessing.MinMaxScaler",
+            {"gordo.machine.model.models.KerasAutoEncoder": {"kind": "feedforward_hourglass", "epochs": 3}}]}}}}
+    raw = []
+    for m in range(3):
+        T = 4 + m
+        phase = rng.uniform(0, 6, T)
+        series = []
+        for j in range(T):
+            s = _series(rng, f"m{m}-tag{j}", start, end, 6000, nan_frac=0.01)
+            secs = (s.index.as_unit("ns").asi8 - start.value) / 1e9
+            series.append(pd.Series(np.sin(secs / 7000.0 + phase[j]) * (j + 1) + rng.normal(0, 0.05, len(s)), index=s.index, name=s.name))
+        raw.append(ds.MachineSeries(series, start, end, name=f"m{m}", row_filter=f"`m{m}-tag0` > -0.95"))
+    fleet = ds.FleetTimeSeries(DEV)
+    joined = fleet.get_data(raw, "10T", interpolation_limit="1H", low_threshold=-100, high_threshold=100)
+    machines = []
+    for mc, jm in zip(raw, joined):
+        want = ods.get_data(mc.series, mc.start, mc.end, resolution="10T", interpolation_limit="1H", row_filter=mc.row_filter,
+                            low_threshold=-100, high_threshold=100)
+        X = jm.frame()
+        _same(X, want)
+        assert 300 < len(X) <= 433
+        machines.append(FleetMachine(mc.name, X.astype(np.float32), model=model, evaluation={"seed": 5}))
+    built = FleetModelBuilder.build_fleet(machines, streams=2)
+    assert [mach.name for _, mach in built] == ["m0", "m1", "m2"]
+    for (det, mach), mc in zip(built, machines):
+        frame = det.anomaly(mc.X, mc.X, frequency=pd.Timedelta("10min"))
+        assert len(frame) == len(mc.X) and np.isfinite(frame["total-anomaly-confidence"].to_numpy()).all()
+        assert mach.build_metadata["model"]["cross_validation"]["scores"]["r2-score"]["fold-mean"] is not None
