@@ -510,5 +510,7 @@ def test_kfcv_detector_over_transformed_target_regressor():
     err = np.abs(frame["model-output"].to_numpy() - X.to_numpy())
     np.testing.assert_allclose(frame["tag-anomaly-unscaled"].to_numpy(), err, rtol=1e-5, atol=1e-6)
     conf = frame["total-anomaly-confidence"].to_numpy().ravel()
-    want = frame["smooth-total-anomaly-scaled"].to_numpy().ravel() / model.aggregate_threshold_
-    np.testing.assert_allclose(conf[~np.isnan(want)], want[~np.isnan(want)], rtol=1e-5)
+    want = frame["total-anomaly-scaled"].to_numpy().ravel() / model.aggregate_threshold_      # diff.py:436-441: not the smoothed one
+    np.testing.assert_allclose(conf, want, rtol=1e-5)
+    assert np.isnan(frame["smooth-total-anomaly-scaled"].to_numpy()[:23]).all() and \
+        np.isfinite(frame["smooth-total-anomaly-scaled"].to_numpy()[23:]).all()               # rolling(24).median()

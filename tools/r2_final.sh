@@ -7,7 +7,7 @@ T=${1:-r2z}
 ( timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | grep -v Warning | tail -12 ) > gpurun_out/${T}_pytest.log
 ( timeout 900 python bench.py ) > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 ( timeout 400 python bench.py --impl reference ) > gpurun_out/${T}_ref.json 2> gpurun_out/${T}_ref.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ff_fit_kernel -c 1 -f -o gpurun_out/prof_r2_ff_fit python tools/bench_build.py --machines 37 --rows 12800 --cpu-rows 2000 > gpurun_out/prof_r2_ff_fit.log 2>&1
+[ -n "$SKIP_NCU" ] || timeout 600 ncu --set full --clock-control none --import-source on -k regex:ff_fit_kernel -c 1 -f -o gpurun_out/prof_r2_ff_fit python tools/bench_build.py --machines 37 --rows 12800 --cpu-rows 2000 > gpurun_out/prof_r2_ff_fit.log 2>&1
 if [ -f gpurun_out/prof_r2_ff_fit.ncu-rep ]; then
   ncu -i gpurun_out/prof_r2_ff_fit.ncu-rep --page raw --csv > gpurun_out/prof_r2_ff_fit_raw.csv 2>/dev/null
   ncu -i gpurun_out/prof_r2_ff_fit.ncu-rep --page details > gpurun_out/prof_r2_ff_fit_details.txt 2>/dev/null
@@ -21,4 +21,4 @@ for k,v in l.get("other_configs",{}).items(): print(" ", k, {kk: v[kk] for kk in
 print(" other_precisions", l.get("other_precisions"))
 r=json.loads(open("gpurun_out/${T}_ref.json").read().strip().splitlines()[-1]); print("ref", r["value"], r["cpu_baseline"]["cores"], r["cpu_baseline"]["parallel_efficiency"])
 PY
-tail -3 gpurun_out/${T}_bench.err; grep -h "Duration\|Issue Slots Busy\|Registers Per" gpurun_out/prof_r2_ff_fit_details.txt | head -4
+tail -3 gpurun_out/${T}_bench.err; [ -n "$SKIP_NCU" ] || grep -h "Duration\|Issue Slots Busy\|Registers Per" gpurun_out/prof_r2_ff_fit_details.txt | head -4
