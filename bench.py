@@ -819,6 +819,74 @@ def run_request(ctx, rounds=100):
     return out
 
 
+def run_upstream(ctx, machines=8, tags=50, seconds=43_200, resolution="10T"):
+    """
+    Upstream of X (build_model.py:208-213 -> gordo-core `TimeSeriesDataset.join_timeseries`): raw
+    one-second tag series of a small fleet -> resampled, interpolated, joined grids.  `join_call`: host pandas Series in,
+    device matrices out (staging + H2D + kernels); `resample_kernel`: the dominant kernel alone on resident samples,
+    against the HBM roofline at 16 B per raw point; `cpu_baseline`: the pandas path of the oracle on one Machine.
+    """
+    import pandas as pd
+    from gordo_b200 import dataset as gbd, _native as N
+    from oracle import dataset as odataset
+    torch = ctx.torch
+    start = pd.Timestamp("2022-01-01 00:00:00+00:00"); end = start + pd.Timedelta(seconds=seconds)
+    idx = pd.date_range(start, periods=seconds, freq="s")
+    rng = np.random.default_rng(SEED0)
+    fleet_in = [gbd.MachineSeries([pd.Series(rng.normal(j, 1, seconds), index=idx, name=f"m{m}-t{j}") for j in range(tags)], start, end)
+                for m in range(machines)]
+    n_points = machines * tags * seconds
+    fleet = gbd.FleetTimeSeries(str(ctx.dev))
+    walls = []
+    for _ in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        joined = fleet.join(fleet_in, resolution)
+        torch.cuda.synchronize(); walls.append(time.perf_counter() - t0)
+    wall = float(np.median(walls[1:]))
+    out = {"shape": f"{machines} Machines x {tags} tags x {seconds} one-second samples -> {resolution} bins",
+           "join_call": {"value": n_points / wall, "unit": "points/s", "s": wall, "rows_out": int(sum(len(j) for j in joined)),
+                         "api": "gordo_b200.dataset.FleetTimeSeries.join (host Series in, device grids out)",
+                         "h2d_bytes": 16 * n_points}}
+    dev = ctx.dev
+    step = gbd._step_ns(resolution)
+    S = machines * tags
+    t = torch.as_tensor(np.tile(idx.as_unit("ns").asi8, S), device=dev)
+    v = torch.randn(S * seconds, dtype=torch.float64, device=dev)
+    poff = torch.arange(S + 1, device=dev, dtype=torch.int64) * seconds
+    nb = seconds * 10 ** 9 // step + 1
+    bin0 = torch.full((S,), int(start.value), dtype=torch.int64, device=dev)
+    nbins = torch.full((S,), nb, dtype=torch.int64, device=dev)
+    ar = torch.arange(S, device=dev, dtype=torch.int64)
+    off = (ar // tags) * (nb * tags) + ar % tags
+    stride = torch.full((S,), tags, dtype=torch.int64, device=dev)
+    res = torch.empty(S * nb, dtype=torch.float64, device=dev)
+
+    def launch():
+        N.check(N.lib().gb200_resample(S, N.ptr(poff), N.ptr(t), N.ptr(v), N.ptr(bin0), N.ptr(nbins), N.ptr(off), N.ptr(stride),
+                                       step, 0, nb, S * seconds, S * nb, N.ptr(res), torch.cuda.current_stream().cuda_stream),
+                "gb200_resample")
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        launch()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    peak = float(ctx.peaks.get("hbm_gbs", 6650.0))
+    ach = (16.0 * n_points + 8.0 * S * nb) / (ms * 1e-3) / 1e9
+    out["resample_kernel"] = {"ms": ms, "value": n_points / (ms * 1e-3), "unit": "points/s",
+                              "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                           "traffic": None, "bytes": "16 B per raw point (timestamp + value) + 8 B per bin",
+                                           "note": "inputs (280-560 MB) exceed L2; 10 back-to-back launches"}}
+    t0 = time.perf_counter()
+    odataset.join_timeseries(fleet_in[0].series, start, end, resolution)
+    out["cpu_baseline"] = {"value": tags * seconds / (time.perf_counter() - t0), "unit": "points/s", "cores": 1, "kind": "port",
+                           "sample": "oracle/dataset.py join_timeseries (the pandas calls gordo-core makes) on Machine 0"}
+    return out
+
+
 def run_ours(args):
     ctx = Ctx(args)
     name = args.config
@@ -862,6 +930,10 @@ def run_ours(args):
                 mine["request"] = run_request(ctx)
             except Exception as e:
                 mine["request"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                mine["upstream"] = run_upstream(ctx)
+            except Exception as e:
+                mine["upstream"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         ctx.collective = True
         gathered = [mine]
         if ctx.world > 1:
@@ -887,6 +959,8 @@ def run_ours(args):
                 extras[other] = e
             if "request" in gathered[0]:
                 extras["request_latency"] = gathered[0]["request"]
+            if "upstream" in gathered[0]:
+                extras["upstream_of_x"] = gathered[0]["upstream"]
     if ctx.rank == 0:
         line.pop("_raw", None)
         if extras:

@@ -37,7 +37,7 @@ constexpr int RS_BINS = 256;               // bins per CTA
 struct ResampleArgs {
     const int64_t* point_off; const int64_t* ts; const double* val;
     const int64_t* bin0; const int64_t* n_bins; const int64_t* out_off; const int64_t* out_stride;
-    int64_t step; int agg; int G; int bins_per_cta; double* out;
+    int64_t step; uint64_t inv_step; int agg; int G; int bins_per_cta; double* out;
 };
 
 // first i in [lo, hi) with ts[i] >= key, found by the whole CTA: every round probes blockDim.x evenly spaced samples
@@ -68,6 +68,7 @@ __device__ __forceinline__ int64_t cta_lower_bound(const int64_t* __restrict__ t
     return *s_lo;
 }
 
+template <int AGG>
 __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_constant__ ResampleArgs a) {
     __shared__ int64_t s_start[RS_BINS + 1];
     __shared__ int64_t s_range[4];
@@ -83,17 +84,17 @@ __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_const
     const int64_t P1 = cta_lower_bound(a.ts, P0, p1, edge0 + (int64_t)nbl * a.step, &s_range[2], &s_range[3]);
     for (int q = tid; q <= nbl; q += RS_THREADS) s_start[q] = P1;
     __syncthreads();
-    // where every bin starts: point i opens all bins in (bin(i-1), bin(i)].  The bin of a point through a reciprocal
-    // multiply and one correction step (offsets inside a CTA's bins are exact in float64); a 64-bit division per
-    // point would make this pass compute-bound.  Four timestamps per thread are loaded before any of them is used
-    // (one 2 KB request per warp at a time leaves HBM idle); the previous point's timestamp comes from the lane below.
-    const double inv_step = 1.0 / (double)a.step;
+    // where every bin starts: point i opens all bins in (bin(i-1), bin(i)].  The bin of a point through a multiply-high
+    // by a precomputed reciprocal and one correction step: a 64-bit division (or the float64 conversions of a
+    // floating reciprocal: the first version issued 70 % of its slots at 33 % of the HBM peak, profiles/r2l) per point
+    // makes this pass instruction-bound.  Four timestamps per thread are loaded before any of them is used (one 2 KB
+    // request per warp at a time leaves HBM idle); the previous point's bin comes from the lane below.
+    const uint64_t inv = a.inv_step;                   // floor(2^64 / step): the high word of dt * inv is the bin or one less
     auto bin_of = [&](int64_t t) -> int {
-        const int64_t dt = t - edge0;
-        int q = (int)((double)dt * inv_step);
-        const int64_t rem = dt - (int64_t)q * a.step;
-        if (rem < 0) --q; else if (rem >= a.step) ++q;
-        return q;
+        const uint64_t dt = (uint64_t)(t - edge0);
+        uint64_t q = __umul64hi(dt, inv);
+        if (dt - q * (uint64_t)a.step >= (uint64_t)a.step) ++q;
+        return (int)q;
     };
     const int64_t* __restrict__ tsp = a.ts;
     const int lane = tid & 31;
@@ -107,11 +108,11 @@ __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_const
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int64_t i = base + k * RS_THREADS + tid;
-            int64_t tp = __shfl_up_sync(0xffffffffu, t[k], 1);
+            const int bl = i < P1 ? bin_of(t[k]) : 0;
+            int prev = __shfl_up_sync(0xffffffffu, bl, 1);
             if (i < P1) {
-                if (lane == 0 && i > P0) tp = tsp[i - 1];
-                const int bl = bin_of(t[k]);
-                const int prev = i == P0 ? -1 : bin_of(tp);
+                if (i == P0) prev = -1;
+                else if (lane == 0) prev = bin_of(tsp[i - 1]);
                 for (int q = prev + 1; q <= bl; ++q) s_start[q] = i;
             }
         }
@@ -124,46 +125,49 @@ __global__ void __launch_bounds__(RS_THREADS) resample_kernel(const __grid_const
         const int q = q0 + grp;
         const bool live = q < nbl;
         const int64_t lo = live ? s_start[q] : 0, hi = live ? s_start[q + 1] : 0;
+        // only what the aggregation needs is accumulated (AGG is a template parameter)
+        constexpr bool W_SUM = AGG == GB200_AGG_MEAN || AGG == GB200_AGG_SUM, W_CNT = AGG == GB200_AGG_MEAN || AGG == GB200_AGG_COUNT ||
+                       AGG == GB200_AGG_MIN || AGG == GB200_AGG_MAX;
+        constexpr bool W_MIN = AGG == GB200_AGG_MIN, W_MAX = AGG == GB200_AGG_MAX, W_FIRST = AGG == GB200_AGG_FIRST, W_LAST = AGG == GB200_AGG_LAST;
         double sum = 0.0, mn = INFINITY, mx = -INFINITY, fv = NAN, lv = NAN;
         long long cnt = 0, fi = LLONG_MAX, li = -1;
+        auto take = [&](double v, int64_t ik) {
+            if (v == v) {
+                if (W_SUM) sum += v;
+                if (W_CNT) ++cnt;
+                if (W_MIN) mn = fmin(mn, v);
+                if (W_MAX) mx = fmax(mx, v);
+                if (W_FIRST && ik < fi) { fi = ik; fv = v; }
+                if (W_LAST && ik > li) { li = ik; lv = v; }
+            }
+        };
         const double* __restrict__ vp = a.val;
         int64_t i = lo + lane_g;
         for (; i + 3 * (int64_t)G < hi; i += 4 * (int64_t)G) {      // same order as one at a time, four loads in flight
             const double v4[4] = {vp[i], vp[i + G], vp[i + 2 * (int64_t)G], vp[i + 3 * (int64_t)G]};
             #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double v = v4[k];
-                if (v == v) {
-                    const int64_t ik = i + k * (int64_t)G;
-                    sum += v; ++cnt; mn = fmin(mn, v); mx = fmax(mx, v);
-                    if (ik < fi) { fi = ik; fv = v; }
-                    if (ik > li) { li = ik; lv = v; }
-                }
-            }
+            for (int k = 0; k < 4; ++k) take(v4[k], i + k * (int64_t)G);
         }
-        for (; i < hi; i += G) {
-            const double v = vp[i];
-            if (v == v) {
-                sum += v; ++cnt; mn = fmin(mn, v); mx = fmax(mx, v);
-                if (i < fi) { fi = i; fv = v; }
-                if (i > li) { li = i; lv = v; }
-            }
-        }
+        for (; i < hi; i += G) take(vp[i], i);
         // butterfly inside the group (G is a power of two, groups are aligned inside a warp): both partners of an
         // exchange compute the same sum, so every lane ends with the same bits and the order depends on G only
         for (int o = 1; o < G; o <<= 1) {
-            const double s2 = __shfl_xor_sync(0xffffffffu, sum, o), mn2 = __shfl_xor_sync(0xffffffffu, mn, o);
-            const double mx2 = __shfl_xor_sync(0xffffffffu, mx, o), fv2 = __shfl_xor_sync(0xffffffffu, fv, o);
-            const double lv2 = __shfl_xor_sync(0xffffffffu, lv, o);
-            const long long c2 = __shfl_xor_sync(0xffffffffu, cnt, o), fi2 = __shfl_xor_sync(0xffffffffu, fi, o);
-            const long long li2 = __shfl_xor_sync(0xffffffffu, li, o);
-            sum += s2; cnt += c2; mn = fmin(mn, mn2); mx = fmax(mx, mx2);
-            if (fi2 < fi) { fi = fi2; fv = fv2; }
-            if (li2 > li) { li = li2; lv = lv2; }
+            if (W_SUM) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (W_CNT) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (W_MIN) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (W_MAX) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (W_FIRST) {
+                const double fv2 = __shfl_xor_sync(0xffffffffu, fv, o); const long long fi2 = __shfl_xor_sync(0xffffffffu, fi, o);
+                if (fi2 < fi) { fi = fi2; fv = fv2; }
+            }
+            if (W_LAST) {
+                const double lv2 = __shfl_xor_sync(0xffffffffu, lv, o); const long long li2 = __shfl_xor_sync(0xffffffffu, li, o);
+                if (li2 > li) { li = li2; lv = lv2; }
+            }
         }
         if (live && lane_g == 0) {
             double r;
-            switch (a.agg) {
+            switch (AGG) {
                 case GB200_AGG_MEAN:  r = cnt ? sum / (double)cnt : NAN; break;
                 case GB200_AGG_MIN:   r = cnt ? mn : NAN; break;
                 case GB200_AGG_MAX:   r = cnt ? mx : NAN; break;
@@ -411,7 +415,16 @@ int gb_launch_resample(int n_series, const int64_t* point_off, const int64_t* ts
     while (bpc > 16 && (int64_t)n_series * ((max_bins + bpc - 1) / bpc) < 148LL * 8 * 4) bpc >>= 1;
     a.bins_per_cta = bpc;
     dim3 grid((unsigned)((max_bins + bpc - 1) / bpc), (unsigned)n_series);
-    resample_kernel<<<grid, RS_THREADS, 0, stream>>>(a);
+    a.inv_step = step == 1 ? ~0ull : (uint64_t)((((unsigned __int128)1) << 64) / (unsigned __int128)step);   // floor(2^64 / step)
+    switch (agg) {
+        case GB200_AGG_MEAN:  resample_kernel<GB200_AGG_MEAN><<<grid, RS_THREADS, 0, stream>>>(a); break;
+        case GB200_AGG_MIN:   resample_kernel<GB200_AGG_MIN><<<grid, RS_THREADS, 0, stream>>>(a); break;
+        case GB200_AGG_MAX:   resample_kernel<GB200_AGG_MAX><<<grid, RS_THREADS, 0, stream>>>(a); break;
+        case GB200_AGG_SUM:   resample_kernel<GB200_AGG_SUM><<<grid, RS_THREADS, 0, stream>>>(a); break;
+        case GB200_AGG_COUNT: resample_kernel<GB200_AGG_COUNT><<<grid, RS_THREADS, 0, stream>>>(a); break;
+        case GB200_AGG_FIRST: resample_kernel<GB200_AGG_FIRST><<<grid, RS_THREADS, 0, stream>>>(a); break;
+        default:              resample_kernel<GB200_AGG_LAST><<<grid, RS_THREADS, 0, stream>>>(a); break;
+    }
     GB_CUDA_CHECK(cudaGetLastError());
     return GB_OK;
 }
