@@ -501,13 +501,14 @@ class FleetTimeSeries:
             return [getattr(mc, attr, None) if getattr(mc, attr, None) is not None else fleet_value for mc in machines]
 
         states = {id(jm._group): jm._group for jm in joined}
+        position = {id(jm): i for i, jm in enumerate(joined)}
         for stage_values in (per_machine("known_filter_periods", known_filter_periods), per_machine("row_filter", row_filter)):
             for state in states.values():
                 members = [jm for jm in joined if jm._group is state]
                 base = int(state["ts"].min().item()) if state["ts"].numel() else 0
                 by_prog: Dict[RowProgram, List[int]] = {}
                 for jm in members:
-                    f = stage_values[joined.index(jm)]
+                    f = stage_values[position[id(jm)]]
                     if not f:
                         continue
                     prog = compile_row_filter(f, jm.columns, base, jm.tz)
