@@ -459,6 +459,10 @@ class FleetTimeSeries:
         dev = self.device
         data, ts, lo, hi = state["data"], state["ts"], state["lo"], state["hi"]
         R, C = data.shape
+        if R == 0:                                   # nothing left to filter (e.g. series that never overlap)
+            if state["data_f32"] is None:
+                state["data_f32"] = torch.empty((0, C), dtype=torch.float32, device=dev)
+            return
         keep = torch.ones((max(R, 1),), dtype=torch.uint8, device=dev)
         if len(jobs) and R:
             sel = torch.as_tensor(np.asarray(jobs, np.int64), device=dev)

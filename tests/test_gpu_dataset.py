@@ -232,3 +232,18 @@ def test_raw_series_to_models_to_anomaly_frames():
         frame = det.anomaly(mc.X, mc.X, frequency=pd.Timedelta("10min"))
         assert len(frame) == len(mc.X) and np.isfinite(frame["total-anomaly-confidence"].to_numpy()).all()
         assert mach.build_metadata["model"]["cross_validation"]["scores"]["r2-score"]["fold-mean"] is not None
+
+
+def test_join_of_series_that_never_overlap_is_empty():
+    """One tag only has samples in the first hour, the other only in the last: every row of the inner join holds a
+    NaN (interpolation limit 1 bin), so the frame is empty -- as with pandas -- and get_data raises InsufficientDataError."""
+    start, end = pd.Timestamp("2020-01-01 00:00:00+00:00"), pd.Timestamp("2020-01-01 12:00:00+00:00")
+    a = pd.Series([1.0, 2.0], index=[start + pd.Timedelta("5min"), start + pd.Timedelta("25min")], name="a")
+    b = pd.Series([3.0, 4.0], index=[end - pd.Timedelta("45min"), end - pd.Timedelta("5min")], name="b")
+    want = ods.join_timeseries([a, b], start, end, "10T", interpolation_limit="10T")
+    got = ds.join_timeseries([a, b], start, end, "10T", interpolation_limit="10T", device=DEV)
+    assert len(want) == 0 and len(got) == 0 and list(got.columns) == ["a", "b"]
+    with pytest.raises(ds.InsufficientDataError):
+        ds.get_data([a, b], start, end, "10T", interpolation_limit="10T", device=DEV)
+    empty = pd.DataFrame({"a": []}, index=pd.DatetimeIndex([], tz="UTC"))
+    assert len(ds.pandas_filter_rows(empty, "a > 1", device=DEV)) == 0
