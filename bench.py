@@ -819,7 +819,7 @@ def run_request(ctx, rounds=100):
     return out
 
 
-def run_upstream(ctx, machines=8, tags=50, seconds=43_200, resolution="10T"):
+def run_upstream(ctx, machines=16, tags=50, seconds=86_400, resolution="10T"):
     """
     Upstream of X (build_model.py:208-213 -> gordo-core `TimeSeriesDataset.join_timeseries`): raw
     one-second tag series of a small fleet -> resampled, interpolated, joined grids.  `join_call`: host pandas Series in,
@@ -879,7 +879,7 @@ def run_upstream(ctx, machines=8, tags=50, seconds=43_200, resolution="10T"):
     out["resample_kernel"] = {"ms": ms, "value": n_points / (ms * 1e-3), "unit": "points/s",
                               "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                            "traffic": None, "bytes": "16 B per raw point (timestamp + value) + 8 B per bin",
-                                           "note": "inputs (280-560 MB) exceed L2; 10 back-to-back launches"}}
+                                           "note": "inputs (1.1 GB) exceed L2; 10 back-to-back launches"}}
     t0 = time.perf_counter()
     odataset.join_timeseries(fleet_in[0].series, start, end, resolution)
     out["cpu_baseline"] = {"value": tags * seconds / (time.perf_counter() - t0), "unit": "points/s", "cores": 1, "kind": "port",
