@@ -310,14 +310,14 @@ class FleetTimeSeries:
         self.device = torch.device(device)
         N.lib()
         from .hostbind import effective_cpus
-        self.host_threads = host_threads or max(1, min(8, effective_cpus()))
+        self.host_threads = host_threads or max(1, min(16, effective_cpus()))
         self._staging: Dict[str, Any] = {}
         self._staging_events: Dict[str, Any] = {}
 
     # ------------------------------------------------------------------ raw samples -> device
     def _upload(self, name: str, parts: Sequence[np.ndarray], point_off: Sequence[int], dtype):
         """The series' arrays copied side by side into a pinned staging buffer (kept and reused between calls; filled
-        by a few threads: numpy copies release the GIL) and from there to the device in one asynchronous copy."""
+        by a few threads: numpy copies release the GIL) and from there to the device, slice by slice, asynchronously."""
         torch = _torch()
         n = int(point_off[-1])
         if name in self._staging_events:
@@ -327,6 +327,7 @@ class FleetTimeSeries:
             stage = torch.empty((max(n, 1),), dtype=dtype, pin_memory=True)
             self._staging[name] = stage
         host = stage.numpy()
+        dev_t = torch.empty((max(n, 1),), dtype=dtype, device=self.device)
 
         def fill(k0, k1):
             for k in range(k0, k1):
@@ -335,13 +336,20 @@ class FleetTimeSeries:
         workers = max(1, min(self.host_threads, len(parts)))
         if workers == 1 or n < (1 << 22):
             fill(0, len(parts))
+            dev_t[:n].copy_(stage[:n], non_blocking=True)
         else:
+            # a few slices of series: while the DMA engine moves slice c, the threads fill slice c + 1
             from concurrent.futures import ThreadPoolExecutor
-            cuts = np.linspace(0, len(parts), workers + 1).astype(int)
+            n_slices = 4
+            bounds = np.searchsorted(np.asarray(point_off), np.linspace(0, n, n_slices + 1)[1:-1]).tolist()
+            slices = sorted(set([0] + [int(b) for b in bounds] + [len(parts)]))
             with ThreadPoolExecutor(max_workers=workers) as pool:
-                list(pool.map(lambda ab: fill(*ab), zip(cuts[:-1], cuts[1:])))
-        dev_t = torch.empty((max(n, 1),), dtype=dtype, device=self.device)
-        dev_t[:n].copy_(stage[:n], non_blocking=True)
+                for s0, s1 in zip(slices[:-1], slices[1:]):
+                    cuts = np.linspace(s0, s1, workers + 1).astype(int)
+                    list(pool.map(lambda ab: fill(*ab), zip(cuts[:-1], cuts[1:])))
+                    a, b = int(point_off[s0]), int(point_off[s1])
+                    if b > a:
+                        dev_t[a:b].copy_(stage[a:b], non_blocking=True)
         self._staging_events[name] = torch.cuda.Event(); self._staging_events[name].record()
         return dev_t[:n] if n else dev_t[:0]
 
@@ -548,7 +556,7 @@ def pandas_filter_rows(df: pd.DataFrame, filter_str: Union[str, Sequence[str]], 
     ts_host = idx.as_unit("ns").asi8 if isinstance(idx, pd.DatetimeIndex) else np.arange(len(df), dtype=np.int64)
     base = int(ts_host.min()) if len(df) else 0
     prog = compile_row_filter(filter_str, list(df.columns), base, tz)
-    data = torch.as_tensor(np.ascontiguousarray(df.to_numpy(np.float64)), device=dev)
+    data = torch.as_tensor(np.array(df.to_numpy(np.float64), order="C", copy=True), device=dev)     # (a frame's array may be read-only)
     ts = torch.as_tensor(np.ascontiguousarray(ts_host), device=dev)
     lo = torch.zeros(1, dtype=torch.int64, device=dev); hi = torch.full((1,), len(df), dtype=torch.int64, device=dev)
     keep = torch.ones((max(len(df), 1),), dtype=torch.uint8, device=dev)
