@@ -376,3 +376,23 @@ def test_fleet_builder_batches_kfcv_detectors():
         frame = model.anomaly(mcs[m].X, mcs[m].X)
         want = det.anomaly(Xd, Xd)
         np.testing.assert_allclose(frame["total-anomaly-confidence"].to_numpy().ravel(), want["total-anomaly-confidence"], rtol=2e-2, atol=1e-5)
+
+
+def test_cv_sums_kernel_matches_the_real_reference_metrics():
+    """gb200_cv_sums -> explained variance / r2 / MSE / MAE per tag and averaged, against the values the REAL reference's
+    scorers (build_model.py:377-446, executed from /root/reference by tests/golden/make_metrics_golden.py) gave for the
+    same y and a prediction that is `offset` rows shorter."""
+    import json, os
+    import torch
+    from gordo_b200.fleet import FFFleet
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "builder_metrics_golden.json")))
+    y = np.asarray(g["y"]); yp = np.asarray(g["y_pred"]); off = g["offset"]
+    full = np.zeros_like(y); full[off:] = yp                      # row-aligned with y; rows < offset are outside the job
+    scale = 1.0 / (y.max(0) - y.min(0))                           # MinMaxScaler fitted on the full y (the scoring scaler)
+    lo = torch.tensor([off], device="cuda:0"); hi = torch.tensor([len(y)], device="cuda:0")
+    got = FFFleet.cv_scores(torch.as_tensor(y.astype(np.float32), device="cuda:0"),
+                            torch.as_tensor(full.astype(np.float32), device="cuda:0"), lo, hi, scale[None])
+    for name in ("explained-variance-score", "r2-score", "mean-squared-error", "mean-absolute-error"):
+        for j, col in enumerate(g["columns"]):
+            np.testing.assert_allclose(got[name][0, j], g["values"][f"{name}-{col.replace(' ', '-')}"], rtol=2e-5, err_msg=f"{name} {col}")
+        np.testing.assert_allclose(got[name][0].mean(), g["values"][name], rtol=2e-5, err_msg=name)

@@ -201,3 +201,32 @@ def test_kfcv_detector_against_real_reference(ci):
         if want.ndim == 2 and want.shape[1] == 1 and got.ndim == 1:
             want = want[:, 0]
         np.testing.assert_allclose(got, want, equal_nan=True, **tol)
+
+
+def test_builder_metric_scorers_match_the_real_reference():
+    """`_metrics_dict` / `metric_wrapper` (the mirror of build_model.py:377-446 and model/utils.py:18-46) against values
+    the REAL reference's `ModelBuilder.build_metrics_dict` produced (tests/golden/make_metrics_golden.py): same 20
+    scorer names (' ' -> '-'), same values, with a model whose output is shorter than y (the LSTM offset)."""
+    import json
+    import os
+    import warnings
+    import pandas as pd
+    from sklearn.base import BaseEstimator, RegressorMixin
+    from gordo_b200.builder import _metrics_dict
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "builder_metrics_golden.json")))
+    y = pd.DataFrame(np.asarray(g["y"]), columns=g["columns"])
+    y_pred = np.asarray(g["y_pred"])
+
+    class Dummy(RegressorMixin, BaseEstimator):
+        def fit(self, X, y=None):
+            return self
+
+        def predict(self, X):
+            return y_pred
+
+    scorers = _metrics_dict(y)
+    assert set(scorers) == set(g["values"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, s in scorers.items():
+            np.testing.assert_allclose(float(s(Dummy(), y, y)), g["values"][k], rtol=1e-12, err_msg=k)
