@@ -103,6 +103,24 @@ def _metrics_dict(y: pd.DataFrame, scaler="sklearn.preprocessing.MinMaxScaler"):
     return out
 
 
+def build_split_dict(X, split_obj=None, bounds=None) -> dict:
+    """ModelBuilder.build_split_dict (build_model.py:347-375): per fold the first / last index label of the train and
+    test rows and their counts.  ``split_obj``: any sklearn splitter; ``bounds``: the (train_end, test_end) pairs of a
+    TimeSeriesSplit (train = rows [0, s), test = rows [s, e)), which is what the batched build already holds."""
+    index = X.index if hasattr(X, "index") else pd.RangeIndex(len(X))
+    out: Dict[str, Any] = {}
+    if bounds is not None:
+        folds = [((0, s - 1), (s, e - 1), s, e - s) for s, e in bounds]
+    else:
+        folds = [((tr[0], tr[-1]), (te[0], te[-1]), len(tr), len(te)) for tr, te in split_obj.split(X)]
+    for i, ((a0, a1), (b0, b1), n_tr, n_te) in enumerate(folds):
+        out.update({f"fold-{i + 1}-train-start": index[a0], f"fold-{i + 1}-train-end": index[a1],
+                    f"fold-{i + 1}-test-start": index[b0], f"fold-{i + 1}-test-end": index[b1]})
+        out[f"fold-{i + 1}-n-train"] = int(n_tr)
+        out[f"fold-{i + 1}-n-test"] = int(n_te)
+    return out
+
+
 def _plain_minmax(sc) -> bool:
     return (type(sc) is MinMaxScaler and tuple(getattr(sc, "feature_range", (0, 1))) == (0, 1)
             and not getattr(sc, "clip", False))
@@ -275,7 +293,7 @@ class FleetBuild:
                 d = {"fold-mean": float(v.mean()), "fold-std": float(v.std()), "fold-max": float(v.max()), "fold-min": float(v.min())}
                 d.update({f"fold-{i + 1}": float(x) for i, x in enumerate(v)})
                 meta["cross_validation"]["scores"][name] = d
-            meta["cross_validation"]["splits"] = {f"fold-{i + 1}-n-train": int(len(tr)) for i, (tr, _) in enumerate(cv.split(X))}
+            meta["cross_validation"]["splits"] = build_split_dict(X, cv)
             meta["cv_duration_sec"] = time.time() - t0
         if cv_mode != "cross_val_only":
             t1 = time.time()
@@ -448,8 +466,7 @@ class FleetBuild:
             meta = {"name": mc.name, "model_offset": int(rows[m]) - fleet.out_rows(int(rows[m])), "model": extract_model_metadata(model),
                     "model_training_duration_sec": t_fit, "cv_duration_sec": (t_total - t_fit) if k else None,
                     "cross_validation": {"scores": scores,
-                                         "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
-                                                    enumerate(time_series_split_bounds(int(rows[m]), k))} if k else {}},
+                                         "splits": build_split_dict(mc.X, bounds=time_series_split_bounds(int(rows[m]), k)) if k else {}},
                     "fleet": {"machines_in_launch": M, "fit_jobs": J, "fit_duration_sec": t_fit,
                               "build_duration_sec": t_total},
                     "cv_fold_history": {f"fold-{i}": {"loss": [float(v) for v in hl_h[m * per + i]]} for i in range(k)}}
@@ -557,8 +574,7 @@ def _build_bucket_lstm_impl(self, mcs, protos, dev):
         # build_model.py:448-471: len(X) - len(predict(X)), from the fleet's own output-row count
         meta = {"name": mc.name, "model_offset": int(rows[m]) - trainer.out_rows(int(rows[m])), "model": extract_model_metadata(model),
                 "model_training_duration_sec": t_total, "cv_duration_sec": None,
-                "cross_validation": {"scores": {}, "splits": {f"fold-{i + 1}-n-train": int(s_) for i, (s_, _) in
-                                                              enumerate(time_series_split_bounds(int(rows[m]), k))} if k else {}},
+                "cross_validation": {"scores": {}, "splits": build_split_dict(mc.X, bounds=time_series_split_bounds(int(rows[m]), k)) if k else {}},
                 "fleet": {"machines_in_launch": M, "fit_jobs": J, "build_duration_sec": t_total}}
         out_models.append((model, meta))
     return out_models

@@ -40,8 +40,14 @@ def main():
     metrics_list = MB.metrics_from_list(None)
     scorers = MB.build_metrics_dict(metrics_list, y, scaler="sklearn.preprocessing.MinMaxScaler")
     values = {k: float(s(Dummy(), y, y)) for k, s in scorers.items()}
+    # split metadata (build_model.py:347-375) for a time-indexed frame under the builder's TimeSeriesSplit(3) and a KFold
+    from sklearn.model_selection import KFold, TimeSeriesSplit
+    Xdt = pd.DataFrame(y.to_numpy(), columns=cols, index=pd.date_range("2020-01-01", periods=n, freq="10min", tz="UTC"))
+    splits = {"tss3": {k: str(v) for k, v in MB.build_split_dict(Xdt, TimeSeriesSplit(n_splits=3)).items()},
+              "kfold4": {k: str(v) for k, v in MB.build_split_dict(Xdt, KFold(n_splits=4)).items()},
+              "tss3_rangeindex": {k: str(v) for k, v in MB.build_split_dict(y, TimeSeriesSplit(n_splits=3)).items()}}
     out = {"columns": cols, "offset": offset, "y": y.to_numpy().tolist(), "y_pred": y_pred.tolist(),
-           "metrics": [m.__name__ for m in metrics_list], "values": values}
+           "metrics": [m.__name__ for m in metrics_list], "values": values, "splits": splits}
     path = os.path.join(HERE, "builder_metrics_golden.json")
     with open(path, "w") as f:
         json.dump(out, f)

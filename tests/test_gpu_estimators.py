@@ -247,7 +247,9 @@ def test_fleet_builder_cv_scores_match_sklearn_scorers():
             np.testing.assert_allclose(got[name][0, j], want, rtol=1e-5, atol=1e-9, err_msg=f"{name} tag {j}")
     m = scores["mean-squared-error"]
     np.testing.assert_allclose(m["fold-mean"], np.mean([m["fold-1"], m["fold-2"], m["fold-3"]]))
-    assert meta["cross_validation"]["splits"] == {"fold-1-n-train": 100, "fold-2-n-train": 200, "fold-3-n-train": 300}
+    sp = meta["cross_validation"]["splits"]                        # build_model.py:347-375: 6 entries per fold
+    assert {k: sp[k] for k in sp if k.endswith("n-train")} == {"fold-1-n-train": 100, "fold-2-n-train": 200, "fold-3-n-train": 300}
+    assert sp["fold-2-n-test"] == 100 and sp["fold-3-test-end"] == 399 and sp["fold-1-train-end"] == 99 and len(sp) == 18
 
 
 def test_validation_split_val_loss_and_early_stopping():

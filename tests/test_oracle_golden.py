@@ -230,3 +230,23 @@ def test_builder_metric_scorers_match_the_real_reference():
         warnings.simplefilter("ignore")
         for k, s in scorers.items():
             np.testing.assert_allclose(float(s(Dummy(), y, y)), g["values"][k], rtol=1e-12, err_msg=k)
+
+
+def test_build_split_dict_matches_the_real_reference():
+    """Split metadata of the build (build_model.py:347-375) for TimeSeriesSplit(3) / KFold(4), time-indexed and
+    range-indexed frames, and the (train_end, test_end) form the batched build uses."""
+    import json
+    import os
+    import pandas as pd
+    from sklearn.model_selection import KFold, TimeSeriesSplit
+    from gordo_b200.builder import build_split_dict
+    from gordo_b200.fleet import time_series_split_bounds
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "builder_metrics_golden.json")))
+    y = pd.DataFrame(np.asarray(g["y"]), columns=g["columns"])
+    Xdt = y.set_axis(pd.date_range("2020-01-01", periods=len(y), freq="10min", tz="UTC"))
+    s = lambda d: {k: str(v) for k, v in d.items()}
+    assert s(build_split_dict(Xdt, TimeSeriesSplit(n_splits=3))) == g["splits"]["tss3"]
+    assert s(build_split_dict(Xdt, KFold(n_splits=4))) == g["splits"]["kfold4"]
+    assert s(build_split_dict(y, TimeSeriesSplit(n_splits=3))) == g["splits"]["tss3_rangeindex"]
+    assert s(build_split_dict(Xdt, bounds=time_series_split_bounds(len(y), 3))) == g["splits"]["tss3"]
+    assert s(build_split_dict(y.to_numpy(), bounds=time_series_split_bounds(len(y), 3))) == g["splits"]["tss3_rangeindex"]
