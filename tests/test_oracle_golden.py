@@ -250,3 +250,75 @@ def test_build_split_dict_matches_the_real_reference():
     assert s(build_split_dict(y, TimeSeriesSplit(n_splits=3))) == g["splits"]["tss3_rangeindex"]
     assert s(build_split_dict(Xdt, bounds=time_series_split_bounds(len(y), 3))) == g["splits"]["tss3"]
     assert s(build_split_dict(y.to_numpy(), bounds=time_series_split_bounds(len(y), 3))) == g["splits"]["tss3_rangeindex"]
+
+
+def _topology_cases():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "topology_golden.json")))
+
+
+@pytest.mark.parametrize("ci", range(17))
+def test_factories_build_the_topologies_the_real_reference_asks_keras_for(ci):
+    """tests/golden/make_topology_golden.py ran the reference's own factories (feedforward_autoencoder.py:15-251,
+    lstm_autoencoder.py:15-263) against recording Keras stand-ins; the mirror's factories must describe the same stack:
+    layer widths, activations, which layers carry the L1 activity regulariser and its strength, the LSTM
+    return_sequences pattern / input shapes, the output layer, Adam's configuration, the loss."""
+    from gordo_b200.machine.model import factories as F      # noqa: F401  (registers the factories)
+    from gordo_b200.machine.model.factories import feedforward_autoencoder as ffa, lstm_autoencoder as lsa
+    case = _topology_cases()["cases"][ci]
+    kw = {k: (tuple(v) if isinstance(v, list) else (dict(v) if isinstance(v, dict) else v)) for k, v in case["kwargs"].items()}
+    fn = getattr(ffa, case["factory"], None) or getattr(lsa, case["factory"])
+    loss = case["compile_kwargs"]["loss"]
+    if loss not in ("mse", "mean_squared_error"):
+        with pytest.raises(ValueError, match="not supported"):           # stated limitation: MSE only
+            fn(**kw)
+        kw.pop("compile_kwargs")
+    topo = fn(**kw)
+    layers = case["layers"]
+    opt = case["compile_kwargs"]["optimizer"]["optimizers.get"]
+    assert opt["class_name"] == "Adam"
+    want_adam = dict(lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+    for k, v in opt["config"].items():
+        want_adam["lr" if k == "learning_rate" else k] = v
+    assert topo.adam == pytest.approx(want_adam)
+    if layers[0]["kind"] == "Dense":
+        assert topo.widths == [layers[0]["input_dim"]] + [l["units"] for l in layers]
+        assert topo.acts == [l["activation"] for l in layers]
+        assert topo.l1 == pytest.approx([(l["activity_regularizer"] or {"l1": 0.0})["l1"] for l in layers])
+        assert all(l["kind"] == "Dense" for l in layers)
+    else:
+        lstm = [l for l in layers if l["kind"] == "LSTM"]
+        assert layers[-1]["kind"] == "Dense" and len(lstm) == len(layers) - 1
+        assert topo.units == [l["units"] for l in lstm] and topo.acts == [l["activation"] for l in lstm]
+        assert topo.out_func == layers[-1]["activation"] and topo.n_features_out == layers[-1]["units"]
+        assert [topo.lookback_window, topo.n_features] == lstm[0]["input_shape"]
+        # every LSTM layer returns sequences except the last one, whose last step feeds the Dense layer
+        assert [l["return_sequences"] for l in lstm] == [True] * (len(lstm) - 1) + [False]
+
+
+def test_factory_registry_matches_the_real_reference():
+    from gordo_b200.machine.model import factories as F      # noqa: F401
+    from gordo_b200.machine.model.register import register_model_builder
+    got = {t: sorted(k) for t, k in register_model_builder.factories.items()}
+    assert got == _topology_cases()["registered"]
+
+
+@pytest.mark.parametrize("ci", range(17))
+def test_oracle_factories_match_the_real_reference_topologies(ci):
+    """The checker's own topology specs (oracle/factories.py) against the same reference-derived goldens."""
+    from oracle import factories as OF
+    case = _topology_cases()["cases"][ci]
+    kw = {k: (tuple(v) if isinstance(v, list) else (dict(v) if isinstance(v, dict) else v)) for k, v in case["kwargs"].items()}
+    spec = getattr(OF, case["factory"])(**kw)
+    layers = case["layers"]
+    assert spec["loss"] in (case["compile_kwargs"]["loss"],) or {spec["loss"], case["compile_kwargs"]["loss"]} <= {"mse", "mean_squared_error"}
+    if layers[0]["kind"] == "Dense":
+        assert spec["widths"] == [layers[0]["input_dim"]] + [l["units"] for l in layers]
+        assert spec["acts"] == [l["activation"] for l in layers]
+        assert spec["l1"] == pytest.approx([(l["activity_regularizer"] or {"l1": 0.0})["l1"] for l in layers])
+    else:
+        lstm = [l for l in layers if l["kind"] == "LSTM"]
+        assert spec["units"] == [l["units"] for l in lstm] and spec["acts"] == [l["activation"] for l in lstm]
+        assert spec["out_func"] == layers[-1]["activation"] and spec["n_features_out"] == layers[-1]["units"]
+        assert [spec["lookback_window"], spec["n_features"]] == lstm[0]["input_shape"]
