@@ -18,11 +18,16 @@ What is restated (file:line are relative to the reference checkout, equinor/gord
 * ``scaler.py``     -- [3P] sklearn MinMaxScaler (examples/config.yaml:75-82, diff.py:25).
 * ``anomaly.py``    -- gordo/machine/model/anomaly/diff.py:166-458 (fit, cross_validate,
   thresholds, anomaly columns) and gordo/machine/model/utils.py:49-165 (frame layout).
+* ``dataset.py``    -- the [3P] gordo-core 0.3.6 resample / interpolate / join / row-filter arithmetic
+  behind ``dataset.get_data()`` (call site gordo/builder/build_model.py:208-213).
 
 PARITY PIN STATUS
 -----------------
 pinned     : hourglass dims (reference golden vectors, tests/gordo/machine/model/
              test_factories_utils.py:8-24 + docstrings), windowing (test_model.py:239-311),
+             the feed-forward and LSTM TOPOLOGIES (the reference's own factories executed
+             against recording Keras stand-ins: tests/golden/make_topology_golden.py ->
+             topology_golden.json, 17 argument sets + the factory registry),
              anomaly columns / thresholds / frame layout: checked against the REAL
              reference ``diff.py`` + ``model/utils.py`` imported here with TensorFlow stubbed
              (tests/golden/make_golden.py wrote tests/golden/*.npz), MinMaxScaler /
@@ -38,4 +43,6 @@ UNPINNED   : Dense / LSTM forward values, loss history, Adam trajectories: Tenso
              trajectory against ``torch.nn.Linear`` + ``torch.optim.Adam``
              (tests/test_oracle_torch_xcheck.py; Keras' epsilon placement is the one known
              difference).  Also pinned: DiffBasedKFCVAnomalyDetector (tests/golden/kfcv_golden.npz).
+             ``dataset.py`` is UNPINNED too: gordo-core is not in the reference tree (its header says so);
+             every step of it is a pandas call, which is what the GPU path is compared with.
 """
