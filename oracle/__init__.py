@@ -27,7 +27,10 @@ pinned     : hourglass dims (reference golden vectors, tests/gordo/machine/model
              test_factories_utils.py:8-24 + docstrings), windowing (test_model.py:239-311),
              the feed-forward and LSTM TOPOLOGIES (the reference's own factories executed
              against recording Keras stand-ins: tests/golden/make_topology_golden.py ->
-             topology_golden.json, 17 argument sets + the factory registry),
+             topology_golden.json, 17 argument sets + the factory registry), the LSTM TRAINING /
+             PREDICTION PROTOCOL (which windows, in which order, primer included; the reference's
+             estimator classes executed with a logging Keras model: make_protocol_golden.py),
+             the builder's CV scorers and split metadata (make_metrics_golden.py),
              anomaly columns / thresholds / frame layout: checked against the REAL
              reference ``diff.py`` + ``model/utils.py`` imported here with TensorFlow stubbed
              (tests/golden/make_golden.py wrote tests/golden/*.npz), MinMaxScaler /

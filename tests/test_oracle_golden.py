@@ -323,3 +323,76 @@ def test_oracle_factories_match_the_real_reference_topologies(ci):
         assert spec["units"] == [l["units"] for l in lstm] and spec["acts"] == [l["activation"] for l in lstm]
         assert spec["out_func"] == layers[-1]["activation"] and spec["n_features_out"] == layers[-1]["units"]
         assert [spec["lookback_window"], spec["n_features"]] == lstm[0]["input_shape"]
+
+
+# ----------------------------------------------------------------------------- training / prediction protocol
+def _protocol():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "protocol_golden.json")))
+
+
+def _numbered(n, c):
+    return np.arange(n, dtype=np.float64)[:, None] + np.arange(c)[None, :] / 100.0
+
+
+@pytest.mark.parametrize("name", ["lstm_autoencoder_lb4_bs5_ep2", "lstm_forecast_lb4_bs5", "lstm_autoencoder_defaults",
+                                  "lstm_forecast_lb1_fit_kwargs"])
+def test_oracle_lstm_fit_feeds_the_batches_the_real_reference_feeds_keras(name, monkeypatch):
+    """tests/golden/make_protocol_golden.py executed the reference's KerasLSTM*.fit / predict (models.py:557-660, 713-793)
+    with a logging Keras model: one primer step on the first window, then `fit(generator, shuffle=False)` -- epochs x
+    batches of consecutive windows -- and prediction over all windows.  The oracle's `lstm_fit` / `lstm_predict` (what
+    the GPU kernels are compared with) must train on exactly those windows, in that order."""
+    from oracle import factories as OF, lstm as olstm
+    case = next(c for c in _protocol()["cases"] if c["name"] == name)
+    primer, main, pred = case["log"]
+    kw = case["estimator_kwargs"]
+    L, bs = kw["lookback_window"], kw["batch_size"]
+    lookahead = 1 if "forecast" in name else 0
+    epochs = main["kwargs"].get("epochs", 1)
+    assert primer["kwargs"]["epochs"] == 1 and main["kwargs"]["shuffle"] is False and main["generator_batch_size"] == bs
+    assert not ({"validation_split", "batch_size"} & set(main["kwargs"]))     # only fit_generator_params reach the main fit
+    X = _numbered(case["n_rows"], case["n_cols"]).astype(np.float32)
+    spec = OF.lstm_model(case["n_cols"], lookback_window=L, encoding_dim=(3,), encoding_func=("tanh",), decoding_dim=(3,),
+                         decoding_func=("tanh",))
+    params = olstm.lstm_init(spec, np.random.default_rng(0))
+    seen = []
+    real = olstm.lstm_loss_and_grads
+
+    def spy(spec_, params_, xw, yb):
+        seen.append({"window_rows": np.rint(xw[:, :, 0]).astype(int).tolist(), "target_rows": np.rint(yb[:, 0]).astype(int).tolist()})
+        return real(spec_, params_, xw, yb)
+    monkeypatch.setattr(olstm, "lstm_loss_and_grads", spy)
+    olstm.lstm_fit(spec, params, X, X.copy(), lookback_window=L, lookahead=lookahead, batch_size=bs, epochs=epochs)
+    assert seen[0] == {"window_rows": primer["window_rows"], "target_rows": primer["target_rows"]}
+    assert seen[1:] == main["batches"]
+    # prediction: every window once, in order, 10 000 per batch; output rows = n - lookback + 1 - lookahead
+    assert pred["generator_batch_size"] == 10000 and pred["kwargs"] == {"verbose": 0}
+    starts, tgt = olstm.window_index(case["predict_rows"], L, lookahead)
+    assert [w[0] for b in pred["batches"] for w in b["window_rows"]] == starts.tolist()
+    assert [t for b in pred["batches"] for t in b["target_rows"]] == tgt.tolist()
+    assert case["predict_out_rows"] == olstm.window_count(case["predict_rows"], L, lookahead)
+
+
+def test_estimator_kwargs_routing_and_errors_match_the_real_reference():
+    """What reaches Keras from the constructor / fit kwargs of the feed-forward estimator, the kwargs the LSTM estimators
+    keep, and the two ValueErrors -- against the reference's own estimator classes run with logging stand-ins."""
+    from gordo_b200.machine.model.models import KerasAutoEncoder, KerasLSTMAutoEncoder, KerasLSTMForecast
+    g = _protocol()
+    ff = next(c for c in g["cases"] if c["name"] == "ff_autoencoder")["log"]
+    assert ff[0]["kwargs"] == {"epochs": 3, "batch_size": 16, "validation_split": 0.1, "shuffle": False, "verbose": 0}
+    assert set(ff[0]["kwargs"]) <= set(KerasAutoEncoder.supported_fit_args)
+    dflt = next(c for c in g["cases"] if c["name"] == "ff_autoencoder_defaults")["log"]
+    assert dflt[0]["kwargs"] == {"epochs": 2, "verbose": 0}                      # Keras' own defaults otherwise: batch 32, shuffle
+    for cls, name in ((KerasLSTMAutoEncoder, "lstm_autoencoder_lb4_bs5_ep2"), (KerasLSTMForecast, "lstm_forecast_lb4_bs5")):
+        want = {k: v for k, v in next(c for c in g["cases"] if c["name"] == name)["estimator_kwargs"].items()
+                if k not in ("n_features", "n_features_out")}
+        est = cls(kind="lstm_hourglass", **{k: v for k, v in want.items()})
+        assert {k: est.kwargs[k] for k in want} == want and est.lookback_window == want["lookback_window"]
+    with pytest.raises(ValueError) as e:
+        KerasAutoEncoder(kind="no_such_kind")
+    assert str(e.value) == g["errors"]["unknown_kind"]
+    assert g["errors"]["lookback_ge_rows"] == "For KerasLSTMForecast lookback_window must be < size of X"
+    import inspect
+    import gordo_b200.machine.model.models as mirror
+    assert g["errors"]["lookback_ge_rows"] in inspect.getsource(mirror)           # raised by the mirror before any device call
