@@ -398,6 +398,80 @@ class KerasAutoEncoder(KerasBaseEstimator, TransformerMixin):
         return explained_variance_score(_values(y), self.predict(X, **kwargs))
 
 
+class KerasRawModelRegressor(KerasAutoEncoder):
+    """
+    A regressor from a raw Keras config (models.py:401-460): ``kind = {"spec": {...Sequential: {layers: [...]}},
+    "compile": {...}}``.  The reference hands the spec to Keras and accepts any graph; here the subset the B200 kernels
+    run is accepted -- a ``Sequential`` of ``Dense`` layers (``units``, ``activation``, ``input_shape`` / ``input_dim``,
+    optional ``activity_regularizer`` L1), ``loss: mse`` and an Adam optimizer -- and built as a feed-forward topology;
+    anything else (other layers, SGD, kernel regularisers, ``use_bias: false``) raises NotImplementedError naming it.
+    """
+
+    _expected_keys = ("spec", "compile")
+
+    def load_kind(self, kind):
+        return kind
+
+    def __repr__(self):
+        from pprint import pformat
+        return f"{self.__class__.__name__}(kind: {pformat(self.kind)})"
+
+    @staticmethod
+    def _single(defn, what):
+        if isinstance(defn, str):
+            return defn, {}
+        if isinstance(defn, dict) and len(defn) == 1:
+            k, v = next(iter(defn.items()))
+            return k, dict(v or {})
+        raise ValueError(f"{what}: expected a class path or a one-key mapping, got {defn!r}")
+
+    def _topology(self):
+        from gordo_b200.fleet import FFTopology
+        from gordo_b200.machine.model.factories.utils import adam_from, loss_from
+        if not all(k in self.kind for k in self._expected_keys):
+            raise ValueError(f"Expected spec to have keys: {self._expected_keys}, but found {self.kind.keys()}")
+        path, body = self._single(self.kind["spec"], "spec")
+        if not path.endswith("Sequential"):
+            raise NotImplementedError(f"KerasRawModelRegressor on B200 runs Sequential models of Dense layers, not {path}")
+        widths, acts, l1 = [self.kwargs.get("n_features")], [], []
+        for i, layer in enumerate(body.get("layers", [])):
+            lpath, lkw = self._single(layer, f"layer {i}")
+            if not lpath.endswith(".Dense"):
+                raise NotImplementedError(f"layer {i} ({lpath}): only Dense layers run on the B200 feed-forward kernels")
+            lkw = dict(lkw)
+            shape = lkw.pop("input_shape", None)
+            n_in = lkw.pop("input_dim", shape[-1] if shape else None)
+            if i == 0 and n_in is not None:
+                widths[0] = int(n_in)
+            reg = lkw.pop("activity_regularizer", None)
+            strength = 0.0
+            if reg is not None:
+                rpath, rkw = self._single(reg, f"layer {i} activity_regularizer")
+                if set(rkw) - {"l1", "l"} or not (rpath.lower().endswith("l1") or rpath.endswith("L1L2")):
+                    raise NotImplementedError(f"layer {i}: activity regulariser {reg!r} (only L1 is implemented)")
+                strength = float(rkw.get("l1", rkw.get("l", 0.01)))
+            units = lkw.pop("units", None)
+            act = lkw.pop("activation", None) or "linear"
+            if units is None:
+                raise ValueError(f"layer {i}: Dense needs `units`")
+            if lkw.pop("use_bias", True) is not True:
+                raise NotImplementedError(f"layer {i}: use_bias=False")
+            lkw.pop("name", None)
+            if lkw:
+                raise NotImplementedError(f"layer {i}: Dense arguments {sorted(lkw)} are not implemented on B200")
+            widths.append(int(units)); acts.append(act); l1.append(strength)
+        if len(widths) < 2:
+            raise ValueError("the Sequential spec holds no layers")
+        if widths[0] is None:
+            raise ValueError("the first Dense layer needs input_shape / input_dim (or call fit first)")
+        compile_kw = dict(self.kind["compile"] or {})
+        loss_from(compile_kw, "mean_squared_error")
+        opath, okw = self._single(compile_kw.get("optimizer", "adam"), "compile.optimizer")
+        if opath.rpartition(".")[2].lower() != "adam":
+            raise NotImplementedError(f"optimizer {opath}: the B200 training kernel implements Adam")
+        return FFTopology(widths, acts, l1, adam_from("Adam", okw))
+
+
 class KerasLSTMBaseEstimator(KerasBaseEstimator, TransformerMixin):
     """Many-to-one LSTM autoencoder / 1-step forecast (models.py:463-698)."""
 

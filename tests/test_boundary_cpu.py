@@ -387,3 +387,93 @@ def test_reference_detector_configs_are_serializable(config):
         est = model.base_estimator.regressor.steps[1][1]
         assert est.kwargs["epochs"] == 1000 and est.kwargs["callbacks"][0] == {
             "tensorflow.keras.callbacks.EarlyStopping": {"monitor": "val_loss", "patience": 10, "restore_best_weights": True}}
+
+
+RAW_KERAS_SPECS = ["""
+        compile:
+            loss: mse
+            optimizer:
+              tensorflow.keras.optimizers.SGD:
+                learning_rate: 0.001
+        spec:
+            tensorflow.keras.models.Sequential:
+                layers:
+                    - tensorflow.keras.layers.Dense:
+                        units: 10
+                    - tensorflow.keras.layers.Dense:
+                        units: 32
+                        kernel_regularizer:
+                            tensorflow.keras.regularizers.L1L2:
+                                l1: 0.2
+                    - tensorflow.keras.layers.Dense:
+                        units: 1
+    """, """
+        compile:
+            loss: mse
+            optimizer: adam
+        spec:
+            tensorflow.keras.models.Sequential:
+                layers:
+                    - tensorflow.keras.layers.Input:
+                        shape: [9]
+                    - tensorflow.keras.layers.Reshape:
+                        target_shape: [3, 3]
+                    - tensorflow.keras.layers.LSTM:
+                        units: 12
+                    - tensorflow.keras.layers.Flatten
+                    - tensorflow.keras.layers.Dense:
+                        units: 1
+    """]
+
+
+def test_raw_keras_regressor_subset_and_its_limits():
+    """KerasRawModelRegressor (models.py:401-460; the reference's tests/gordo/machine/model/test_raw_keras.py): the
+    Dense / MSE / Adam subset becomes a feed-forward topology; the reference's two arbitrary-graph specs (SGD + kernel
+    regulariser, Reshape / LSTM / Flatten) are refused by name instead of being approximated."""
+    import yaml
+    from gordo_b200 import serializer
+    from gordo_b200.machine.model.models import KerasRawModelRegressor
+    from sklearn.pipeline import Pipeline
+    for spec_str in RAW_KERAS_SPECS:
+        est = KerasRawModelRegressor(yaml.safe_load(spec_str))
+        est.kwargs["n_features"] = 9
+        with pytest.raises(NotImplementedError):
+            est._topology()
+    config = yaml.safe_load("""
+    sklearn.pipeline.Pipeline:
+        steps:
+            - sklearn.decomposition.PCA:
+                n_components: 4
+            - gordo.machine.model.models.KerasRawModelRegressor:
+                kind:
+                    compile:
+                        loss: mse
+                        optimizer:
+                            tensorflow.keras.optimizers.Adam:
+                                learning_rate: 0.01
+                    spec:
+                        tensorflow.keras.models.Sequential:
+                            layers:
+                                - tensorflow.keras.layers.Dense:
+                                    units: 4
+                                    input_shape: [4]
+                                    activation: tanh
+                                    activity_regularizer:
+                                        tensorflow.keras.regularizers.L1:
+                                            l1: 0.001
+                                - tensorflow.keras.layers.Dense:
+                                    units: 1
+    """)
+    pipe = serializer.from_definition(config, redirect_gordo=True)
+    assert isinstance(pipe, Pipeline) and type(pipe.steps[1][1]) is KerasRawModelRegressor
+    topo = pipe.steps[1][1]._topology()
+    assert topo.widths == [4, 4, 1] and topo.acts == ["tanh", "linear"] and topo.l1 == [0.001, 0.0] and topo.adam["lr"] == 0.01
+    again = serializer.from_definition(serializer.into_definition(pipe))
+    assert again.steps[1][1].kind == pipe.steps[1][1].kind
+    with pytest.raises(ValueError, match="Expected spec to have keys"):
+        KerasRawModelRegressor({"spec": {}})._topology()
+    bare = KerasRawModelRegressor(yaml.safe_load("{compile: {loss: mse, optimizer: adam}, spec: {tensorflow.keras.models.Sequential: {layers: [{tensorflow.keras.layers.Dense: {units: 3}}]}}}"))
+    with pytest.raises(ValueError, match="input_shape"):
+        bare._topology()
+    bare.kwargs["n_features"] = 7                     # what fit() records before building the model
+    assert bare._topology().widths == [7, 3]
