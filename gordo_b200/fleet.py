@@ -335,6 +335,12 @@ class FFFleet:
             raise ValueError(f"x must be float32 [{sched.rows_total}, {self.topo.n_in}]")
         R, To = sched.rows_total, self.topo.n_out
         want = set(columns)
+        if y is None and self.topo.n_in != To:
+            # the targets cannot alias the samples here.  A pure forward pass (estimator.predict) does not need them:
+            # the kernel gets a zero target matrix and only the model output is read back
+            if not want <= {"model-output", "activity-l1"}:
+                raise ValueError("y is required when n_features_out != n_features (the error columns are |model-output - y|)")
+            y = torch.zeros((R, To), dtype=torch.float32, device=x.device)
         if self.feat_thr is None:
             want.discard("anomaly-confidence")
         if self.agg_thr is None:

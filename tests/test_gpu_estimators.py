@@ -399,43 +399,3 @@ def test_cv_sums_kernel_matches_the_real_reference_metrics():
             np.testing.assert_allclose(got[name][0, j], g["values"][f"{name}-{col.replace(' ', '-')}"], rtol=2e-5, err_msg=f"{name} {col}")
         np.testing.assert_allclose(got[name][0].mean(), g["values"][name], rtol=2e-5, err_msg=name)
 
-
-def test_raw_keras_regressor_in_a_pipeline_fits_and_matches_the_oracle():
-    """The reference's test_raw_keras_part_of_pipeline (PCA -> KerasRawModelRegressor: Dense(4) -> Dense(1), y != X), then
-    the fitted weights' forward pass against the oracle's Dense forward."""
-    import yaml
-    from gordo_b200 import serializer
-    rng = np.random.default_rng(0)
-    X, y = rng.random((100, 4)), rng.random((100, 1))
-    config = yaml.safe_load("""
-    sklearn.pipeline.Pipeline:
-        steps:
-            - sklearn.decomposition.PCA:
-                n_components: 4
-            - gordo.machine.model.models.KerasRawModelRegressor:
-                kind:
-                    compile:
-                        loss: mse
-                        optimizer: adam
-                    spec:
-                        tensorflow.keras.models.Sequential:
-                            layers:
-                                - tensorflow.keras.layers.Dense:
-                                    units: 4
-                                    input_shape: [4]
-                                    activation: tanh
-                                - tensorflow.keras.layers.Dense:
-                                    units: 1
-                epochs: 5
-    """)
-    pipe = serializer.from_definition(config, redirect_gordo=True)
-    pipe.fit(X, y)
-    out = pipe.predict(X)
-    assert out.shape == (100, 1) and np.isfinite(out).all()
-    est = pipe.steps[1][1]
-    hist = est.get_metadata()["history"]
-    assert len(hist["loss"]) == 5 and hist["loss"][-1] < hist["loss"][0]
-    spec = {"type": "ff", "widths": [4, 4, 1], "acts": ["tanh", "linear"], "l1": [0.0, 0.0]}
-    Z = pipe.steps[0][1].transform(X).astype(np.float32)
-    want = dense.ff_forward(spec, dense.ff_unflatten(est.model.params, spec["widths"]), Z)
-    np.testing.assert_allclose(out, want, rtol=0, atol=2e-5)
