@@ -46,8 +46,13 @@ def main():
     splits = {"tss3": {k: str(v) for k, v in MB.build_split_dict(Xdt, TimeSeriesSplit(n_splits=3)).items()},
               "kfold4": {k: str(v) for k, v in MB.build_split_dict(Xdt, KFold(n_splits=4)).items()},
               "tss3_rangeindex": {k: str(v) for k, v in MB.build_split_dict(y, TimeSeriesSplit(n_splits=3)).items()}}
+    # model metadata extraction (build_model.py:516-570) over nested estimators
+    sys.path.insert(0, HERE)
+    from metadata_structures import build_structures
+    GordoBase = sys.modules["gordo.machine.model.base"].GordoBase
+    extracted = {name: MB._extract_metadata_from_model(model) for name, model in build_structures(GordoBase).items()}
     out = {"columns": cols, "offset": offset, "y": y.to_numpy().tolist(), "y_pred": y_pred.tolist(),
-           "metrics": [m.__name__ for m in metrics_list], "values": values, "splits": splits}
+           "metrics": [m.__name__ for m in metrics_list], "values": values, "splits": splits, "extracted_metadata": extracted}
     path = os.path.join(HERE, "builder_metrics_golden.json")
     with open(path, "w") as f:
         json.dump(out, f)

@@ -396,3 +396,20 @@ def test_estimator_kwargs_routing_and_errors_match_the_real_reference():
     import inspect
     import gordo_b200.machine.model.models as mirror
     assert g["errors"]["lookback_ge_rows"] in inspect.getsource(mirror)           # raised by the mirror before any device call
+
+
+def test_model_metadata_extraction_matches_the_real_reference():
+    """`extract_model_metadata` against `ModelBuilder._extract_metadata_from_model` (build_model.py:516-570) run from
+    /root/reference on the same nested structures: a bare estimator, a Pipeline (only its LAST step is looked at), a
+    detector over a Pipeline / over an estimator holding another estimator / over a TransformedTargetRegressor (the
+    unfitted `regressor` attribute is skipped, the fitted clone is found), inner keys overriding outer ones."""
+    import json
+    import os
+    import sys
+    from gordo_b200.builder import extract_model_metadata
+    from gordo_b200.machine.model.base import GordoBase
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from metadata_structures import build_structures
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "builder_metrics_golden.json")))
+    got = {name: extract_model_metadata(model) for name, model in build_structures(GordoBase).items()}
+    assert got == g["extracted_metadata"]
