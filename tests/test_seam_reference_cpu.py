@@ -68,6 +68,17 @@ def test_reference_serializer_resolves_and_round_trips_the_mirror():
         lstm = ser.from_definition({"gordo_b200.machine.model.models.KerasLSTMAutoEncoder":
                                     {"kind": "lstm_hourglass", "lookback_window": 12}})
         assert lstm.lookback_window == 12 and ser.from_definition(ser.into_definition(lstm)).lookback_window == 12
+        # the raw-Keras regressor: its `kind` (a spec holding tensorflow.keras.* paths) must reach the class untouched --
+        # the reference's from_definition hands it over through the from_definition hook instead of importing the paths
+        raw = {"gordo_b200.machine.model.models.KerasRawModelRegressor": {"kind": {
+            "compile": {"loss": "mse", "optimizer": "adam"},
+            "spec": {"tensorflow.keras.models.Sequential": {"layers": [
+                {"tensorflow.keras.layers.Dense": {"units": 4, "input_shape": [4], "activation": "tanh"}},
+                {"tensorflow.keras.layers.Dense": {"units": 1}}]}}}, "epochs": 2}}
+        reg = ser.from_definition(raw)
+        assert type(reg) is m.KerasRawModelRegressor and reg.kwargs == {"epochs": 2}
+        assert reg._topology().widths == [4, 4, 1] and reg._topology().acts == ["tanh", "linear"]
+        assert ser.from_definition(ser.into_definition(reg)).kind == reg.kind
         # our own codec and the reference's agree on the same definition
         from gordo_b200 import serializer as ours
         mine = ours.from_definition(definition)
